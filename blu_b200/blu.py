@@ -1,0 +1,299 @@
+"""Host-side mirror of the reference's public surface (src/blu.rs, src/lib.rs:11-64).
+
+``BLU(m, b_nz)`` has the methods of ``impl BLU`` (blu.rs:61-334) with the same argument
+meaning; instead of ``Result<(), Status>`` every method returns the integer status
+(``Status.OK`` == ``Ok(())``), numbered as in include/blu_b200.h.
+"""
+import ctypes
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+i64p = ctypes.POINTER(ctypes.c_int64)
+f64p = ctypes.POINTER(ctypes.c_double)
+i32p = ctypes.POINTER(ctypes.c_int)
+
+
+class Status:
+    OK = 0
+    REALLOCATE = 1
+    WARNING_SINGULAR_MATRIX = 2
+    ERROR_INVALID_CALL = -2
+    ERROR_ARGUMENT_MISSING = -3
+    ERROR_INVALID_ARGUMENT = -4
+    ERROR_MAXIMUM_UPDATES = -5
+    ERROR_SINGULAR_UPDATE = -6
+    ERROR_INTERNAL = -100
+    ERROR_CUDA = -101
+    ERROR_OUT_OF_MEMORY = -102
+
+
+# selectors (include/blu_b200.h)
+P = dict(droptol=0, abstol=1, reltol=2, nzbias=3, maxsearch=4, pad=5, stretch=6, compress_thres=7,
+         sparse_thres=8, search_rows=9, realloc_factor=10, l_mem=11, u_mem=12, w_mem=13,
+         threads_per_basis=14)
+_INFO_NAMES = ["m", "rank", "bump_size", "bump_nz", "matrix_nz", "l_nz", "u_nz", "r_nz", "nsearch_pivot",
+               "nexpand", "ngarbage", "factor_flops", "min_pivot", "max_pivot", "max_eta", "nupdate",
+               "nforrest", "nfactorize", "nupdate_total", "nforrest_total", "nsymperm_total", "l_flops",
+               "u_flops", "r_flops", "condest_l", "condest_u", "norm_l", "norm_u", "normest_l_inv",
+               "normest_u_inv", "onenorm", "infnorm", "residual_test", "pivot_error", "update_cost",
+               "time_factorize", "time_solve", "time_update", "elim_bytes", "nelim_div", "pivotlen",
+               "rankdef", "internal_error", "status", "nrealloc"]
+I = {n: 100 + k for k, n in enumerate(_INFO_NAMES)}
+
+
+def library_path():
+    return os.environ.get("BLU_B200_LIB", os.path.join(_HERE, "libblu_b200.so"))
+
+
+def load_library(path=None):
+    """Load the C-ABI library.  Raises if it is missing: there is no fallback."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    path = path or library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(f"blu_b200: CUDA library not built: {path} (run __graft_entry__.build())")
+    L = ctypes.CDLL(path)
+    vp = ctypes.c_void_p
+    L.blu_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+    L.blu_destroy.argtypes = [vp]
+    L.blu_set_param.argtypes = [vp, ctypes.c_int, ctypes.c_double]
+    L.blu_get_param.argtypes = [vp, ctypes.c_int]; L.blu_get_param.restype = ctypes.c_double
+    L.blu_get_info.argtypes = [vp, ctypes.c_int]; L.blu_get_info.restype = ctypes.c_double
+    L.blu_factorize.argtypes = [vp, i64p, i64p, i64p, f64p]
+    L.blu_get_factors.argtypes = [vp, i64p, i64p, i64p, i64p, f64p, i64p, i64p, f64p]
+    L.blu_solve_dense.argtypes = [vp, f64p, f64p, ctypes.c_char]
+    L.blu_solve_sparse.argtypes = [vp, ctypes.c_int64, i64p, f64p, i64p, i64p, f64p, ctypes.c_char]
+    L.blu_solve_for_update.argtypes = [vp, ctypes.c_int64, i64p, f64p, i64p, i64p, f64p, ctypes.c_char]
+    L.blu_update.argtypes = [vp, ctypes.c_double]
+    L.blu_batch_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
+    L.blu_batch_destroy.argtypes = [vp]
+    L.blu_batch_factorize.argtypes = [vp, i64p, i64p, i64p, f64p, ctypes.c_int64, i32p]
+    L.blu_batch_solve_dense.argtypes = [vp, f64p, f64p, ctypes.c_char, i32p]
+    L.blu_batch_get_info.argtypes = [vp, ctypes.c_int64, ctypes.c_int]; L.blu_batch_get_info.restype = ctypes.c_double
+    L.blu_batch_get_factors.argtypes = [vp, ctypes.c_int64, i64p, i64p, i64p, i64p, f64p, i64p, i64p, f64p]
+    L.blu_batch_upload.argtypes = [vp, i64p, i64p, i64p, f64p, ctypes.c_int64, f64p]
+    L.blu_batch_factorize_resident.argtypes = [vp]
+    L.blu_batch_solve_dense_resident.argtypes = [vp, ctypes.c_char]
+    L.blu_batch_download.argtypes = [vp, f64p, i32p]
+    L.blu_batch_stream.argtypes = [vp]; L.blu_batch_stream.restype = vp
+    L.blu_batch_set_stream.argtypes = [vp, vp]
+    L.blu_batch_synchronize.argtypes = [vp]
+    L.blu_batch_last_kernel_ms.argtypes = [vp, ctypes.c_int]; L.blu_batch_last_kernel_ms.restype = ctypes.c_double
+    L.blu_batch_launch_count.argtypes = [vp]; L.blu_batch_launch_count.restype = ctypes.c_int64
+    L.blu_version.restype = ctypes.c_char_p
+    if path == library_path():
+        _LIB = L
+    return L
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _pi(a):
+    return a.ctypes.data_as(i64p) if a is not None else None
+
+
+def _pf(a):
+    return a.ctypes.data_as(f64p) if a is not None else None
+
+
+def _ch(trans):
+    return (trans if isinstance(trans, bytes) else str(trans).encode())[:1]
+
+
+class _Base:
+    _get_info_fn = "blu_get_info"
+
+    def set_param(self, name, value):
+        return self._L.blu_set_param(self._h, P[name], float(value))
+
+    def get_param(self, name):
+        return self._L.blu_get_param(self._h, P[name])
+
+    def __setattr__(self, name, value):
+        # the tunables of `LU` are plain pub fields in the reference (lu.rs:10-66)
+        if name in P and "_h" in self.__dict__:
+            st = self.set_param(name, value)
+            if st != 0:
+                raise ValueError(f"set {name}={value}: status {st}")
+        else:
+            object.__setattr__(self, name, value)
+
+
+class BLU(_Base):
+    """struct BLU, blu.rs:9-20: `lu` state on the device, `lhs/ilhs/nzlhs` on the host."""
+
+    def __init__(self, m, b_nz, device=-1, lib=None):
+        self._L = lib or load_library()
+        h = ctypes.c_void_p()
+        st = self._L.blu_create(ctypes.byref(h), int(m), int(b_nz), int(device))
+        if st != 0:
+            raise RuntimeError(f"blu_create failed with status {st} (no CUDA device? there is no CPU path)")
+        self._h = h
+        self.m = int(m)
+        self.lhs = np.zeros(self.m)
+        self.ilhs = np.zeros(self.m, dtype=np.int64)
+        self.nzlhs = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.blu_destroy(self._h)
+            object.__setattr__(self, "_h", None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self, name):
+        return self._L.blu_get_info(self._h, I[name])
+
+    # blu.rs:95
+    def factorize(self, b_begin, b_end, b_i, b_x):
+        bb, be, bi, bx = _i64(b_begin), _i64(b_end), _i64(b_i), _f64(b_x)
+        if len(bb) < self.m or len(be) < self.m:
+            raise IndexError("b_begin/b_end shorter than m")
+        return self._L.blu_factorize(self._h, _pi(bb), _pi(be), _pi(bi), _pf(bx))
+
+    # blu.rs:139
+    def get_factors(self, want_l=True, want_u=True):
+        m = self.m
+        lnz, unz = int(self.info("l_nz")), int(self.info("u_nz"))
+        out = dict(rowperm=np.zeros(m, np.int64), colperm=np.zeros(m, np.int64))
+        if want_l:
+            out.update(l_colptr=np.zeros(m + 1, np.int64), l_rowidx=np.zeros(m + lnz, np.int64), l_value=np.zeros(m + lnz))
+        if want_u:
+            out.update(u_colptr=np.zeros(m + 1, np.int64), u_rowidx=np.zeros(m + unz, np.int64), u_value=np.zeros(m + unz))
+        st = self._L.blu_get_factors(self._h, _pi(out["rowperm"]), _pi(out["colperm"]),
+                                     _pi(out.get("l_colptr")), _pi(out.get("l_rowidx")), _pf(out.get("l_value")),
+                                     _pi(out.get("u_colptr")), _pi(out.get("u_rowidx")), _pf(out.get("u_value")))
+        return st, out
+
+    # blu.rs:182
+    def solve_dense(self, rhs, trans="N"):
+        r = _f64(rhs)
+        if len(r) != self.m:
+            raise IndexError("rhs length != m")   # the reference panics here (lu/solve_dense.rs:37)
+        x = np.zeros(self.m)
+        st = self._L.blu_solve_dense(self._h, _pf(r), _pf(x), _ch(trans))
+        return st, x
+
+    # blu.rs:207: result in self.lhs / self.ilhs / self.nzlhs
+    def solve_sparse(self, nzrhs, irhs, xrhs, trans="N"):
+        ir, xr = _i64(irhs), _f64(xrhs)
+        self.lhs[:] = 0.0   # lu_clear_lhs, blu.rs:380-395
+        nz = ctypes.c_int64(0)
+        st = self._L.blu_solve_sparse(self._h, int(nzrhs), _pi(ir), _pf(xr), ctypes.byref(nz), _pi(self.ilhs), _pf(self.lhs), _ch(trans))
+        self.nzlhs = nz.value
+        return st
+
+    # blu.rs:257
+    def solve_for_update(self, nzrhs, irhs, xrhs, trans="N", want_solution=0):
+        ir = _i64(irhs)
+        xr = _f64(xrhs) if xrhs is not None else None
+        if want_solution:
+            self.lhs[:] = 0.0
+            nz = ctypes.c_int64(0)
+            st = self._L.blu_solve_for_update(self._h, int(nzrhs), _pi(ir), _pf(xr), ctypes.byref(nz), _pi(self.ilhs), _pf(self.lhs), _ch(trans))
+            self.nzlhs = nz.value
+        else:
+            st = self._L.blu_solve_for_update(self._h, int(nzrhs), _pi(ir), _pf(xr), None, None, None, _ch(trans))
+        return st
+
+    # blu.rs:319
+    def update(self, xtbl):
+        return self._L.blu_update(self._h, float(xtbl))
+
+
+class BLUBatch(_Base):
+    """Many independent bases of one dimension on one GPU (one `BLU` per basis on the CPU)."""
+
+    def __init__(self, nmat, m, bnz_cap, device=-1, lib=None):
+        self._L = lib or load_library()
+        h = ctypes.c_void_p()
+        st = self._L.blu_batch_create(ctypes.byref(h), int(nmat), int(m), int(bnz_cap), int(device))
+        if st != 0:
+            raise RuntimeError(f"blu_batch_create failed with status {st} (no CUDA device? there is no CPU path)")
+        self._h = h
+        self.nmat, self.m = int(nmat), int(m)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.blu_batch_destroy(self._h)
+            object.__setattr__(self, "_h", None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self, k, name):
+        return self._L.blu_batch_get_info(self._h, int(k), I[name])
+
+    def factorize(self, b_begin, b_end, b_i, b_x):
+        bb, be, bi, bx = _i64(b_begin), _i64(b_end), _i64(b_i), _f64(b_x)
+        status = np.zeros(self.nmat, dtype=np.int32)
+        st = self._L.blu_batch_factorize(self._h, _pi(bb), _pi(be), _pi(bi), _pf(bx), len(bi), status.ctypes.data_as(i32p))
+        return st, status
+
+    def solve_dense(self, rhs, trans="N"):
+        r = _f64(rhs).reshape(-1)
+        x = np.zeros(self.nmat * self.m)
+        status = np.zeros(self.nmat, dtype=np.int32)
+        st = self._L.blu_batch_solve_dense(self._h, _pf(r), _pf(x), _ch(trans), status.ctypes.data_as(i32p))
+        return st, x.reshape(self.nmat, self.m), status
+
+    def get_factors(self, k):
+        m = self.m
+        lnz, unz = int(self.info(k, "l_nz")), int(self.info(k, "u_nz"))
+        out = dict(rowperm=np.zeros(m, np.int64), colperm=np.zeros(m, np.int64),
+                   l_colptr=np.zeros(m + 1, np.int64), l_rowidx=np.zeros(m + lnz, np.int64), l_value=np.zeros(m + lnz),
+                   u_colptr=np.zeros(m + 1, np.int64), u_rowidx=np.zeros(m + unz, np.int64), u_value=np.zeros(m + unz))
+        st = self._L.blu_batch_get_factors(self._h, int(k), _pi(out["rowperm"]), _pi(out["colperm"]),
+                                           _pi(out["l_colptr"]), _pi(out["l_rowidx"]), _pf(out["l_value"]),
+                                           _pi(out["u_colptr"]), _pi(out["u_rowidx"]), _pf(out["u_value"]))
+        return st, out
+
+    # device-resident path (bench)
+    def upload(self, b_begin=None, b_end=None, b_i=None, b_x=None, rhs=None):
+        bb = _i64(b_begin) if b_begin is not None else None
+        be = _i64(b_end) if b_end is not None else None
+        bi = _i64(b_i) if b_i is not None else None
+        bx = _f64(b_x) if b_x is not None else None
+        r = _f64(rhs).reshape(-1) if rhs is not None else None
+        return self._L.blu_batch_upload(self._h, _pi(bb), _pi(be), _pi(bi), _pf(bx), len(bi) if bi is not None else 0, _pf(r))
+
+    def factorize_resident(self):
+        return self._L.blu_batch_factorize_resident(self._h)
+
+    def solve_dense_resident(self, trans="N"):
+        return self._L.blu_batch_solve_dense_resident(self._h, _ch(trans))
+
+    def download(self):
+        x = np.zeros(self.nmat * self.m)
+        status = np.zeros(self.nmat, dtype=np.int32)
+        st = self._L.blu_batch_download(self._h, _pf(x), status.ctypes.data_as(i32p))
+        return st, x.reshape(self.nmat, self.m), status
+
+    def last_kernel_ms(self, which):
+        return self._L.blu_batch_last_kernel_ms(self._h, int(which))
+
+    def launch_count(self):
+        return self._L.blu_batch_launch_count(self._h)
+
+    def set_stream(self, stream_ptr):
+        return self._L.blu_batch_set_stream(self._h, ctypes.c_void_p(stream_ptr))
+
+    def synchronize(self):
+        return self._L.blu_batch_synchronize(self._h)

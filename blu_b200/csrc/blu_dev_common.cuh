@@ -1,0 +1,255 @@
+/* blu_dev_common.cuh -- per-slot view, shared-memory state and block/warp primitives. */
+#ifndef BLU_DEV_COMMON_CUH
+#define BLU_DEV_COMMON_CUH
+
+#include "blu_types.h"
+
+#ifndef BLU_EMU
+#include <cuda_runtime.h>
+#define BLU_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define BLU_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+typedef blu_u64 u64;
+typedef blu_i64 i64;
+
+#define FULLMASK 0xffffffffu
+#define KEY_INF 0xffffffffffffffffull
+#define STAMP_BITS 40
+#define MAXROW_SMALL 64 /* pivot.rs:22 */
+#define MAXCAND 32      /* upper bound on maxsearch honoured by the search kernel */
+
+/* per-slot view of BluDev */
+struct Mat {
+    int m;
+    int l_mem, u_mem, w_mem, bnz_cap;
+    BluParams prm;
+    const i64 *b_begin, *b_end, *b_i;
+    const double *b_x;
+    int *bt_ptr, *bt_idx; double *bt_val;
+    int *pinv, *qinv, *prank, *qrank;
+    double *colpiv, *rowpiv;
+    int *l_idx; double *l_val;
+    int *u_idx; double *u_val;
+    int *w_idx; double *w_val;
+    int *lbeg, *lend, *lcap;
+    u64 *ckey, *rkey;
+    int *l_begin_p, *u_begin, *l_begin, *lt_begin, *lt_begin_p, *p, *r_begin, *eta_row;
+    int *pivotcol, *pivotrow;
+    int *rowmark, *colmark, *marked, *iwork1, *pstack, *acols, *tmpi;
+    u64 *cancelled;
+    double *work0, *work1, *gwork;
+    BluInfo *info;
+};
+
+__device__ __forceinline__ void mat_view(Mat &M, const BluDev &D, int s) {
+    const size_t m = (size_t)D.m, S = (size_t)s;
+    M.m = D.m;
+    M.l_mem = (int)D.l_mem; M.u_mem = (int)D.u_mem; M.w_mem = (int)D.w_mem; M.bnz_cap = (int)D.bnz_cap;
+    M.prm = D.prm;
+    M.b_begin = D.b_begin + S * m; M.b_end = D.b_end + S * m; M.b_i = D.b_i; M.b_x = D.b_x;
+    M.bt_ptr = D.bt_ptr + S * (m + 1);
+    M.bt_idx = D.bt_idx + S * (size_t)D.bnz_cap; M.bt_val = D.bt_val + S * (size_t)D.bnz_cap;
+    M.pinv = D.pinv + S * m; M.qinv = D.qinv + S * m;
+    M.prank = D.prank + S * m; M.qrank = D.qrank + S * m;
+    M.colpiv = D.colpiv + S * m; M.rowpiv = D.rowpiv + S * m;
+    M.l_idx = D.l_idx + S * (size_t)D.l_mem; M.l_val = D.l_val + S * (size_t)D.l_mem;
+    M.u_idx = D.u_idx + S * (size_t)D.u_mem; M.u_val = D.u_val + S * (size_t)D.u_mem;
+    M.w_idx = D.w_idx + S * 2 * (size_t)D.w_mem; M.w_val = D.w_val + S * 2 * (size_t)D.w_mem;
+    M.lbeg = D.lbeg + S * 2 * m; M.lend = D.lend + S * 2 * m; M.lcap = D.lcap + S * 2 * m;
+    M.ckey = D.ckey + S * m; M.rkey = D.rkey + S * m;
+    M.l_begin_p = D.l_begin_p + S * (m + 1); M.u_begin = D.u_begin + S * (m + 1);
+    M.l_begin = D.l_begin + S * (m + 1); M.lt_begin = D.lt_begin + S * (m + 1);
+    M.lt_begin_p = D.lt_begin_p + S * (m + 1); M.p = D.p + S * (m + 1);
+    M.r_begin = D.r_begin + S * (m + 1); M.eta_row = D.eta_row + S * (m + 1);
+    M.pivotcol = D.pivotcol + S * (2 * m + 2); M.pivotrow = D.pivotrow + S * (2 * m + 2);
+    M.rowmark = D.rowmark + S * m; M.colmark = D.colmark + S * m; M.marked = D.marked + S * m;
+    M.iwork1 = D.iwork1 + S * (2 * m + 2); M.pstack = D.pstack + S * m;
+    M.acols = D.acols + S * m; M.tmpi = D.tmpi + S * (4 * m + 4);
+    M.cancelled = D.cancelled + S * m;
+    M.work0 = D.work0 + S * m; M.work1 = D.work1 + S * m;
+    M.gwork = D.gwork + S * (size_t)D.gwork_warps * m;
+    M.info = D.info + s;
+}
+
+/* block-shared state of one factorization */
+struct Shm {
+    Mat M;
+    int iscr[40];
+    u64 kscr[40];
+    double dscr[40];
+    int status;
+    int rank, rankdef;
+    int w_used, w_limit;      /* fill pointer and end of the live W half */
+    int w_half;
+    i64 cstamp, rstamp;
+    int nact, ndead;
+    int pivot_row, pivot_col;
+    int flag_a, flag_b, need_remove;
+    int nexpand, ngarbage;
+    i64 nsearch;
+    i64 factor_flops;
+    int cand_col[MAXCAND];
+    i64 cand_mc[MAXCAND];
+    int cand_row[MAXCAND];
+    int ncand;
+    int cap;                  /* entries of the smem line caches */
+    int *cidx, *ridx; double *cval, *work; /* dynamic smem carve-up */
+    double elim_bytes; i64 nelim_div;
+};
+
+template <int NT> __device__ __forceinline__ void bsync() {
+    if (NT > 32) __syncthreads(); else __syncwarp();
+}
+__device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
+
+__device__ __forceinline__ u64 mkkey(int cnt, i64 stamp) { return ((u64)(unsigned)cnt << STAMP_BITS) | (u64)stamp; }
+__device__ __forceinline__ int key_cnt(u64 k) { return (int)(k >> STAMP_BITS); }
+
+/* ---- warp primitives ---- */
+__device__ __forceinline__ int warp_incl_scan(int v) {
+    const int lane = threadIdx.x & 31;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULLMASK, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
+    return v;
+}
+__device__ __forceinline__ i64 warp_sum64(i64 v) {
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { int t = __shfl_xor_sync(FULLMASK, v, d); v = t > v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ int warp_min(int v) {
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { int t = __shfl_xor_sync(FULLMASK, v, d); v = t < v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ double warp_maxd(double v) {
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { double t = __shfl_xor_sync(FULLMASK, v, d); v = t > v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ double warp_mind(double v) {
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { double t = __shfl_xor_sync(FULLMASK, v, d); v = t < v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ u64 warp_min64(u64 v) {
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { u64 t = __shfl_xor_sync(FULLMASK, v, d); v = t < v ? t : v; }
+    return v;
+}
+/* sum of doubles in lane order is not needed bit-exactly anywhere in the factorization */
+__device__ __forceinline__ double warp_sumd(double v) {
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
+    return v;
+}
+
+/* ---- block primitives (every thread of the block must call them) ---- */
+template <int NT> __device__ __forceinline__ int block_excl_scan(int v, int *total, int *scr) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = warp_incl_scan(v);
+    if (NW == 1) {
+        *total = __shfl_sync(FULLMASK, incl, 31);
+        return incl - v;
+    }
+    if (lane == 31) scr[wid] = incl;
+    bsync<NT>();
+    if (wid == 0) {
+        int t = lane < NW ? scr[lane] : 0;
+        int ti = warp_incl_scan(t);
+        if (lane < NW) scr[lane] = ti - t;
+        if (lane == NW - 1) scr[NW] = ti;
+    }
+    bsync<NT>();
+    int res = incl - v + scr[wid];
+    *total = scr[NW];
+    bsync<NT>();
+    return res;
+}
+template <int NT> __device__ __forceinline__ i64 block_sum64(i64 v, u64 *scr) {
+    constexpr int NW = NT / 32;
+    v = warp_sum64(v);
+    if (NW == 1) return v;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) scr[wid] = (u64)v;
+    bsync<NT>();
+    i64 r = 0;
+    #pragma unroll
+    for (int w = 0; w < NW; w++) r += (i64)scr[w];
+    bsync<NT>();
+    return r;
+}
+template <int NT> __device__ __forceinline__ int block_max(int v, int *scr) {
+    constexpr int NW = NT / 32;
+    v = warp_max(v);
+    if (NW == 1) return v;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) scr[wid] = v;
+    bsync<NT>();
+    int r = scr[0];
+    #pragma unroll
+    for (int w = 1; w < NW; w++) r = scr[w] > r ? scr[w] : r;
+    bsync<NT>();
+    return r;
+}
+template <int NT> __device__ __forceinline__ u64 block_min64(u64 v, u64 *scr) {
+    constexpr int NW = NT / 32;
+    v = warp_min64(v);
+    if (NW == 1) return v;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) scr[wid] = v;
+    bsync<NT>();
+    u64 r = scr[0];
+    #pragma unroll
+    for (int w = 1; w < NW; w++) r = scr[w] < r ? scr[w] : r;
+    bsync<NT>();
+    return r;
+}
+template <int NT> __device__ __forceinline__ double block_maxd(double v, double *scr) {
+    constexpr int NW = NT / 32;
+    v = warp_maxd(v);
+    if (NW == 1) return v;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) scr[wid] = v;
+    bsync<NT>();
+    double r = scr[0];
+    #pragma unroll
+    for (int w = 1; w < NW; w++) r = scr[w] > r ? scr[w] : r;
+    bsync<NT>();
+    return r;
+}
+template <int NT> __device__ __forceinline__ double block_mind(double v, double *scr) {
+    constexpr int NW = NT / 32;
+    v = warp_mind(v);
+    if (NW == 1) return v;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) scr[wid] = v;
+    bsync<NT>();
+    double r = scr[0];
+    #pragma unroll
+    for (int w = 1; w < NW; w++) r = scr[w] < r ? scr[w] : r;
+    bsync<NT>();
+    return r;
+}
+
+/* record the first failed device-side invariant (kept live like the reference's assert!s) */
+#define BLU_CHECK(S, cond) do { if (!(cond)) { if ((S).M.info->internal_error == 0) (S).M.info->internal_error = __LINE__; (S).status = BLU_ERROR_INTERNAL; } } while (0)
+
+__device__ __forceinline__ int slack_of(const BluParams &p, int nz) { return (int)(p.stretch * (double)nz) + p.pad; }
+
+#endif

@@ -1,0 +1,276 @@
+/* blu_factor_build.cuh -- phase 4: assemble the factors in the layout the solves and the
+ * Forrest-Tomlin update work on (reference: src/lu/build_factors.rs:113-423; layout
+ * documented there at :10-112), then the factorize kernel itself. */
+#ifndef BLU_FACTOR_BUILD_CUH
+#define BLU_FACTOR_BUILD_CUH
+#include "blu_dev_common.cuh"
+#include "blu_factor_setup.cuh"
+#include "blu_factor_bump.cuh"
+
+template <int NT> __device__ void phase_build_factors(Shm &S) {
+    Mat &M = S.M;
+    const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int rank = S.rank;
+    const int l_nz = M.l_begin_p[rank] - rank;
+    int u_nz = M.u_begin[rank];
+
+    /* memory, build_factors.rs:163-177 */
+    {
+        int st = BLU_OK;
+        i64 need = 2 * ((i64)l_nz + m);
+        if ((i64)M.l_mem < need) { if (tid == 0) M.info->addmem_l = need - M.l_mem; st = BLU_REALLOCATE; }
+        need = (i64)u_nz + m + 1;
+        if (st == BLU_OK && (i64)M.u_mem < need) { if (tid == 0) M.info->addmem_u = need - M.u_mem; st = BLU_REALLOCATE; }
+        need = (i64)u_nz + (i64)(M.prm.stretch * (double)u_nz) + (i64)m * M.prm.pad;
+        if (st == BLU_OK && (i64)M.w_mem < need) { if (tid == 0) M.info->addmem_w = need - M.w_mem; st = BLU_REALLOCATE; }
+        if (st != BLU_OK) { bsync<NT>(); if (tid == 0) S.status = st; bsync<NT>(); return; }
+    }
+
+    /* permutations, build_factors.rs:192-209: non-pivotal rows/columns in index order */
+    {
+        int lr = rank, lc = rank;
+        for (int base = 0; base < m; base += NT) {
+            int i = base + tid;
+            int fr = i < m && M.pinv[i] < 0, fc = i < m && M.qinv[i] < 0;
+            int totr, exr = block_excl_scan<NT>(fr, &totr, S.iscr);
+            int totc, exc = block_excl_scan<NT>(fc, &totc, S.iscr);
+            if (i < m) {
+                int pr = fr ? lr + exr : M.pinv[i];
+                int qc = fc ? lc + exc : M.qinv[i];
+                M.pinv[i] = pr; M.qinv[i] = qc;
+                M.prank[i] = pr; M.qrank[i] = qc;
+                M.pivotrow[pr] = i; M.pivotcol[qc] = i;
+            }
+            lr += totr; lc += totc;
+        }
+        if (tid == 0) { BLU_CHECK(S, lr == m && lc == m); }
+    }
+    bsync<NT>();
+    /* unit pivots for dependent columns; L column-wise completion, :221-238 */
+    {
+        const int lb = M.l_begin_p[rank];
+        for (int k = rank + tid; k < m; k += NT) {
+            M.colpiv[M.pivotcol[k]] = 1.0;
+            M.l_idx[lb + (k - rank)] = -1;
+            M.l_begin_p[k + 1] = lb + (k - rank) + 1;
+        }
+    }
+    bsync<NT>();
+    for (int i = tid; i < m; i += NT) M.l_begin[i] = M.l_begin_p[M.pinv[i]];
+
+    /* L row-wise, build_factors.rs:242-274.  Counting in parallel; the scatter runs in
+     * pivot order on one warp so every row is filled in ascending pivot step exactly
+     * as the reference does (no atomics => deterministic storage order). */
+    int *cnt = M.iwork1;
+    for (int i = tid; i < m; i += NT) cnt[i] = 0;
+    bsync<NT>();
+    for (int g = tid; g < l_nz + m; g += NT) { int i = M.l_idx[g]; if (i >= 0) atomicAdd(&cnt[i], 1); }
+    bsync<NT>();
+    {
+        int put = l_nz + m;
+        for (int base = 0; base < m; base += NT) {
+            int k = base + tid;
+            int i = k < m ? M.pivotrow[k] : 0;
+            int c = k < m ? cnt[i] + 1 : 0;
+            int tot, ex = block_excl_scan<NT>(c, &tot, S.iscr);
+            if (k < m) {
+                int b = put + ex;
+                M.lt_begin_p[k] = b; M.lt_begin[i] = b;
+                M.l_idx[b + c - 1] = -1;
+                cnt[i] = b;
+            }
+            put += tot;
+        }
+        if (tid == 0) { BLU_CHECK(S, put == 2 * (l_nz + m)); M.lt_begin_p[m] = put; M.r_begin[0] = put; }
+    }
+    bsync<NT>();
+    if (wid == 0) {
+        for (int k = 0; k < m; k++) {
+            const int b = M.l_begin_p[k], e = M.l_begin_p[k + 1] - 1;
+            if (e <= b) continue;
+            const int ipivot = M.pivotrow[k];
+            for (int g = b + lane; g < e; g += 32) {
+                int r = M.l_idx[g];
+                int dst = cnt[r]; cnt[r] = dst + 1;
+                M.l_idx[dst] = ipivot; M.l_val[dst] = M.l_val[g];
+            }
+            __syncwarp();
+        }
+    }
+    bsync<NT>();
+
+    /* U row-wise into the W file in pivot order with slack, build_factors.rs:286-351 */
+    int *ucnt = M.iwork1;      /* per column j: entries of U column j */
+    for (int j = tid; j < m; j += NT) ucnt[j] = 0;
+    bsync<NT>();
+    {
+        int put = 0, unz_new = 0;
+        const bool full = rank == m;
+        for (int base = 0; base < m; base += NT) {
+            int k = base + tid;
+            int nz = 0;
+            if (k < rank) {
+                if (full) nz = M.u_begin[k + 1] - M.u_begin[k];
+                else for (int pos = M.u_begin[k]; pos < M.u_begin[k + 1]; pos++) nz += M.qinv[M.u_idx[pos]] < rank;
+            }
+            int sz = k < m ? (k < rank ? nz + slack_of(M.prm, nz) : M.prm.pad) : 0;
+            int tot, ex = block_excl_scan<NT>(sz, &tot, S.iscr);
+            int totn, exn = block_excl_scan<NT>(nz, &totn, S.iscr);
+            (void)exn;
+            if (k < m) {
+                int jp = M.pivotcol[k];
+                int b = put + ex, w = b;
+                if (k < rank) {
+                    for (int pos = M.u_begin[k]; pos < M.u_begin[k + 1]; pos++) {
+                        int j = M.u_idx[pos];
+                        if (full || M.qinv[j] < rank) {
+                            M.w_idx[w] = j; M.w_val[w] = M.u_val[pos]; w++;
+                            atomicAdd(&ucnt[j], 1);
+                        }
+                    }
+                }
+                M.lbeg[jp] = b; M.lend[jp] = w; M.lcap[jp] = b + sz;
+            }
+            put += tot; unz_new += totn;
+        }
+        u_nz = unz_new;
+        if (tid == 0) {
+            BLU_CHECK(S, put <= M.w_mem);
+            S.w_half = 0; S.w_used = put; S.w_limit = M.w_mem;
+        }
+    }
+    bsync<NT>();
+    /* U column-wise, build_factors.rs:354-384 */
+    {
+        int put = 1;
+        if (tid == 0) M.u_idx[0] = -1;
+        for (int base = 0; base < m; base += NT) {
+            int k = base + tid;
+            int j = k < m ? M.pivotcol[k] : 0, i = k < m ? M.pivotrow[k] : 0;
+            int nz = k < m ? ucnt[j] : 0;
+            int sz = nz > 0 ? nz + 1 : 0;
+            int tot, ex = block_excl_scan<NT>(sz, &tot, S.iscr);
+            if (k < m) {
+                int b = nz > 0 ? put + ex : 0;
+                M.u_begin[i] = b;
+                if (nz > 0) M.u_idx[b + nz] = -1;
+                ucnt[j] = b;
+            }
+            put += tot;
+        }
+        if (tid == 0) M.u_begin[m] = put;
+    }
+    bsync<NT>();
+    if (wid == 0) {
+        for (int k = 0; k < m; k++) {
+            const int jp = M.pivotcol[k], ip = M.pivotrow[k];
+            const int b = M.lbeg[jp], e = M.lend[jp];
+            for (int pos = b + lane; pos < e; pos += 32) {
+                int j = M.w_idx[pos];
+                int dst = ucnt[j]; ucnt[j] = dst + 1;
+                M.u_idx[dst] = ip; M.u_val[dst] = M.w_val[pos];
+            }
+            __syncwarp();
+        }
+    }
+    bsync<NT>();
+    /* pmap / qmap overwrite pinv / qinv, build_factors.rs:395-400; row_pivot, min/max, :403-410 */
+    for (int k = tid; k < m; k += NT) {
+        int i = M.pivotrow[k], j = M.pivotcol[k];
+        M.pinv[j] = i; M.qinv[i] = j;
+        M.p[k] = i;
+    }
+    bsync<NT>();
+    double mx = 0.0, mn = INFINITY;
+    for (int i = tid; i < m; i += NT) {
+        double pv = M.colpiv[M.qinv[i]];
+        M.rowpiv[i] = pv;
+        pv = fabs(pv);
+        mx = fmax(mx, pv); mn = fmin(mn, pv);
+    }
+    mx = block_maxd<NT>(mx, S.dscr);
+    mn = block_mind<NT>(mn, S.dscr);
+    if (tid == 0) {
+        BluInfo *I = M.info;
+        I->min_pivot = mn; I->max_pivot = mx;
+        I->pivotlen = m; I->l_nz = l_nz; I->u_nz = u_nz; I->r_nz = 0;
+    }
+    bsync<NT>();
+}
+
+/* ------------------------------------------------------------------ */
+/* the factorize kernel: one CTA per basis (factorize.rs:34-119)       */
+/* ------------------------------------------------------------------ */
+__device__ __forceinline__ void shm_carve(Shm &S, unsigned char *dyn, int cap, int nw) {
+    /* [cval: cap f64][work: nw*cap f64][cidx: cap i32][ridx: cap i32] */
+    S.cap = cap;
+    S.cval = (double *)dyn;
+    S.work = S.cval + cap;
+    S.cidx = (int *)(S.work + (size_t)nw * cap);
+    S.ridx = S.cidx + cap;
+}
+static inline size_t blu_factor_smem_bytes(int cap, int nw) {
+    return (size_t)cap * 8 + (size_t)nw * cap * 8 + (size_t)cap * 4 * 2;
+}
+
+template <int NT> __global__ void __launch_bounds__(NT) k_factorize(BluDev D, int cap) {
+    BLU_DYN_SMEM(dyn);
+    __shared__ Shm S;
+    const int tid = threadIdx.x;
+    for (int s = blockIdx.x; s < D.nmat; s += gridDim.x) {
+        if (tid == 0) {
+            mat_view(S.M, D, s);
+            shm_carve(S, dyn, cap, NT / 32);
+            BluInfo *I = S.M.info;
+            /* LU::reset, lu.rs:329-396 (cumulative counters survive) */
+            I->m = D.m;
+            I->nupdate = -1; I->nforrest = 0; I->l_nz = I->u_nz = I->r_nz = 0;
+            I->min_pivot = I->max_pivot = I->max_eta = 0.0;
+            I->update_cost_numer = 0.0; I->update_cost_denom = 1.0;
+            I->l_flops = I->u_flops = I->r_flops = 0;
+            I->matrix_nz = 0; I->rank = 0; I->bump_size = 0; I->bump_nz = 0;
+            I->nsearch_pivot = I->nexpand = I->ngarbage = I->factor_flops = 0;
+            I->pivot_error = 0.0; I->ftran_for_update = I->btran_for_update = -1;
+            I->marker = 0; I->pivotlen = 0; I->rankdef = 0;
+            I->addmem_l = I->addmem_u = I->addmem_w = 0;
+            I->internal_error = 0; I->elim_bytes = 0.0; I->nelim_div = 0;
+            I->condest_l = I->condest_u = I->norm_l = I->norm_u = 0.0;
+            I->normest_l_inv = I->normest_u_inv = I->onenorm = I->infnorm = I->residual_test = 0.0;
+            S.status = BLU_OK;
+            S.rank = 0; S.rankdef = 0; S.need_remove = 0;
+            S.nexpand = 0; S.ngarbage = 0; S.nsearch = 0; S.factor_flops = 0;
+            S.elim_bytes = 0.0; S.nelim_div = 0;
+            S.w_used = 0; S.w_limit = (int)D.w_mem; S.w_half = 0;
+        }
+        bsync<NT>();
+        for (int i = tid; i < D.m; i += NT) S.M.marked[i] = 0;
+        phase_singletons<NT>(S);
+        if (S.status == BLU_OK) phase_setup_bump<NT>(S);
+        if (S.status == BLU_OK) phase_bump<NT>(S);
+        if (S.status == BLU_OK) phase_build_factors<NT>(S);
+        bsync<NT>();
+        if (tid == 0) {
+            BluInfo *I = S.M.info;
+            I->rank = S.rank; I->rankdef = S.rankdef;
+            I->nsearch_pivot = S.nsearch; I->nexpand = S.nexpand; I->ngarbage = S.ngarbage;
+            I->factor_flops = S.factor_flops;
+            I->elim_bytes = S.elim_bytes; I->nelim_div = S.nelim_div;
+            I->w_half = S.w_half; I->w_used = S.w_used;
+            I->cstamp = S.cstamp; I->rstamp = S.rstamp;
+            int st = S.status;
+            if (st == BLU_OK) {
+                I->nupdate = 0; I->nfactorize++;
+                /* cost model, factorize.rs:160-166 */
+                double factor_cost = 0.04 * (double)D.m + 0.07 * (double)I->matrix_nz + 0.20 * (double)I->bump_nz +
+                                     0.20 * (double)I->nsearch_pivot + 0.008 * (double)I->factor_flops;
+                I->update_cost_denom = factor_cost * 250.0;
+                if (S.rank < D.m) st = BLU_WARNING_SINGULAR_MATRIX;
+            }
+            I->status = st;
+        }
+        bsync<NT>();
+    }
+}
+
+#endif

@@ -1,0 +1,868 @@
+/* blu_factor_bump.cuh -- phase 3: Markowitz search + one elimination step per pivot,
+ * looped inside the kernel (reference: src/lu/factorize_bump.rs:12-49,
+ * src/lu/markowitz.rs:34-219, src/lu/pivot.rs:48-1381).
+ *
+ * Parallel formulation that keeps the reference's pivot sequence bit for bit:
+ *  - the count buckets of list.rs are FIFO by last insertion; a column/row carries the
+ *    key (count << 40 | stamp) with a monotone stamp handed out in the order the
+ *    reference would call list_add, so "walk bucket nz from the head" == ascending key;
+ *  - lines (columns with values, rows pattern-only) are updated by one warp each with
+ *    ballot/prefix compaction, which reproduces the in-line storage order of the
+ *    sequential code;
+ *  - a*b and the subtraction are separate roundings (__dmul_rn/__dsub_rn) like Rust.
+ * Where a line lives in memory is free (file.rs keeps only in-line order), so lines
+ * that outgrow their slack move to the end of the live W half (atomic bump pointer)
+ * and garbage collection copies all live lines to the other half.
+ */
+#ifndef BLU_FACTOR_BUMP_CUH
+#define BLU_FACTOR_BUMP_CUH
+#include "blu_dev_common.cuh"
+
+/* ------------------------------------------------------------------ */
+/* garbage collection (role of file.rs:92 file_compress)               */
+/* ------------------------------------------------------------------ */
+template <int NT> __device__ void w_compact(Shm &S) {
+    Mat &M = S.M;
+    const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int nbase = (1 - S.w_half) * M.w_mem;
+    int *newbeg = M.tmpi;       /* 2m */
+    int *newcap = M.tmpi + 2 * m;
+    /* try with slack first; if that does not fit fall back to exact sizes */
+    for (int attempt = 0; attempt < 2; attempt++) {
+        int put = 0;
+        for (int base = 0; base < 2 * m; base += NT) {
+            int l = base + tid;
+            int sz = 0, nz = 0;
+            if (l < 2 * m) {
+                int live = l < m ? (M.ckey[l] != KEY_INF) : (M.rkey[l - m] != KEY_INF);
+                nz = live ? M.lend[l] - M.lbeg[l] : 0;
+                sz = (live && nz > 0) ? nz + (attempt == 0 ? slack_of(M.prm, nz) : 0) : 0;
+            }
+            int tot, ex = block_excl_scan<NT>(sz, &tot, S.iscr);
+            if (l < 2 * m) { newbeg[l] = nbase + put + ex; newcap[l] = nbase + put + ex + sz; }
+            put += tot;
+        }
+        bsync<NT>();
+        if (put <= M.w_mem) { if (tid == 0) S.w_used = nbase + put; break; }
+        if (attempt == 1 && tid == 0) BLU_CHECK(S, 0);
+    }
+    bsync<NT>();
+    for (int l = wid; l < 2 * m; l += NW) {
+        int ob = M.lbeg[l], oe = M.lend[l];
+        int live = l < m ? (M.ckey[l] != KEY_INF) : (M.rkey[l - m] != KEY_INF);
+        int nb = newbeg[l];
+        if (live && oe > ob) {
+            for (int t = lane; t < oe - ob; t += 32) {
+                M.w_idx[nb + t] = M.w_idx[ob + t];
+                if (l < m) M.w_val[nb + t] = M.w_val[ob + t];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int nz = (live && oe > ob) ? oe - ob : 0;
+            M.lbeg[l] = nb; M.lend[l] = nb + nz; M.lcap[l] = newcap[l];
+        }
+    }
+    if (tid == 0) {
+        S.w_half = 1 - S.w_half;
+        S.w_limit = nbase + M.w_mem;
+        S.ngarbage++;
+    }
+    bsync<NT>();
+}
+
+/* Make sure `grow` more slots can be handed out; may compact.  Uniform result. */
+template <int NT> __device__ bool w_reserve(Shm &S, i64 grow) {
+    if (grow > (i64)(S.w_limit - S.w_used)) {
+        w_compact<NT>(S);
+        if (grow > (i64)(S.w_limit - S.w_used)) {
+            if (threadIdx.x == 0) { S.M.info->addmem_w = grow - (S.w_limit - S.w_used); S.status = BLU_REALLOCATE; }
+            bsync<NT>();
+            return false;
+        }
+    }
+    return true;
+}
+
+/* ------------------------------------------------------------------ */
+/* Markowitz search, markowitz.rs:34-193 (search_rows == 0 path)       */
+/* ------------------------------------------------------------------ */
+template <int NT> __device__ void markowitz_search(Shm &S) {
+    Mat &M = S.M;
+    const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    int maxsearch = M.prm.maxsearch;
+    if (maxsearch < 1) maxsearch = 1;
+    if (maxsearch > MAXCAND) maxsearch = MAXCAND;
+
+    /* shrink the active-column list when more than half of it is dead */
+    if (S.ndead * 2 > S.nact && S.nact > 2 * NT) {
+        int *tmp = M.tmpi;
+        int put = 0;
+        for (int base = 0; base < S.nact; base += NT) {
+            int t = base + tid;
+            int j = t < S.nact ? M.acols[t] : -1;
+            int live = j >= 0 && M.ckey[j] != KEY_INF;
+            int tot, ex = block_excl_scan<NT>(live, &tot, S.iscr);
+            if (live) tmp[put + ex] = j;
+            put += tot;
+        }
+        bsync<NT>();
+        for (int t = tid; t < put; t += NT) M.acols[t] = tmp[t];
+        if (tid == 0) { S.nact = put; S.ndead = 0; }
+        bsync<NT>();
+    }
+    const int nact = S.nact;
+
+    /* the first `maxsearch` live columns in ascending (count, stamp) order */
+    int ncand = 0;
+    u64 prev = 0; int have_prev = 0;
+    while (ncand < maxsearch) {
+        u64 k0 = KEY_INF, k1 = KEY_INF, k2 = KEY_INF;
+        int j0 = -1, j1 = -1, j2 = -1;
+        for (int t = tid; t < nact; t += NT) {
+            int j = M.acols[t];
+            u64 k = M.ckey[j];
+            if (k == KEY_INF || (have_prev && k <= prev)) continue;
+            if (k < k2) {
+                if (k < k1) {
+                    k2 = k1; j2 = j1;
+                    if (k < k0) { k1 = k0; j1 = j0; k0 = k; j0 = j; }
+                    else { k1 = k; j1 = j; }
+                } else { k2 = k; j2 = j; }
+            }
+        }
+        int got = 0;
+        for (int r = 0; r < 3 && ncand < maxsearch; r++) {
+            u64 best = block_min64<NT>(k0, S.kscr);
+            if (best == KEY_INF) break;
+            if (k0 == best) {
+                S.cand_col[ncand] = j0;
+                k0 = k1; j0 = j1; k1 = k2; j1 = j2; k2 = KEY_INF; j2 = -1;
+            }
+            prev = best; have_prev = 1;
+            ncand++; got++;
+        }
+        bsync<NT>();
+        if (got < 3) break;     /* fewer live columns than asked for */
+    }
+    if (ncand == 0) { if (tid == 0) { BLU_CHECK(S, 0); } bsync<NT>(); return; }
+
+    /* empty column => rank-deficiency step (markowitz.rs:73-78): bucket 0 sorts first */
+    if (key_cnt(M.ckey[S.cand_col[0]]) == 0) {
+        if (tid == 0) { S.pivot_col = S.cand_col[0]; S.pivot_row = -1; }
+        bsync<NT>();
+        return;
+    }
+
+    /* evaluate the candidates, one warp per column (markowitz.rs:82-123) */
+    const double abstol = M.prm.abstol, reltol = M.prm.reltol;
+    for (int c = wid; c < ncand; c += NW) {
+        const int j = S.cand_col[c];
+        const int beg = M.lbeg[j], end = M.lend[j];
+        const i64 nz1 = end - beg;
+        const double cmx = M.colpiv[j];
+        const double tol = fmax(abstol, reltol * cmx);
+        u64 bestmc = KEY_INF; int bestpos = 0x7fffffff;
+        for (int pos = beg + lane; pos < end; pos += 32) {
+            double x = fabs(M.w_val[pos]);
+            if (x == 0.0 || x < tol) continue;
+            int i = M.w_idx[pos];
+            i64 nz2 = M.lend[m + i] - M.lbeg[m + i];
+            u64 mc = (u64)((nz1 - 1) * (nz2 - 1));
+            if (mc < bestmc) { bestmc = mc; bestpos = pos; }
+        }
+        u64 wmc = warp_min64(bestmc);
+        int p = (bestmc == wmc && wmc != KEY_INF) ? bestpos : 0x7fffffff;
+        p = warp_min(p);
+        if (lane == 0) {
+            S.cand_mc[c] = wmc == KEY_INF ? -1 : (i64)wmc;
+            S.cand_row[c] = wmc == KEY_INF ? -1 : M.w_idx[p];
+        }
+    }
+    bsync<NT>();
+    if (tid == 0) {
+        i64 mc64 = (i64)m * (i64)m;
+        int pr = -1, pc = -1;
+        for (int c = 0; c < ncand; c++) {
+            if (S.cand_mc[c] >= 0 && S.cand_mc[c] < mc64) { mc64 = S.cand_mc[c]; pr = S.cand_row[c]; pc = S.cand_col[c]; }
+        }
+        BLU_CHECK(S, pc >= 0);
+        S.pivot_row = pr; S.pivot_col = pc;
+        S.nsearch += ncand;
+    }
+    bsync<NT>();
+}
+
+/* ------------------------------------------------------------------ */
+/* helpers shared by the elimination variants                          */
+/* ------------------------------------------------------------------ */
+
+/* squeeze out entries marked idx == -2 from [base, base+n) keeping order; one warp.
+ * Returns the new count (uniform). */
+__device__ __forceinline__ int warp_squeeze(int *idx, double *val, int base, int n) {
+    const int lane = threadIdx.x & 31;
+    int put = base;
+    for (int b = 0; b < n; b += 32) {
+        int pos = base + b + lane;
+        int ok = (b + lane) < n;
+        int i = ok ? idx[pos] : -2; double v = ok ? val[pos] : 0.0;
+        int keep = ok && i != -2;
+        unsigned km = __ballot_sync(FULLMASK, keep);
+        __syncwarp();
+        if (keep) { int d = put + __popc(km & lanemask_lt()); idx[d] = i; val[d] = v; }
+        put += __popc(km);
+        __syncwarp();
+    }
+    return put - base;
+}
+
+/* pivot.rs:1333-1381: empty column j whose max dropped below abstol.  One warp. */
+__device__ __forceinline__ void warp_remove_col(Shm &S, int j) {
+    Mat &M = S.M;
+    const int m = M.m, lane = threadIdx.x & 31;
+    const int cbeg = M.lbeg[j], cend = M.lend[j];
+    for (int pos = cbeg; pos < cend; pos++) {
+        const int i = M.w_idx[pos];
+        const int rb = M.lbeg[m + i], re = M.lend[m + i];
+        int where = -1;
+        for (int b = rb; b < re; b += 32) {
+            int q = b + lane;
+            int hit = q < re && M.w_idx[q] == j;
+            unsigned hm = __ballot_sync(FULLMASK, hit);
+            if (hm) { where = b + __ffs((int)hm) - 1; break; }
+        }
+        if (lane == 0) {
+            if (where < 0) { BLU_CHECK(S, 0); }
+            else {
+                M.w_idx[where] = M.w_idx[re - 1];
+                M.lend[m + i] = re - 1;
+                M.rkey[i] = mkkey(re - 1 - rb, S.rstamp++);
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        M.colpiv[j] = 0.0;
+        M.lend[j] = cbeg;
+        M.ckey[j] = mkkey(0, S.cstamp++);
+    }
+    __syncwarp();
+}
+
+/* pivot.rs:96-106: after a step, empty every touched column whose max is 0 or < abstol */
+template <int NT> __device__ void post_remove_cols(Shm &S, int rank) {
+    Mat &M = S.M;
+    if (S.need_remove) {
+        if ((threadIdx.x >> 5) == 0) {
+            const double abstol = M.prm.abstol;
+            for (int pos = M.u_begin[rank]; pos < M.u_begin[rank + 1]; pos++) {
+                int j = M.u_idx[pos];
+                double c = M.colpiv[j];
+                if (c == 0.0 || c < abstol) warp_remove_col(S, j);
+            }
+            if ((threadIdx.x & 31) == 0) S.need_remove = 0;
+        }
+        bsync<NT>();
+    }
+}
+
+/* common tail of every variant: pointers, pivot value, unlink pivot row/column */
+__device__ __forceinline__ void finish_step(Shm &S, int rank, int lput, int uput, double pivot,
+                                            int nz_col, int nz_row) {
+    Mat &M = S.M;
+    const int m = M.m, pc = S.pivot_col, pr = S.pivot_row;
+    M.l_begin_p[rank + 1] = lput;
+    M.u_begin[rank + 1] = uput;
+    M.colpiv[pc] = pivot;
+    M.lend[pc] = M.lbeg[pc];
+    M.lend[m + pr] = M.lbeg[m + pr];
+    M.ckey[pc] = KEY_INF;
+    M.rkey[pr] = KEY_INF;
+    S.ndead++;
+    S.factor_flops += (i64)(nz_col - 1) * (i64)(nz_row - 1);
+    S.elim_bytes += 12.0 * nz_col + 4.0 * nz_row + 12.0 * (nz_col - 1) + 12.0 * (nz_row - 1);
+    S.nelim_div += nz_col - 1;
+}
+
+/* ------------------------------------------------------------------ */
+/* pivot_any (pivot.rs:114-458) and pivot_small (pivot.rs:460-833)     */
+/* ------------------------------------------------------------------ */
+template <int NT> __device__ void pivot_general(Shm &S, const bool small) {
+    Mat &M = S.M;
+    const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int pc = S.pivot_col, pr = S.pivot_row, rank = S.rank;
+    const double droptol = M.prm.droptol, abstol = M.prm.abstol;
+    int cbeg = M.lbeg[pc], cend = M.lend[pc];
+    int rbeg = M.lbeg[m + pr], rend = M.lend[m + pr];
+    const int cnz1 = cend - cbeg - 1, rnz1 = rend - rbeg - 1;
+
+    /* prologue, pivot.rs:142-208: find the pivot in its column and row, bound the growth */
+    i64 grow = 0; int wc = -1, wr = -1;
+    for (int pos = cbeg + tid; pos < cend; pos += NT) {
+        int i = M.w_idx[pos];
+        if (i == pr) wc = pos;
+        else { int nz = M.lend[m + i] - M.lbeg[m + i]; grow += nz + rnz1 + slack_of(M.prm, nz + rnz1); }
+    }
+    for (int pos = rbeg + tid; pos < rend; pos += NT) {
+        int j = M.w_idx[pos];
+        if (j == pc) wr = pos;
+        else { int nz = M.lend[j] - M.lbeg[j]; grow += nz + cnz1 + slack_of(M.prm, nz + cnz1); }
+    }
+    grow = block_sum64<NT>(grow, S.kscr);
+    wc = block_max<NT>(wc, S.iscr);
+    wr = block_max<NT>(wr, S.iscr);
+    if (wc < 0 || wr < 0) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
+    if (tid == 0) {
+        int ti = M.w_idx[cbeg]; M.w_idx[cbeg] = M.w_idx[wc]; M.w_idx[wc] = ti;
+        double tv = M.w_val[cbeg]; M.w_val[cbeg] = M.w_val[wc]; M.w_val[wc] = tv;
+        ti = M.w_idx[rbeg]; M.w_idx[rbeg] = M.w_idx[wr]; M.w_idx[wr] = ti;
+    }
+    bsync<NT>();
+    if (!w_reserve<NT>(S, grow)) return;
+    cbeg = M.lbeg[pc]; cend = M.lend[pc];
+    rbeg = M.lbeg[m + pr]; rend = M.lend[m + pr];
+    const double pivot = M.w_val[cbeg];
+
+    /* stage the pivot column / row in shared memory when they fit */
+    const bool ccached = cnz1 + 1 <= S.cap, rcached = rnz1 + 1 <= S.cap;
+    const int *cidx = ccached ? S.cidx : M.w_idx + cbeg;
+    const double *cval = ccached ? S.cval : M.w_val + cbeg;
+    const int *ridx = rcached ? S.ridx : M.w_idx + rbeg;
+    if (ccached) for (int p = tid; p <= cnz1; p += NT) { S.cidx[p] = M.w_idx[cbeg + p]; S.cval[p] = M.w_val[cbeg + p]; }
+    if (rcached) for (int k = tid; k <= rnz1; k += NT) S.ridx[k] = M.w_idx[rbeg + k];
+    for (int p = 1 + tid; p <= cnz1; p += NT) M.rowmark[M.w_idx[cbeg + p]] = p;
+    for (int k = tid; k <= rnz1; k += NT) M.colmark[M.w_idx[rbeg + k]] = 1;
+    double *work = ccached ? S.work + (size_t)wid * S.cap : M.gwork + (size_t)wid * m;
+    if (ccached) for (int p = lane; p <= cnz1; p += 32) work[p] = 0.0;
+    if (tid == 0) { S.flag_a = 0; S.flag_b = 0; }
+    bsync<NT>();
+
+    const int ubase = M.u_begin[rank];
+    const i64 cbase = S.cstamp, rbase = S.rstamp;
+    double acc_bytes = 0.0;
+
+    /* column file update, pivot.rs:219-331 / 569-693: one warp per column of the pivot row */
+    for (int k = 1 + wid; k <= rnz1; k += NW) {
+        const int j = ridx[k];
+        int beg = M.lbeg[j], end = M.lend[j], cap = M.lcap[j];
+        const int oldnz = end - beg;
+        int put = beg, where = -1;
+        double cmx = 0.0;
+        for (int base = beg; base < end; base += 32) {
+            int pos = base + lane;
+            int valid = pos < end;
+            int i = valid ? M.w_idx[pos] : 0;
+            double x = valid ? M.w_val[pos] : 0.0;
+            int mk = valid ? M.rowmark[i] : 0;
+            int isT = valid && mk == 0;
+            if (valid && mk > 0) work[mk] = x;
+            unsigned tm = __ballot_sync(FULLMASK, isT);
+            int dst = put + __popc(tm & lanemask_lt());
+            if (isT) { if (i == pr) where = dst; else { double a = fabs(x); if (a > cmx) cmx = a; } }
+            __syncwarp();
+            if (isT) { M.w_idx[dst] = i; M.w_val[dst] = x; }
+            put += __popc(tm);
+        }
+        where = warp_max(where);
+        __syncwarp();
+        const double xrj = M.w_val[where];
+        __syncwarp();
+        if (lane == 0 && where != beg) { M.w_idx[where] = M.w_idx[beg]; M.w_val[where] = M.w_val[beg]; }
+        __syncwarp();
+        const int nT = put - beg;
+        beg += 1;                            /* the pivot-row entry leaves the line */
+        if (cap - put < cnz1) {              /* move the line to the end of the file */
+            int nz = put - beg;
+            int room = cnz1 + slack_of(M.prm, nT + cnz1);
+            int np = 0;
+            if (lane == 0) { np = atomicAdd(&S.w_used, nz + room); atomicAdd(&S.nexpand, 1); }
+            np = __shfl_sync(FULLMASK, np, 0);
+            for (int t = lane; t < nz; t += 32) { M.w_idx[np + t] = M.w_idx[beg + t]; M.w_val[np + t] = M.w_val[beg + t]; }
+            beg = np; put = np + nz; cap = np + nz + room;
+            __syncwarp();
+        }
+        const double a = __ddiv_rn(xrj, pivot);
+        u64 cmask = 0;
+        for (int base = 1; base <= cnz1; base += 32) {
+            int p = base + lane;
+            int valid = p <= cnz1;
+            double x = 0.0;
+            if (valid) { x = __dsub_rn(work[p], __dmul_rn(a, cval[p])); work[p] = 0.0; }
+            if (!small) {
+                if (valid) {
+                    M.w_idx[put + p - 1] = cidx[p]; M.w_val[put + p - 1] = x;
+                    double ax = fabs(x); if (ax > cmx) cmx = ax;
+                }
+            } else {
+                int keep = valid && fabs(x) > droptol;
+                unsigned km = __ballot_sync(FULLMASK, keep);
+                unsigned dm = __ballot_sync(FULLMASK, valid && !keep);
+                if (keep) {
+                    int d = put + __popc(km & lanemask_lt());
+                    M.w_idx[d] = cidx[p]; M.w_val[d] = x;
+                    double ax = fabs(x); if (ax > cmx) cmx = ax;
+                }
+                cmask |= (u64)dm << (base - 1);
+                put += __popc(km);
+            }
+        }
+        if (!small) put += cnz1;
+        cmx = warp_maxd(cmx);
+        if (lane == 0) {
+            M.lbeg[j] = beg; M.lend[j] = put; M.lcap[j] = cap;
+            M.colpiv[j] = cmx;
+            M.ckey[j] = mkkey(put - beg, cbase + k);
+            if (small) M.cancelled[k - 1] = cmask;
+            if (fabs(xrj) > droptol) { M.u_idx[ubase + k - 1] = j; M.u_val[ubase + k - 1] = xrj; }
+            else { M.u_idx[ubase + k - 1] = -2; M.u_val[ubase + k - 1] = 0.0; S.flag_a = 1; }
+            if (cmx == 0.0 || cmx < abstol) S.need_remove = 1;
+            acc_bytes += 12.0 * (oldnz + put - beg);
+        }
+        __syncwarp();
+    }
+    if (small) bsync<NT>();      /* the row update needs every column's cancellation mask */
+
+    /* row file update, pivot.rs:335-401 / 697-774: one warp per row of the pivot column */
+    for (int p = 1 + wid; p <= cnz1; p += NW) {
+        const int i = cidx[p];
+        const int line = m + i;
+        int beg = M.lbeg[line], end = M.lend[line], cap = M.lcap[line];
+        const int oldnz = end - beg;
+        int put = beg;
+        for (int base = beg; base < end; base += 32) {
+            int pos = base + lane;
+            int valid = pos < end;
+            int j = valid ? M.w_idx[pos] : 0;
+            int keep = valid && M.colmark[j] == 0;
+            unsigned km = __ballot_sync(FULLMASK, keep);
+            __syncwarp();
+            if (keep) M.w_idx[put + __popc(km & lanemask_lt())] = j;
+            put += __popc(km);
+        }
+        __syncwarp();
+        if (cap - put < rnz1) {
+            int nz = put - beg;
+            int room = rnz1 + slack_of(M.prm, nz + rnz1);
+            int np = 0;
+            if (lane == 0) { np = atomicAdd(&S.w_used, nz + room); atomicAdd(&S.nexpand, 1); }
+            np = __shfl_sync(FULLMASK, np, 0);
+            for (int t = lane; t < nz; t += 32) M.w_idx[np + t] = M.w_idx[beg + t];
+            beg = np; put = np + nz; cap = np + nz + room;
+            __syncwarp();
+        }
+        if (!small) {
+            for (int k = 1 + lane; k <= rnz1; k += 32) M.w_idx[put + k - 1] = ridx[k];
+            put += rnz1;
+        } else {
+            for (int base = 1; base <= rnz1; base += 32) {
+                int k = base + lane;
+                int keep = k <= rnz1 && ((M.cancelled[k - 1] >> (p - 1)) & 1ull) == 0;
+                unsigned km = __ballot_sync(FULLMASK, keep);
+                if (keep) M.w_idx[put + __popc(km & lanemask_lt())] = ridx[k];
+                put += __popc(km);
+            }
+        }
+        if (lane == 0) {
+            M.lbeg[line] = beg; M.lend[line] = put; M.lcap[line] = cap;
+            M.rkey[i] = mkkey(put - beg, rbase + p);
+            acc_bytes += 4.0 * (oldnz + put - beg);
+        }
+        __syncwarp();
+    }
+
+    /* L column, pivot.rs:403-415 (tentative slots, squeezed if something was dropped) */
+    const int lbase = M.l_begin_p[rank];
+    for (int p = 1 + tid; p <= cnz1; p += NT) {
+        double x = __ddiv_rn(cval[p], pivot);
+        if (fabs(x) > droptol) { M.l_idx[lbase + p - 1] = cidx[p]; M.l_val[lbase + p - 1] = x; }
+        else { M.l_idx[lbase + p - 1] = -2; M.l_val[lbase + p - 1] = 0.0; S.flag_b = 1; }
+    }
+    if (acc_bytes != 0.0) atomicAdd(&S.elim_bytes, acc_bytes);
+    bsync<NT>();
+    /* clear marks */
+    for (int p = 1 + tid; p <= cnz1; p += NT) M.rowmark[cidx[p]] = 0;
+    for (int k = tid; k <= rnz1; k += NT) M.colmark[ridx[k]] = 0;
+    if (wid == 0) {
+        int ln = cnz1, un = rnz1;
+        if (S.flag_b) ln = warp_squeeze(M.l_idx, M.l_val, lbase, cnz1);
+        if (S.flag_a) un = warp_squeeze(M.u_idx, M.u_val, ubase, rnz1);
+        if (lane == 0) {
+            M.l_idx[lbase + ln] = -1;
+            finish_step(S, rank, lbase + ln + 1, ubase + un, pivot, cnz1 + 1, rnz1 + 1);
+            S.cstamp = cbase + rnz1 + 1;
+            S.rstamp = rbase + cnz1 + 1;
+        }
+    }
+    bsync<NT>();
+}
+
+/* ------------------------------------------------------------------ */
+/* pivot_singleton_row, pivot.rs:835-926                               */
+/* ------------------------------------------------------------------ */
+template <int NT> __device__ void pivot_singleton_row(Shm &S) {
+    Mat &M = S.M;
+    const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int pc = S.pivot_col, pr = S.pivot_row, rank = S.rank;
+    const double droptol = M.prm.droptol;
+    const int cbeg = M.lbeg[pc], cend = M.lend[pc];
+    const int n = cend - cbeg;
+    int wc = -1;
+    for (int pos = cbeg + tid; pos < cend; pos += NT) if (M.w_idx[pos] == pr) wc = pos;
+    wc = block_max<NT>(wc, S.iscr);
+    if (wc < 0) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
+    const double pivot = M.w_val[wc];
+    const int lbase = M.l_begin_p[rank];
+    const i64 rbase = S.rstamp;
+    if (tid == 0) S.flag_b = 0;
+    bsync<NT>();
+    /* L in column order, skipping the pivot: slot = position minus one behind the pivot */
+    for (int pos = cbeg + tid; pos < cend; pos += NT) {
+        if (pos == wc) continue;
+        int slot = lbase + (pos - cbeg) - (pos > wc ? 1 : 0);
+        double x = __ddiv_rn(M.w_val[pos], pivot);
+        if (fabs(x) > droptol) { M.l_idx[slot] = M.w_idx[pos]; M.l_val[slot] = x; }
+        else { M.l_idx[slot] = -2; M.l_val[slot] = 0.0; S.flag_b = 1; }
+    }
+    /* each row of the column loses the pivot column: move-last-into-hole, re-stamp in column order */
+    double acc_bytes = 0.0;
+    for (int q = wid; q < n; q += NW) {
+        const int pos = cbeg + q;
+        const int i = M.w_idx[pos];
+        if (i == pr) continue;
+        const int rb = M.lbeg[m + i], re = M.lend[m + i];
+        int where = -1;
+        for (int b = rb; b < re; b += 32) {
+            int t = b + lane;
+            int hit = t < re && M.w_idx[t] == pc;
+            unsigned hm = __ballot_sync(FULLMASK, hit);
+            if (hm) { where = b + __ffs((int)hm) - 1; break; }
+        }
+        if (lane == 0) {
+            if (where < 0) { BLU_CHECK(S, 0); }
+            else {
+                M.w_idx[where] = M.w_idx[re - 1];
+                M.lend[m + i] = re - 1;
+                M.rkey[i] = mkkey(re - 1 - rb, rbase + q);
+                acc_bytes += 4.0 * (2 * (re - rb) - 1);
+            }
+        }
+        __syncwarp();
+    }
+    if (acc_bytes != 0.0) atomicAdd(&S.elim_bytes, acc_bytes);
+    bsync<NT>();
+    if (wid == 0) {
+        int ln = n - 1;
+        if (S.flag_b) ln = warp_squeeze(M.l_idx, M.l_val, lbase, n - 1);
+        if (lane == 0) {
+            M.l_idx[lbase + ln] = -1;
+            finish_step(S, rank, lbase + ln + 1, M.u_begin[rank], pivot, n, 1);
+            S.rstamp = rbase + n;
+        }
+    }
+    bsync<NT>();
+}
+
+/* ------------------------------------------------------------------ */
+/* pivot_singleton_col, pivot.rs:928-1025                              */
+/* ------------------------------------------------------------------ */
+template <int NT> __device__ void pivot_singleton_col(Shm &S) {
+    Mat &M = S.M;
+    const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int pc = S.pivot_col, pr = S.pivot_row, rank = S.rank;
+    const double droptol = M.prm.droptol, abstol = M.prm.abstol;
+    const int cbeg = M.lbeg[pc];
+    const int rbeg = M.lbeg[m + pr], rend = M.lend[m + pr];
+    const int n = rend - rbeg;
+    const double pivot = M.w_val[cbeg];
+    int wr = -1;
+    for (int pos = rbeg + tid; pos < rend; pos += NT) if (M.w_idx[pos] == pc) wr = pos;
+    wr = block_max<NT>(wr, S.iscr);
+    if (wr < 0) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
+    const int ubase = M.u_begin[rank];
+    const i64 cbase = S.cstamp;
+    if (tid == 0) S.flag_a = 0;
+    bsync<NT>();
+    double acc_bytes = 0.0;
+    for (int q = wid; q < n; q += NW) {
+        const int rpos = rbeg + q;
+        if (rpos == wr) continue;
+        const int j = M.w_idx[rpos];
+        const int beg = M.lbeg[j], end = M.lend[j];
+        int where = -1; double cmx = 0.0, xrj = 0.0;
+        for (int b = beg; b < end; b += 32) {
+            int t = b + lane;
+            if (t < end) {
+                double v = M.w_val[t];
+                if (M.w_idx[t] == pr) { where = t; xrj = v; }
+                else { double a = fabs(v); if (a > cmx) cmx = a; }
+            }
+        }
+        where = warp_max(where);
+        cmx = warp_maxd(cmx);
+        if (where < 0) { if (lane == 0) BLU_CHECK(S, 0); continue; }
+        xrj = M.w_val[where];
+        __syncwarp();
+        if (lane == 0) {
+            int slot = ubase + q - (rpos > wr ? 1 : 0);
+            if (fabs(xrj) > droptol) { M.u_idx[slot] = j; M.u_val[slot] = xrj; }
+            else { M.u_idx[slot] = -2; M.u_val[slot] = 0.0; S.flag_a = 1; }
+            M.w_idx[where] = M.w_idx[end - 1];
+            M.w_val[where] = M.w_val[end - 1];
+            M.lend[j] = end - 1;
+            M.ckey[j] = mkkey(end - 1 - beg, cbase + q);
+            M.colpiv[j] = cmx;
+            if (cmx == 0.0 || cmx < abstol) S.need_remove = 1;
+            acc_bytes += 12.0 * (2 * (end - beg) - 1);
+        }
+        __syncwarp();
+    }
+    if (acc_bytes != 0.0) atomicAdd(&S.elim_bytes, acc_bytes);
+    bsync<NT>();
+    if (wid == 0) {
+        int un = n - 1;
+        if (S.flag_a) un = warp_squeeze(M.u_idx, M.u_val, ubase, n - 1);
+        if (lane == 0) {
+            int lbase = M.l_begin_p[rank];
+            M.l_idx[lbase] = -1;
+            finish_step(S, rank, lbase + 1, ubase + un, pivot, 1, n);
+            S.cstamp = cbase + n;
+        }
+    }
+    bsync<NT>();
+}
+
+/* ------------------------------------------------------------------ */
+/* pivot_doubleton_col, pivot.rs:1027-1331                             */
+/* ------------------------------------------------------------------ */
+template <int NT> __device__ void pivot_doubleton_col(Shm &S) {
+    Mat &M = S.M;
+    const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int pc = S.pivot_col, pr = S.pivot_row, rank = S.rank;
+    const double droptol = M.prm.droptol, abstol = M.prm.abstol;
+    int cbeg = M.lbeg[pc];
+    int rbeg = M.lbeg[m + pr], rend = M.lend[m + pr];
+    const int rnz1 = rend - rbeg - 1;
+
+    /* pivot to the front of column and row, pivot.rs:1068-1082 */
+    int wr = -1;
+    for (int pos = rbeg + tid; pos < rend; pos += NT) if (M.w_idx[pos] == pc) wr = pos;
+    wr = block_max<NT>(wr, S.iscr);
+    if (wr < 0) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
+    if (tid == 0) {
+        if (M.w_idx[cbeg] != pr) {
+            int ti = M.w_idx[cbeg]; M.w_idx[cbeg] = M.w_idx[cbeg + 1]; M.w_idx[cbeg + 1] = ti;
+            double tv = M.w_val[cbeg]; M.w_val[cbeg] = M.w_val[cbeg + 1]; M.w_val[cbeg + 1] = tv;
+        }
+        int ti = M.w_idx[rbeg]; M.w_idx[rbeg] = M.w_idx[wr]; M.w_idx[wr] = ti;
+        S.flag_a = 0; S.flag_b = 0;
+    }
+    bsync<NT>();
+    /* room for the other row, pivot.rs:1087-1111 */
+    {
+        const int orow = M.w_idx[cbeg + 1];
+        int nz = M.lend[m + orow] - M.lbeg[m + orow];
+        i64 grow = nz + rnz1 + slack_of(M.prm, nz + rnz1);
+        if (!w_reserve<NT>(S, grow)) return;
+    }
+    cbeg = M.lbeg[pc]; rbeg = M.lbeg[m + pr]; rend = M.lend[m + pr];
+    const double pivot = M.w_val[cbeg];
+    const int other_row = M.w_idx[cbeg + 1];
+    const double other_value = M.w_val[cbeg + 1];
+    const double q_op = __ddiv_rn(other_value, pivot);
+    const int ubase = M.u_begin[rank];
+    const i64 cbase = S.cstamp;
+    int *kind = M.tmpi;          /* per column of the pivot row: 1 = fill-in, 2 = cancelled */
+    double acc_bytes = 0.0;
+
+    /* column file update, pivot.rs:1115-1222 */
+    for (int k = 1 + wid; k <= rnz1; k += NW) {
+        const int j = M.w_idx[rbeg + k];
+        const int beg = M.lbeg[j];
+        int end = M.lend[j];
+        const int oldnz = end - beg;
+        int wp = -1, wo = -1; double cmx = 0.0;
+        for (int b = beg; b < end; b += 32) {
+            int t = b + lane;
+            if (t < end) {
+                int i = M.w_idx[t];
+                if (i == pr) wp = t;
+                else if (i == other_row) wo = t;
+                else { double a = fabs(M.w_val[t]); if (a > cmx) cmx = a; }
+            }
+        }
+        wp = warp_max(wp); wo = warp_max(wo); cmx = warp_maxd(cmx);
+        if (wp < 0) { if (lane == 0) BLU_CHECK(S, 0); continue; }
+        __syncwarp();
+        if (lane == 0) {
+            const double xrj = M.w_val[wp];
+            if (fabs(xrj) > droptol) { M.u_idx[ubase + k - 1] = j; M.u_val[ubase + k - 1] = xrj; }
+            else { M.u_idx[ubase + k - 1] = -2; M.u_val[ubase + k - 1] = 0.0; S.flag_a = 1; }
+            int kd = 0;
+            if (wo < 0) {
+                /* fill-in takes the slot of the pivot-row entry: no re-bucketing */
+                double x = __dmul_rn(-xrj, q_op);
+                double xa = fabs(x);
+                if (xa > droptol) {
+                    M.w_idx[wp] = other_row; M.w_val[wp] = x;
+                    kd = 1;
+                    if (xa > cmx) cmx = xa;
+                } else {
+                    end--;
+                    M.w_idx[wp] = M.w_idx[end]; M.w_val[wp] = M.w_val[end];
+                    M.lend[j] = end;
+                    M.ckey[j] = mkkey(end - beg, cbase + k);
+                }
+            } else {
+                end--;
+                M.w_idx[wp] = M.w_idx[end]; M.w_val[wp] = M.w_val[end];
+                if (wo == end) wo = wp;
+                double v = __dsub_rn(M.w_val[wo], __dmul_rn(xrj, q_op));
+                M.w_val[wo] = v;
+                double xa = fabs(v);
+                if (xa <= droptol) {
+                    end--;
+                    M.w_idx[wo] = M.w_idx[end]; M.w_val[wo] = M.w_val[end];
+                    kd = 2; S.flag_b = 1;
+                } else if (xa > cmx) cmx = xa;
+                M.lend[j] = end;
+                M.ckey[j] = mkkey(end - beg, cbase + k);
+            }
+            kind[k] = kd;
+            M.colpiv[j] = cmx;
+            if (cmx == 0.0 || cmx < abstol) S.need_remove = 1;
+            acc_bytes += 12.0 * (oldnz + end - beg);
+        }
+        __syncwarp();
+    }
+    if (acc_bytes != 0.0) atomicAdd(&S.elim_bytes, acc_bytes);
+    bsync<NT>();
+
+    /* row file update of the other row, pivot.rs:1228-1293; warp 0 */
+    if (wid == 0) {
+        const int line = m + other_row;
+        int beg = M.lbeg[line], end = M.lend[line], cap = M.lcap[line];
+        const int oldnz = end - beg;
+        if (S.flag_b) {
+            /* order-preserving removal of the pivot column and of cancelled columns */
+            for (int k = 1 + lane; k <= rnz1; k += 32) if (kind[k] == 2) M.colmark[M.w_idx[rbeg + k]] = 1;
+            if (lane == 0) M.colmark[pc] = 1;
+            __syncwarp();
+            int put = beg;
+            for (int b = beg; b < end; b += 32) {
+                int t = b + lane;
+                int valid = t < end;
+                int j = valid ? M.w_idx[t] : 0;
+                int keep = valid && M.colmark[j] == 0;
+                unsigned km = __ballot_sync(FULLMASK, keep);
+                __syncwarp();
+                if (keep) M.w_idx[put + __popc(km & lanemask_lt())] = j;
+                put += __popc(km);
+            }
+            __syncwarp();
+            for (int k = 1 + lane; k <= rnz1; k += 32) if (kind[k] == 2) M.colmark[M.w_idx[rbeg + k]] = 0;
+            if (lane == 0) M.colmark[pc] = 0;
+            end = put;
+            __syncwarp();
+        } else {
+            int where = -1;
+            for (int b = beg; b < end; b += 32) {
+                int t = b + lane;
+                int hit = t < end && M.w_idx[t] == pc;
+                unsigned hm = __ballot_sync(FULLMASK, hit);
+                if (hm) { where = b + __ffs((int)hm) - 1; break; }
+            }
+            if (where < 0) { if (lane == 0) BLU_CHECK(S, 0); }
+            else { if (lane == 0) M.w_idx[where] = M.w_idx[end - 1]; end--; }
+            __syncwarp();
+        }
+        /* count fill-in columns, make room, append them in pivot-row order */
+        int nfill = 0;
+        for (int k = 1 + lane; k <= rnz1; k += 32) nfill += kind[k] == 1;
+        nfill = warp_sum(nfill);
+        if (nfill > cap - end) {
+            int nz = end - beg;
+            int room = nfill + slack_of(M.prm, nz + nfill);
+            int np = 0;
+            if (lane == 0) { np = atomicAdd(&S.w_used, nz + room); S.nexpand++; }
+            np = __shfl_sync(FULLMASK, np, 0);
+            for (int t = lane; t < nz; t += 32) M.w_idx[np + t] = M.w_idx[beg + t];
+            beg = np; end = np + nz; cap = np + nz + room;
+            __syncwarp();
+        }
+        for (int b = 1; b <= rnz1; b += 32) {
+            int k = b + lane;
+            int f = k <= rnz1 && kind[k] == 1;
+            unsigned fm = __ballot_sync(FULLMASK, f);
+            if (f) M.w_idx[end + __popc(fm & lanemask_lt())] = M.w_idx[rbeg + k];
+            end += __popc(fm);
+        }
+        __syncwarp();
+        int un = rnz1;
+        if (S.flag_a) un = warp_squeeze(M.u_idx, M.u_val, ubase, rnz1);
+        if (lane == 0) {
+            M.lbeg[line] = beg; M.lend[line] = end; M.lcap[line] = cap;
+            M.rkey[other_row] = mkkey(end - beg, S.rstamp);
+            S.rstamp += 1;
+            S.elim_bytes += 4.0 * (oldnz + end - beg);
+            /* L column, pivot.rs:1296-1305 */
+            int lput = M.l_begin_p[rank];
+            if (fabs(q_op) > droptol) { M.l_idx[lput] = other_row; M.l_val[lput] = q_op; lput++; }
+            M.l_idx[lput++] = -1;
+            finish_step(S, rank, lput, ubase + un, pivot, 2, rnz1 + 1);
+            S.cstamp = cbase + rnz1 + 1;
+        }
+    }
+    bsync<NT>();
+}
+
+/* ------------------------------------------------------------------ */
+/* pivot dispatcher (pivot.rs:48-112) + driver (factorize_bump.rs)     */
+/* ------------------------------------------------------------------ */
+template <int NT> __device__ void phase_bump(Shm &S) {
+    Mat &M = S.M;
+    const int m = M.m, tid = threadIdx.x;
+    while (S.rank + S.rankdef < m) {
+        markowitz_search<NT>(S);
+        if (S.status != BLU_OK) return;
+        const int pc = S.pivot_col, pr = S.pivot_row;
+        if (pr < 0) {
+            /* empty column: drop it, no pivot (factorize_bump.rs:23-31) */
+            bsync<NT>();
+            if (tid == 0) { M.ckey[pc] = KEY_INF; S.ndead++; S.rankdef++; }
+            bsync<NT>();
+            continue;
+        }
+        const int rank = S.rank;
+        const int nz_col = M.lend[pc] - M.lbeg[pc];
+        const int nz_row = M.lend[m + pr] - M.lbeg[m + pr];
+        /* room in L and U, pivot.rs:69-81 */
+        {
+            int room = M.l_mem - M.l_begin_p[rank];
+            int st = BLU_OK;
+            if (room < nz_col) { if (tid == 0) M.info->addmem_l = nz_col - room; st = BLU_REALLOCATE; }
+            room = M.u_mem - M.u_begin[rank];
+            if (room < nz_row - 1) { if (tid == 0) M.info->addmem_u = nz_row - 1 - room; st = BLU_REALLOCATE; }
+            if (st != BLU_OK) { bsync<NT>(); if (tid == 0) S.status = st; bsync<NT>(); return; }
+        }
+        if (nz_row == 1) pivot_singleton_row<NT>(S);
+        else if (nz_col == 1) pivot_singleton_col<NT>(S);
+        else if (nz_col == 2) pivot_doubleton_col<NT>(S);
+        else pivot_general<NT>(S, nz_col - 1 <= MAXROW_SMALL);
+        if (S.status != BLU_OK) return;
+        post_remove_cols<NT>(S, rank);
+        if (tid == 0) {
+            M.pinv[pr] = rank; M.qinv[pc] = rank;
+            S.rank = rank + 1;
+        }
+        bsync<NT>();
+        if (S.status != BLU_OK) return;
+    }
+}
+
+#endif

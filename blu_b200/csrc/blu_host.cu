@@ -1,0 +1,576 @@
+/* blu_host.cu -- host side of libblu_b200.so: owns device memory, copies, launches.
+ * Mirrors struct BLU (reference src/blu.rs:9-395): the Reallocate protocol is hidden
+ * here exactly as BLU::factorize / solve_for_update / update hide it (blu.rs:95-118,
+ * 257-294, 319-334), by growing the L/U/W stores (lu_realloc_obj, blu.rs:345-377)
+ * and re-running. */
+#ifdef BLU_EMU
+#include "cuda_emu.h"
+#endif
+#include "blu_types.h"
+#include "blu_dev_common.cuh"
+#include "blu_factor_build.cuh"
+#include "blu_solve.cuh"
+#include "blu_sparse.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+
+#define PADDING 64 /* slack entries after the L/U/W stores: warp-wide terminator scans read ahead */
+
+struct blu_b200 {
+    int device;
+    int single;                 /* created by blu_create (object API) */
+    BluDev d;
+    double realloc_factor;
+    int nthreads;               /* CTA size of the factorization kernel */
+    int cap;                    /* smem line cache entries */
+    std::vector<void *> allocs; /* every device allocation */
+    std::vector<void **> store_ptrs;
+    /* resizable stores */
+    cudaStream_t stream; int own_stream;
+    cudaEvent_t ev0, ev1;
+    double last_ms[2];
+    int64_t launches;
+    int nrealloc;
+    /* device staging for B, rhs, lhs, status */
+    int64_t *db_begin, *db_end, *db_i; double *db_x; int64_t b_cap;
+    double *d_rhs, *d_lhs; int *d_status;
+    /* sparse-solve staging (object API) */
+    int64_t *d_irhs; double *d_xrhs; int64_t *d_ilhs; int *d_scal;
+    /* get_factors staging */
+    int64_t *gf_i; double *gf_x; int64_t gf_cap;
+    std::vector<BluInfo> hinfo;
+    std::vector<int64_t> hb_begin, hb_end, hb_i; std::vector<double> hb_x; /* compact staging (object API) */
+    int have_b;                 /* B resident on device (for re-runs) */
+    double time_factorize, time_solve, time_update;
+};
+
+static int cuda_ok(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) {
+        fprintf(stderr, "blu_b200: CUDA error in %s: %s\n", what, cudaGetErrorString(e));
+        return 0;
+    }
+    return 1;
+}
+#define CK(call) do { if (!cuda_ok((call), #call)) return BLU_ERROR_CUDA; } while (0)
+
+template <typename T> static int dalloc(blu_b200 *o, T **p, size_t n) {
+    void *q = nullptr;
+    if (cudaMalloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return BLU_ERROR_OUT_OF_MEMORY; }
+    if (cudaMemset(q, 0, (n ? n : 1) * sizeof(T)) != cudaSuccess) return BLU_ERROR_CUDA;
+    *p = (T *)q;
+    o->allocs.push_back(q);
+    return BLU_OK;
+}
+static void dfree(blu_b200 *o, void *p) {
+    if (!p) return;
+    auto it = std::find(o->allocs.begin(), o->allocs.end(), p);
+    if (it != o->allocs.end()) o->allocs.erase(it);
+    cudaFree(p);
+}
+
+static int alloc_stores(blu_b200 *o) {
+    BluDev &d = o->d;
+    const size_t n = (size_t)d.nmat;
+    int st;
+    if ((st = dalloc(o, &d.l_idx, n * d.l_mem + PADDING))) return st;
+    if ((st = dalloc(o, &d.l_val, n * d.l_mem + PADDING))) return st;
+    if ((st = dalloc(o, &d.u_idx, n * d.u_mem + PADDING))) return st;
+    if ((st = dalloc(o, &d.u_val, n * d.u_mem + PADDING))) return st;
+    if ((st = dalloc(o, &d.w_idx, n * 2 * d.w_mem + PADDING))) return st;
+    if ((st = dalloc(o, &d.w_val, n * 2 * d.w_mem + PADDING))) return st;
+    return BLU_OK;
+}
+static void free_stores(blu_b200 *o) {
+    BluDev &d = o->d;
+    dfree(o, d.l_idx); dfree(o, d.l_val); dfree(o, d.u_idx); dfree(o, d.u_val); dfree(o, d.w_idx); dfree(o, d.w_val);
+    d.l_idx = d.u_idx = d.w_idx = nullptr; d.l_val = d.u_val = d.w_val = nullptr;
+}
+
+static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_cap, int device, int single) {
+    if (!out || m < 1 || nmat < 1 || bnz_cap < 0 || m > 0x3fffffff) return BLU_ERROR_INVALID_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        fprintf(stderr, "blu_b200: no CUDA device (this library has no CPU path)\n");
+        return BLU_ERROR_CUDA;
+    }
+    if (device >= 0) CK(cudaSetDevice(device)); else CK(cudaGetDevice(&device));
+    blu_b200 *o = new blu_b200();
+    o->device = device; o->single = single;
+    o->realloc_factor = 1.5;   /* blu.rs:68 */
+    o->nthreads = 128; o->cap = 256;
+    o->launches = 0; o->nrealloc = 0; o->last_ms[0] = o->last_ms[1] = 0.0;
+    o->have_b = 0;
+    o->time_factorize = o->time_solve = o->time_update = 0.0;
+    BluDev &d = o->d;
+    memset(&d, 0, sizeof d);
+    d.m = (int)m; d.nmat = (int)nmat; d.bnz_cap = bnz_cap < 1 ? 1 : bnz_cap;
+    /* lu.rs:245-259.  The reference starts every store at b_nz and grows on demand; the
+     * device build starts larger because a Reallocate costs a full re-run here. */
+    d.l_mem = d.u_mem = 8 * d.bnz_cap + 4 * m;
+    d.w_mem = 8 * d.bnz_cap + 8 * m;
+    d.prm.droptol = 1e-20; d.prm.abstol = 1e-14; d.prm.reltol = 0.1;
+    d.prm.nzbias = 1; d.prm.maxsearch = 3; d.prm.pad = 4; d.prm.stretch = 0.3;
+    d.prm.compress_thres = 0.5; d.prm.sparse_thres = 0.05; d.prm.search_rows = 0;
+    d.gwork_warps = 32;
+    const size_t n = (size_t)nmat, M = (size_t)m;
+    int st = BLU_OK;
+#define A(p, cnt) if (st == BLU_OK) st = dalloc(o, &(p), (cnt))
+    A(d.bt_ptr, n * (M + 1)); A(d.bt_idx, n * d.bnz_cap); A(d.bt_val, n * d.bnz_cap);
+    A(d.pinv, n * M); A(d.qinv, n * M); A(d.prank, n * M); A(d.qrank, n * M);
+    A(d.colpiv, n * M); A(d.rowpiv, n * M);
+    A(d.lbeg, n * 2 * M); A(d.lend, n * 2 * M); A(d.lcap, n * 2 * M);
+    A(d.ckey, n * M); A(d.rkey, n * M);
+    A(d.l_begin_p, n * (M + 1)); A(d.u_begin, n * (M + 1)); A(d.l_begin, n * (M + 1));
+    A(d.lt_begin, n * (M + 1)); A(d.lt_begin_p, n * (M + 1)); A(d.p, n * (M + 1));
+    A(d.r_begin, n * (M + 1)); A(d.eta_row, n * (M + 1));
+    A(d.pivotcol, n * (2 * M + 2)); A(d.pivotrow, n * (2 * M + 2));
+    A(d.rowmark, n * M); A(d.colmark, n * M); A(d.marked, n * M);
+    A(d.iwork1, n * (2 * M + 2)); A(d.pstack, n * M); A(d.acols, n * M); A(d.tmpi, n * (4 * M + 4));
+    A(d.cancelled, n * M); A(d.work0, n * M); A(d.work1, n * M);
+    A(d.gwork, n * (size_t)d.gwork_warps * M);
+    A(d.info, n);
+    A(o->db_begin, n * M); A(o->db_end, n * M);
+    A(o->d_rhs, n * M); A(o->d_lhs, n * M); A(o->d_status, n);
+    if (single) { A(o->d_irhs, M); A(o->d_xrhs, M); A(o->d_ilhs, M); A(o->d_scal, 16); }
+#undef A
+    o->b_cap = 0; o->db_i = nullptr; o->db_x = nullptr;
+    o->gf_i = nullptr; o->gf_x = nullptr; o->gf_cap = 0;
+    if (st == BLU_OK) st = alloc_stores(o);
+    if (st == BLU_OK) {
+        /* nupdate = None until the first factorization (lu.rs:329-331) */
+        o->hinfo.assign(n, BluInfo());
+        for (auto &I : o->hinfo) { memset(&I, 0, sizeof I); I.nupdate = -1; I.m = (int)m; I.ftran_for_update = I.btran_for_update = -1; I.update_cost_denom = 1.0; }
+        if (cudaMemcpy(d.info, o->hinfo.data(), n * sizeof(BluInfo), cudaMemcpyHostToDevice) != cudaSuccess) st = BLU_ERROR_CUDA;
+    }
+    if (st == BLU_OK && cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) != cudaSuccess) st = BLU_ERROR_CUDA;
+    o->own_stream = 1;
+#ifndef BLU_EMU
+    if (st == BLU_OK && (cudaEventCreate(&o->ev0) != cudaSuccess || cudaEventCreate(&o->ev1) != cudaSuccess)) st = BLU_ERROR_CUDA;
+#endif
+    if (st != BLU_OK) {
+        for (void *p : o->allocs) cudaFree(p);
+        delete o;
+        return st;
+    }
+    *out = o;
+    return BLU_OK;
+}
+
+static void destroy_common(blu_b200 *o) {
+    if (!o) return;
+    cudaSetDevice(o->device);
+    cudaStreamSynchronize(o->stream);
+    for (void *p : o->allocs) cudaFree(p);
+#ifndef BLU_EMU
+    cudaEventDestroy(o->ev0); cudaEventDestroy(o->ev1);
+#endif
+    if (o->own_stream) cudaStreamDestroy(o->stream);
+    delete o;
+}
+
+static int ensure_b_cap(blu_b200 *o, int64_t total) {
+    if (total <= o->b_cap) return BLU_OK;
+    dfree(o, o->db_i); dfree(o, o->db_x);
+    o->db_i = nullptr; o->db_x = nullptr;
+    int st = dalloc(o, &o->db_i, (size_t)total);
+    if (st == BLU_OK) st = dalloc(o, &o->db_x, (size_t)total);
+    if (st == BLU_OK) o->b_cap = total;
+    return st;
+}
+
+static void timer_start(blu_b200 *o) {
+#ifndef BLU_EMU
+    cudaEventRecord(o->ev0, o->stream);
+#endif
+}
+static void timer_stop(blu_b200 *o, int which) {
+#ifndef BLU_EMU
+    cudaEventRecord(o->ev1, o->stream);
+    cudaEventSynchronize(o->ev1);
+    float ms = 0; cudaEventElapsedTime(&ms, o->ev0, o->ev1);
+    o->last_ms[which] = ms;
+#else
+    o->last_ms[which] = 0.0;
+#endif
+}
+
+template <int NT> static int launch_factorize_nt(blu_b200 *o) {
+    const size_t smem = blu_factor_smem_bytes(o->cap, NT / 32);
+#ifndef BLU_EMU
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_factorize<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+    BLU_LAUNCH(k_factorize<NT>, o->d.nmat, NT, smem, o->stream, o->d, o->cap);
+    o->launches++;
+    CK(cudaGetLastError());
+    return BLU_OK;
+}
+static int launch_factorize(blu_b200 *o) {
+    switch (o->nthreads) {
+    case 32: return launch_factorize_nt<32>(o);
+    case 64: return launch_factorize_nt<64>(o);
+    case 256: return launch_factorize_nt<256>(o);
+    case 512: return launch_factorize_nt<512>(o);
+    case 1024: return launch_factorize_nt<1024>(o);
+    default: return launch_factorize_nt<128>(o);
+    }
+}
+
+static int fetch_info(blu_b200 *o) {
+    CK(cudaMemcpyAsync(o->hinfo.data(), o->d.info, (size_t)o->d.nmat * sizeof(BluInfo), cudaMemcpyDeviceToHost, o->stream));
+    CK(cudaStreamSynchronize(o->stream));
+    return BLU_OK;
+}
+
+/* factorize what is resident in db_*; loops on Reallocate like blu.rs:95-118 */
+static int factorize_resident(blu_b200 *o) {
+    CK(cudaSetDevice(o->device));
+    BluDev &d = o->d;
+    d.b_begin = (const blu_i64 *)o->db_begin; d.b_end = (const blu_i64 *)o->db_end;
+    d.b_i = (const blu_i64 *)o->db_i; d.b_x = o->db_x;
+    double total_ms = 0.0;
+    for (int attempt = 0; attempt < 40; attempt++) {
+        timer_start(o);
+        int st = launch_factorize(o);
+        if (st != BLU_OK) return st;
+        timer_stop(o, 0);
+        total_ms += o->last_ms[0];
+        if ((st = fetch_info(o)) != BLU_OK) return st;
+        int64_t al = 0, au = 0, aw = 0; int need = 0;
+        for (auto &I : o->hinfo) {
+            if (I.status == BLU_REALLOCATE) { need = 1; al = std::max<int64_t>(al, I.addmem_l); au = std::max<int64_t>(au, I.addmem_u); aw = std::max<int64_t>(aw, I.addmem_w); }
+        }
+        if (!need) { o->last_ms[0] = total_ms; return BLU_OK; }
+        /* lu_realloc_obj, blu.rs:345-377 */
+        double f = o->realloc_factor < 1.0 ? 1.0 : o->realloc_factor;
+        if (al > 0) d.l_mem = (int64_t)(f * (double)(d.l_mem + al)) + 1;
+        if (au > 0) d.u_mem = (int64_t)(f * (double)(d.u_mem + au)) + 1;
+        if (aw > 0) d.w_mem = (int64_t)(f * (double)(d.w_mem + aw)) + 1;
+        if (d.l_mem > 0x3fffffff || d.u_mem > 0x3fffffff || d.w_mem > 0x1fffffff) return BLU_ERROR_OUT_OF_MEMORY;
+        free_stores(o);
+        if ((st = alloc_stores(o)) != BLU_OK) return st;
+        o->nrealloc++;
+    }
+    return BLU_ERROR_INTERNAL;
+}
+
+/* ------------------------------------------------------------------ */
+/* batch API                                                           */
+/* ------------------------------------------------------------------ */
+extern "C" int blu_batch_create(blu_batch_t **out, int64_t nmat, int64_t m, int64_t bnz_cap, int device) {
+    return create_common(out, nmat, m, bnz_cap, device, 0);
+}
+extern "C" void blu_batch_destroy(blu_batch_t *b) { destroy_common(b); }
+
+extern "C" int blu_batch_upload(blu_batch_t *o, const int64_t *b_begin, const int64_t *b_end,
+                                const int64_t *b_i, const double *b_x, int64_t bnz_total, const double *rhs) {
+    if (!o) return BLU_ERROR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(o->device));
+    const size_t n = (size_t)o->d.nmat, m = (size_t)o->d.m;
+    if (b_begin) {
+        if (!b_end || !b_i || !b_x || bnz_total < 0) return BLU_ERROR_INVALID_ARGUMENT;
+        int st = ensure_b_cap(o, bnz_total);
+        if (st != BLU_OK) return st;
+        CK(cudaMemcpyAsync(o->db_begin, b_begin, n * m * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
+        CK(cudaMemcpyAsync(o->db_end, b_end, n * m * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
+        CK(cudaMemcpyAsync(o->db_i, b_i, (size_t)bnz_total * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
+        CK(cudaMemcpyAsync(o->db_x, b_x, (size_t)bnz_total * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+        o->have_b = 1;
+    }
+    if (rhs) CK(cudaMemcpyAsync(o->d_rhs, rhs, n * m * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+    CK(cudaStreamSynchronize(o->stream));
+    return BLU_OK;
+}
+
+extern "C" int blu_batch_factorize_resident(blu_batch_t *o) {
+    if (!o || !o->have_b) return BLU_ERROR_INVALID_CALL;
+    return factorize_resident(o);
+}
+
+static int solve_dense_resident(blu_b200 *o, char trans) {
+    CK(cudaSetDevice(o->device));
+    timer_start(o);
+    BLU_LAUNCH(k_solve_dense, o->d.nmat, 32, 0, o->stream, o->d, (const double *)o->d_rhs, o->d_lhs, trans, o->d_status);
+    o->launches++;
+    CK(cudaGetLastError());
+    timer_stop(o, 1);
+    return BLU_OK;
+}
+extern "C" int blu_batch_solve_dense_resident(blu_batch_t *o, char trans) {
+    if (!o) return BLU_ERROR_INVALID_ARGUMENT;
+    return solve_dense_resident(o, trans);
+}
+
+extern "C" int blu_batch_download(blu_batch_t *o, double *lhs, int *status) {
+    if (!o) return BLU_ERROR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(o->device));
+    const size_t n = (size_t)o->d.nmat, m = (size_t)o->d.m;
+    if (lhs) CK(cudaMemcpyAsync(lhs, o->d_lhs, n * m * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+    if (status) CK(cudaMemcpyAsync(status, o->d_status, n * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+    CK(cudaStreamSynchronize(o->stream));
+    return BLU_OK;
+}
+
+extern "C" int blu_batch_factorize(blu_batch_t *o, const int64_t *b_begin, const int64_t *b_end,
+                                   const int64_t *b_i, const double *b_x, int64_t bnz_total, int *status) {
+    if (!o || !b_begin || !b_end || !b_i || !b_x) return BLU_ERROR_INVALID_ARGUMENT;
+    int st = blu_batch_upload(o, b_begin, b_end, b_i, b_x, bnz_total, nullptr);
+    if (st != BLU_OK) return st;
+    st = factorize_resident(o);
+    if (st != BLU_OK) return st;
+    if (status) for (int k = 0; k < o->d.nmat; k++) status[k] = o->hinfo[k].status;
+    return BLU_OK;
+}
+
+extern "C" int blu_batch_solve_dense(blu_batch_t *o, const double *rhs, double *lhs, char trans, int *status) {
+    if (!o || !rhs || !lhs) return BLU_ERROR_INVALID_ARGUMENT;
+    int st = blu_batch_upload(o, nullptr, nullptr, nullptr, nullptr, 0, rhs);
+    if (st != BLU_OK) return st;
+    st = solve_dense_resident(o, trans);
+    if (st != BLU_OK) return st;
+    return blu_batch_download(o, lhs, status);
+}
+
+extern "C" void *blu_batch_stream(blu_batch_t *o) { return o ? (void *)o->stream : nullptr; }
+extern "C" int blu_batch_set_stream(blu_batch_t *o, void *s) {
+    if (!o) return BLU_ERROR_INVALID_ARGUMENT;
+    cudaStreamSynchronize(o->stream);
+    if (o->own_stream) cudaStreamDestroy(o->stream);
+    o->stream = (cudaStream_t)s; o->own_stream = 0;
+    return BLU_OK;
+}
+extern "C" int blu_batch_synchronize(blu_batch_t *o) {
+    if (!o) return BLU_ERROR_INVALID_ARGUMENT;
+    CK(cudaStreamSynchronize(o->stream));
+    return BLU_OK;
+}
+extern "C" double blu_batch_last_kernel_ms(blu_batch_t *o, int which) { return o && which >= 0 && which < 2 ? o->last_ms[which] : 0.0; }
+extern "C" int64_t blu_batch_launch_count(blu_batch_t *o) { return o ? o->launches : 0; }
+
+static double info_value(blu_b200 *o, const BluInfo &I, int what) {
+    switch (what) {
+    case BLU_I_M: return I.m;
+    case BLU_I_RANK: return I.rank;
+    case BLU_I_BUMP_SIZE: return I.bump_size;
+    case BLU_I_BUMP_NZ: return (double)I.bump_nz;
+    case BLU_I_MATRIX_NZ: return (double)I.matrix_nz;
+    case BLU_I_L_NZ: return (double)I.l_nz;
+    case BLU_I_U_NZ: return (double)I.u_nz;
+    case BLU_I_R_NZ: return (double)I.r_nz;
+    case BLU_I_NSEARCH_PIVOT: return (double)I.nsearch_pivot;
+    case BLU_I_NEXPAND: return (double)I.nexpand;
+    case BLU_I_NGARBAGE: return (double)I.ngarbage;
+    case BLU_I_FACTOR_FLOPS: return (double)I.factor_flops;
+    case BLU_I_MIN_PIVOT: return I.min_pivot;
+    case BLU_I_MAX_PIVOT: return I.max_pivot;
+    case BLU_I_MAX_ETA: return I.max_eta;
+    case BLU_I_NUPDATE: return I.nupdate;
+    case BLU_I_NFORREST: return I.nforrest;
+    case BLU_I_NFACTORIZE: return I.nfactorize;
+    case BLU_I_NUPDATE_TOTAL: return (double)I.nupdate_total;
+    case BLU_I_NFORREST_TOTAL: return (double)I.nforrest_total;
+    case BLU_I_NSYMPERM_TOTAL: return (double)I.nsymperm_total;
+    case BLU_I_L_FLOPS: return (double)I.l_flops;
+    case BLU_I_U_FLOPS: return (double)I.u_flops;
+    case BLU_I_R_FLOPS: return (double)I.r_flops;
+    case BLU_I_CONDEST_L: return I.condest_l;
+    case BLU_I_CONDEST_U: return I.condest_u;
+    case BLU_I_NORM_L: return I.norm_l;
+    case BLU_I_NORM_U: return I.norm_u;
+    case BLU_I_NORMEST_L_INV: return I.normest_l_inv;
+    case BLU_I_NORMEST_U_INV: return I.normest_u_inv;
+    case BLU_I_ONENORM: return I.onenorm;
+    case BLU_I_INFNORM: return I.infnorm;
+    case BLU_I_RESIDUAL_TEST: return I.residual_test;
+    case BLU_I_PIVOT_ERROR: return I.pivot_error;
+    case BLU_I_UPDATE_COST: return I.update_cost_numer / I.update_cost_denom; /* lu.rs:324 */
+    case BLU_I_TIME_FACTORIZE: return o->time_factorize;
+    case BLU_I_TIME_SOLVE: return o->time_solve;
+    case BLU_I_TIME_UPDATE: return o->time_update;
+    case BLU_I_ELIM_BYTES: return I.elim_bytes;
+    case BLU_I_NELIM_DIV: return (double)I.nelim_div;
+    case BLU_I_PIVOTLEN: return I.pivotlen;
+    case BLU_I_RANKDEF: return I.rankdef;
+    case BLU_I_INTERNAL_ERROR: return I.internal_error;
+    case BLU_I_STATUS: return I.status;
+    case BLU_I_NREALLOC: return o->nrealloc;
+    default: return 0.0;
+    }
+}
+extern "C" double blu_batch_get_info(blu_batch_t *o, int64_t k, int what) {
+    if (!o || k < 0 || k >= o->d.nmat) return 0.0;
+    if (what < 100) return blu_get_param(o, what);
+    return info_value(o, o->hinfo[(size_t)k], what);
+}
+
+extern "C" int blu_set_param(blu_t *o, int what, double v) {
+    if (!o) return BLU_ERROR_INVALID_ARGUMENT;
+    BluParams &p = o->d.prm;
+    switch (what) {
+    case BLU_P_DROPTOL: p.droptol = v; break;
+    case BLU_P_ABSTOL: p.abstol = v; break;
+    case BLU_P_RELTOL: p.reltol = v; break;
+    case BLU_P_NZBIAS: p.nzbias = (int)v; break;
+    case BLU_P_MAXSEARCH: p.maxsearch = (int)v; break;
+    case BLU_P_PAD: p.pad = (int)v; break;
+    case BLU_P_STRETCH: p.stretch = v; break;
+    case BLU_P_COMPRESS_THRES: p.compress_thres = v; break;
+    case BLU_P_SPARSE_THRES: p.sparse_thres = v; break;
+    case BLU_P_SEARCH_ROWS: p.search_rows = (int)v; break;
+    case BLU_P_REALLOC_FACTOR: o->realloc_factor = v; break;
+    case BLU_P_THREADS_PER_BASIS: {
+        int t = (int)v;
+        if (t != 32 && t != 64 && t != 128 && t != 256 && t != 512 && t != 1024) return BLU_ERROR_INVALID_ARGUMENT;
+        o->nthreads = t; break;
+    }
+    case BLU_P_L_MEM: case BLU_P_U_MEM: case BLU_P_W_MEM: {
+        int64_t n = (int64_t)v;
+        if (n < 1) return BLU_ERROR_INVALID_ARGUMENT;
+        if (cudaSetDevice(o->device) != cudaSuccess) return BLU_ERROR_CUDA;
+        cudaStreamSynchronize(o->stream);
+        if (what == BLU_P_L_MEM) o->d.l_mem = n; else if (what == BLU_P_U_MEM) o->d.u_mem = n; else o->d.w_mem = n;
+        free_stores(o);
+        int st = alloc_stores(o);
+        if (st != BLU_OK) return st;
+        /* the factors are gone */
+        for (auto &I : o->hinfo) I.nupdate = -1;
+        if (cudaMemcpy(o->d.info, o->hinfo.data(), o->hinfo.size() * sizeof(BluInfo), cudaMemcpyHostToDevice) != cudaSuccess) return BLU_ERROR_CUDA;
+        break;
+    }
+    default: return BLU_ERROR_INVALID_ARGUMENT;
+    }
+    return BLU_OK;
+}
+extern "C" double blu_get_param(const blu_t *o, int what) {
+    if (!o) return 0.0;
+    const BluParams &p = o->d.prm;
+    switch (what) {
+    case BLU_P_DROPTOL: return p.droptol;
+    case BLU_P_ABSTOL: return p.abstol;
+    case BLU_P_RELTOL: return p.reltol;
+    case BLU_P_NZBIAS: return p.nzbias;
+    case BLU_P_MAXSEARCH: return p.maxsearch;
+    case BLU_P_PAD: return p.pad;
+    case BLU_P_STRETCH: return p.stretch;
+    case BLU_P_COMPRESS_THRES: return p.compress_thres;
+    case BLU_P_SPARSE_THRES: return p.sparse_thres;
+    case BLU_P_SEARCH_ROWS: return p.search_rows;
+    case BLU_P_REALLOC_FACTOR: return o->realloc_factor;
+    case BLU_P_L_MEM: return (double)o->d.l_mem;
+    case BLU_P_U_MEM: return (double)o->d.u_mem;
+    case BLU_P_W_MEM: return (double)o->d.w_mem;
+    case BLU_P_THREADS_PER_BASIS: return o->nthreads;
+    default: return 0.0;
+    }
+}
+extern "C" double blu_get_info(blu_t *o, int what) { return blu_batch_get_info(o, 0, what); }
+
+static int ensure_gf_cap(blu_b200 *o, int64_t n) {
+    if (n <= o->gf_cap) return BLU_OK;
+    dfree(o, o->gf_i); dfree(o, o->gf_x); o->gf_i = nullptr; o->gf_x = nullptr;
+    int st = dalloc(o, &o->gf_i, (size_t)n);
+    if (st == BLU_OK) st = dalloc(o, &o->gf_x, (size_t)n);
+    if (st == BLU_OK) o->gf_cap = n;
+    return st;
+}
+
+extern "C" int blu_batch_get_factors(blu_batch_t *o, int64_t k, int64_t *rowperm, int64_t *colperm,
+                                     int64_t *l_colptr, int64_t *l_rowidx, double *l_value,
+                                     int64_t *u_colptr, int64_t *u_rowidx, double *u_value) {
+    if (!o || k < 0 || k >= o->d.nmat) return BLU_ERROR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(o->device));
+    const BluInfo &I = o->hinfo[(size_t)k];
+    if (I.nupdate != 0) return BLU_ERROR_INVALID_CALL;   /* get_factors.rs:59-61 (D9: no panic) */
+    const int64_t m = o->d.m, lz = m + I.l_nz, uz = m + I.u_nz;
+    /* staging layout (i64): rowperm m | colperm m | l_colptr m+1 | l_rowidx lz | u_colptr m+1 | u_rowidx uz ; (f64): l_value lz | u_value uz */
+    const int64_t ni = 4 * m + 2 + lz + uz, nx = lz + uz;
+    int st = ensure_gf_cap(o, std::max(ni, nx));
+    if (st != BLU_OK) return st;
+    int64_t *d_rp = o->gf_i, *d_cp = d_rp + m, *d_lp = d_cp + m, *d_li = d_lp + m + 1, *d_up = d_li + lz, *d_ui = d_up + m + 1;
+    double *d_lx = o->gf_x, *d_ux = d_lx + lz;
+    BLU_LAUNCH(k_get_factors<128>, 1, 128, 0, o->stream, o->d, (int)k, (i64 *)d_rp, (i64 *)d_cp, (i64 *)d_lp, (i64 *)d_li, d_lx,
+               (i64 *)d_up, (i64 *)d_ui, d_ux, o->d_status + k);
+    o->launches++;
+    CK(cudaGetLastError());
+#define DL(dst, src, cnt, T) if (dst) CK(cudaMemcpyAsync(dst, src, (size_t)(cnt) * sizeof(T), cudaMemcpyDeviceToHost, o->stream))
+    DL(rowperm, d_rp, m, int64_t); DL(colperm, d_cp, m, int64_t);
+    if (l_colptr && l_rowidx && l_value) { DL(l_colptr, d_lp, m + 1, int64_t); DL(l_rowidx, d_li, lz, int64_t); DL(l_value, d_lx, lz, double); }
+    if (u_colptr && u_rowidx && u_value) { DL(u_colptr, d_up, m + 1, int64_t); DL(u_rowidx, d_ui, uz, int64_t); DL(u_value, d_ux, uz, double); }
+#undef DL
+    CK(cudaStreamSynchronize(o->stream));
+    return BLU_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* object API                                                          */
+/* ------------------------------------------------------------------ */
+extern "C" int blu_create(blu_t **out, int64_t m, int64_t b_nz, int device) { return create_common(out, 1, m, b_nz, device, 1); }
+extern "C" void blu_destroy(blu_t *o) { destroy_common(o); }
+
+extern "C" int blu_factorize(blu_t *o, const int64_t *b_begin, const int64_t *b_end, const int64_t *b_i, const double *b_x) {
+    if (!o || !b_begin || !b_end || !b_i || !b_x) return BLU_ERROR_INVALID_ARGUMENT;
+    if (o->d.nmat != 1) return BLU_ERROR_INVALID_CALL;
+    const int64_t m = o->d.m;
+    /* gather the referenced columns into a compact staging copy (B may live inside a
+     * much larger array, as in maxvolume.rs:180-224) */
+    o->hb_begin.resize((size_t)m); o->hb_end.resize((size_t)m);
+    int64_t nnz = 0;
+    for (int64_t j = 0; j < m; j++) {
+        if (b_end[j] < b_begin[j]) return BLU_ERROR_INVALID_ARGUMENT;   /* singletons.rs:122-131 */
+        o->hb_begin[(size_t)j] = nnz; nnz += b_end[j] - b_begin[j]; o->hb_end[(size_t)j] = nnz;
+    }
+    o->hb_i.resize((size_t)nnz); o->hb_x.resize((size_t)nnz);
+    for (int64_t j = 0; j < m; j++) {
+        const int64_t n = b_end[j] - b_begin[j];
+        if (n) {
+            memcpy(&o->hb_i[(size_t)o->hb_begin[(size_t)j]], b_i + b_begin[j], (size_t)n * sizeof(int64_t));
+            memcpy(&o->hb_x[(size_t)o->hb_begin[(size_t)j]], b_x + b_begin[j], (size_t)n * sizeof(double));
+        }
+    }
+    if (nnz > o->d.bnz_cap) {
+        /* the object was created for fewer nonzeros: grow the row-copy store */
+        CK(cudaSetDevice(o->device));
+        dfree(o, o->d.bt_idx); dfree(o, o->d.bt_val);
+        o->d.bnz_cap = nnz;
+        int st = dalloc(o, &o->d.bt_idx, (size_t)nnz);
+        if (st == BLU_OK) st = dalloc(o, &o->d.bt_val, (size_t)nnz);
+        if (st != BLU_OK) return st;
+    }
+    int st = blu_batch_upload(o, o->hb_begin.data(), o->hb_end.data(), o->hb_i.data(), o->hb_x.data(), nnz, nullptr);
+    if (st != BLU_OK) return st;
+    st = factorize_resident(o);
+    o->time_factorize += 1e-3 * o->last_ms[0];
+    if (st != BLU_OK) return st;
+    return o->hinfo[0].status;
+}
+
+extern "C" int blu_get_factors(blu_t *o, int64_t *rowperm, int64_t *colperm,
+                               int64_t *l_colptr, int64_t *l_rowidx, double *l_value,
+                               int64_t *u_colptr, int64_t *u_rowidx, double *u_value) {
+    return blu_batch_get_factors(o, 0, rowperm, colperm, l_colptr, l_rowidx, l_value, u_colptr, u_rowidx, u_value);
+}
+
+extern "C" int blu_solve_dense(blu_t *o, const double *rhs, double *lhs, char trans) {
+    if (!o || !rhs || !lhs) return BLU_ERROR_INVALID_ARGUMENT;
+    if (o->hinfo[0].nupdate < 0) return BLU_ERROR_INVALID_CALL;   /* solve_dense.rs:25 */
+    int status = BLU_OK;
+    int st = blu_batch_solve_dense(o, rhs, lhs, trans, &status);
+    o->time_solve += 1e-3 * o->last_ms[1];
+    return st != BLU_OK ? st : status;
+}
+
+extern "C" const char *blu_version(void) {
+#ifdef BLU_EMU
+    return "blu_b200 0.1 (SIMT emulation build: tests only)";
+#else
+    return "blu_b200 0.1 (sm_100a)";
+#endif
+}
+
+/* ---- not yet on the device: fail loudly (there is no CPU path) ---- */
+extern "C" int blu_solve_sparse(blu_t *, int64_t, const int64_t *, const double *, int64_t *, int64_t *, double *, char) { return BLU_ERROR_INTERNAL; }
+extern "C" int blu_solve_for_update(blu_t *, int64_t, const int64_t *, const double *, int64_t *, int64_t *, double *, char) { return BLU_ERROR_INTERNAL; }
+extern "C" int blu_update(blu_t *, double) { return BLU_ERROR_INTERNAL; }

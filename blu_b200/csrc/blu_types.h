@@ -1,0 +1,99 @@
+/* blu_types.h -- plain structs shared by the host layer and the CUDA kernels.
+ *
+ * Device data layout (one "slot" per basis matrix; a batch is an array of slots with
+ * uniform strides so that slot s of every array is base + s*stride):
+ *
+ *   B (caller's format, copied verbatim)   b_begin[m] b_end[m] (i64)  b_i[] (i64)  b_x[] (f64)
+ *   row-wise copy of B                      bt_ptr[m+1]  bt_idx[bnz]  bt_val[bnz]
+ *   L store (col-wise | row-wise | etas)    l_idx[l_mem] l_val[l_mem]      (reference: lu.rs:137-138)
+ *   U store (rows during elimination,
+ *            col-wise + spike afterwards)   u_idx[u_mem] u_val[u_mem]      (lu.rs:139-140)
+ *   W line file, two halves (ping-pong GC)  w_idx[2*w_mem] w_val[2*w_mem]  (lu.rs:141-142, file.rs)
+ *   line table of W                         lbeg[2m] lend[2m] lcap[2m]
+ *   Markowitz keys (count<<40 | stamp)      ckey[m] rkey[m]                (replaces list.rs buckets)
+ *
+ * Indices are 32-bit on the device (m < 2^31); the C ABI converts from/to the
+ * reference's 64-bit usize/LUInt (lib.rs:32).
+ */
+#ifndef BLU_TYPES_H
+#define BLU_TYPES_H
+#include <stdint.h>
+
+typedef unsigned long long blu_u64;
+typedef long long blu_i64;
+
+/* lu.rs:17-66, defaults lu.rs:250-259 */
+struct BluParams {
+    double droptol, abstol, reltol, stretch, compress_thres, sparse_thres;
+    int nzbias;      /* >=0 <=> Some(_), <0 <=> None */
+    int maxsearch, pad, search_rows;
+};
+
+/* Everything the getters of lu.rs:399-683 report, plus internal cursors. */
+struct BluInfo {
+    int status;
+    int m, rank, rankdef, bump_size;
+    int nupdate;            /* -1 <=> None */
+    int nforrest, pivotlen, nfactorize;
+    int ftran_for_update, btran_for_update; /* -1 <=> None */
+    int marker;
+    int w_half;             /* which half of W is live */
+    int nact;               /* entries of the active-column list */
+    int internal_error;     /* line number of a failed device-side invariant, 0 = none */
+    int pad0;
+    blu_i64 matrix_nz, bump_nz, l_nz, u_nz, r_nz;
+    blu_i64 nsearch_pivot, nexpand, ngarbage, factor_flops;
+    blu_i64 l_flops, u_flops, r_flops;
+    blu_i64 addmem_l, addmem_u, addmem_w;
+    blu_i64 nupdate_total, nforrest_total, nsymperm_total;
+    blu_i64 w_used;         /* fill pointer of the live W half */
+    blu_i64 cstamp, rstamp; /* monotone insertion stamps (FIFO order of list.rs:54) */
+    blu_i64 nelim_div;
+    double min_pivot, max_pivot, max_eta, pivot_error;
+    double update_cost_numer, update_cost_denom;
+    double elim_bytes;      /* algorithmic bytes of the elimination */
+    double condest_l, condest_u, norm_l, norm_u, normest_l_inv, normest_u_inv;
+    double onenorm, infnorm, residual_test;
+};
+
+/* Batch-wide device pointers.  Per-slot strides follow from m and the *_mem sizes. */
+struct BluDev {
+    int m, nmat;
+    blu_i64 l_mem, u_mem, w_mem, bnz_cap;
+    BluParams prm;
+    /* input B */
+    const blu_i64 *b_begin, *b_end, *b_i; /* b_begin/b_end: nmat*m; positions into b_i/b_x */
+    const double *b_x;
+    /* row-wise copy */
+    int *bt_ptr; int *bt_idx; double *bt_val;
+    /* permutations / pivots */
+    int *pinv, *qinv;           /* m each; become pmap/qmap after build_factors */
+    int *prank, *qrank;         /* m each: rank of row i / column j (kept for get_factors) */
+    double *colpiv, *rowpiv;    /* m each */
+    /* factors */
+    int *l_idx; double *l_val;
+    int *u_idx; double *u_val;
+    int *w_idx; double *w_val;
+    int *lbeg, *lend, *lcap;    /* 2m each */
+    blu_u64 *ckey, *rkey;       /* m each */
+    int *l_begin_p, *u_begin;   /* m+1 each */
+    int *l_begin, *lt_begin, *lt_begin_p, *p, *r_begin, *eta_row; /* m+1 each */
+    int *pivotcol, *pivotrow;   /* 2m+2 each */
+    /* workspaces */
+    int *rowmark, *colmark;     /* m each, zero between steps */
+    int *marked;                /* m (iwork0 of the reference) */
+    int *iwork1;                /* 2m+2 */
+    int *pstack;                /* m */
+    int *acols;                 /* m: active-column list for the Markowitz search */
+    int *tmpi;                  /* 4m+4 scratch */
+    blu_u64 *cancelled;         /* m */
+    double *work0, *work1;      /* m each */
+    double *gwork;              /* gwork_warps*m: per-warp scatter space when a pivot column exceeds the smem cache */
+    int gwork_warps;
+    BluInfo *info;              /* nmat */
+};
+
+/* status codes live in the public header */
+#include "blu_b200.h"
+
+#endif

@@ -1,0 +1,141 @@
+/* blu_b200.h -- C ABI of the B200-native BLU hot path (libblu_b200.so).
+ *
+ * Drop-in boundary for the public surface of the rwl/blu crate (paths relative to
+ * /root/reference/src).  Every entry point takes plain host pointers and sizes; the
+ * library owns all device memory, does the H2D/D2H copies and launches hand-written
+ * sm_100a kernels.  There is no CPU fallback: without a CUDA device every call
+ * returns BLU_ERROR_CUDA.
+ *
+ * Index type: the reference uses usize/LUInt = 64-bit (lib.rs:32); so does this ABI.
+ * Return codes: the Rust `Status` enum (lib.rs:39-64) has no discriminants; BASICLU's
+ * numbering is used.  Ok(()) == BLU_OK.  WarningSingularMatrix is returned like an
+ * error by the crate but the factorization IS valid (factorize.rs:115-119,176-178).
+ * `Reallocate` never escapes the object API (blu.rs:95-118 loops on it); it does not
+ * escape this ABI either -- the library grows device memory and re-runs.
+ */
+#ifndef BLU_B200_H
+#define BLU_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    BLU_OK = 0,
+    BLU_REALLOCATE = 1,                 /* lib.rs:41  (internal, never returned) */
+    BLU_WARNING_SINGULAR_MATRIX = 2,    /* lib.rs:44 */
+    BLU_ERROR_INVALID_CALL = -2,        /* lib.rs:48 */
+    BLU_ERROR_ARGUMENT_MISSING = -3,    /* lib.rs:51 */
+    BLU_ERROR_INVALID_ARGUMENT = -4,    /* lib.rs:54 */
+    BLU_ERROR_MAXIMUM_UPDATES = -5,     /* lib.rs:58 */
+    BLU_ERROR_SINGULAR_UPDATE = -6,     /* lib.rs:63 */
+    BLU_ERROR_INTERNAL = -100,          /* a device-side invariant (a reference assert!) failed */
+    BLU_ERROR_CUDA = -101,              /* no device / CUDA runtime error */
+    BLU_ERROR_OUT_OF_MEMORY = -102
+};
+
+/* parameter / info selectors for blu_set_param, blu_get_param, blu_get_info.
+ * Parameters: pub fields of `LU` (lu/lu.rs:10-66) and BLU.realloc_factor (blu.rs:19).
+ * Info: the getters of lu/lu.rs:399-683. */
+enum {
+    BLU_P_DROPTOL = 0, BLU_P_ABSTOL, BLU_P_RELTOL, BLU_P_NZBIAS, BLU_P_MAXSEARCH, BLU_P_PAD,
+    BLU_P_STRETCH, BLU_P_COMPRESS_THRES, BLU_P_SPARSE_THRES, BLU_P_SEARCH_ROWS,
+    BLU_P_REALLOC_FACTOR, BLU_P_L_MEM, BLU_P_U_MEM, BLU_P_W_MEM,
+    BLU_P_THREADS_PER_BASIS,            /* CTA size of the factorization kernel (32..1024) */
+    BLU_I_M = 100, BLU_I_RANK, BLU_I_BUMP_SIZE, BLU_I_BUMP_NZ, BLU_I_MATRIX_NZ, BLU_I_L_NZ,
+    BLU_I_U_NZ, BLU_I_R_NZ, BLU_I_NSEARCH_PIVOT, BLU_I_NEXPAND, BLU_I_NGARBAGE,
+    BLU_I_FACTOR_FLOPS, BLU_I_MIN_PIVOT, BLU_I_MAX_PIVOT, BLU_I_MAX_ETA, BLU_I_NUPDATE,
+    BLU_I_NFORREST, BLU_I_NFACTORIZE, BLU_I_NUPDATE_TOTAL, BLU_I_NFORREST_TOTAL,
+    BLU_I_NSYMPERM_TOTAL, BLU_I_L_FLOPS, BLU_I_U_FLOPS, BLU_I_R_FLOPS, BLU_I_CONDEST_L,
+    BLU_I_CONDEST_U, BLU_I_NORM_L, BLU_I_NORM_U, BLU_I_NORMEST_L_INV, BLU_I_NORMEST_U_INV,
+    BLU_I_ONENORM, BLU_I_INFNORM, BLU_I_RESIDUAL_TEST, BLU_I_PIVOT_ERROR, BLU_I_UPDATE_COST,
+    BLU_I_TIME_FACTORIZE, BLU_I_TIME_SOLVE, BLU_I_TIME_UPDATE, BLU_I_ELIM_BYTES, BLU_I_NELIM_DIV,
+    BLU_I_PIVOTLEN, BLU_I_RANKDEF, BLU_I_INTERNAL_ERROR, BLU_I_STATUS, BLU_I_NREALLOC
+};
+
+/* ------------------------------------------------------------------ */
+/* object API: struct BLU, blu.rs:9-334                                 */
+/* ------------------------------------------------------------------ */
+typedef struct blu_b200 blu_t;
+
+/* BLU::new(m, b_nz), blu.rs:61-70.  device < 0: current device. */
+int blu_create(blu_t **out, int64_t m, int64_t b_nz, int device);
+void blu_destroy(blu_t *o);
+
+int blu_set_param(blu_t *o, int what, double value);
+double blu_get_param(const blu_t *o, int what);
+double blu_get_info(blu_t *o, int what);
+
+/* BLU::factorize, blu.rs:95-118 -> factorize(), factorize.rs:34.  Column j of B is
+ * b_i/b_x[b_begin[j] .. b_end[j]); pass (colptr, colptr+1) for CSC. */
+int blu_factorize(blu_t *o, const int64_t *b_begin, const int64_t *b_end,
+                  const int64_t *b_i, const double *b_x);
+
+/* BLU::get_factors, blu.rs:139-160 -> get_factors.rs:48.  Every output may be NULL. */
+int blu_get_factors(blu_t *o, int64_t *rowperm, int64_t *colperm,
+                    int64_t *l_colptr, int64_t *l_rowidx, double *l_value,
+                    int64_t *u_colptr, int64_t *u_rowidx, double *u_value);
+
+/* BLU::solve_dense, blu.rs:182-184 -> solve_dense.rs:24.  trans 't'/'T' = transposed. */
+int blu_solve_dense(blu_t *o, const double *rhs, double *lhs, char trans);
+
+/* BLU::solve_sparse, blu.rs:207-230 -> solve_sparse.rs:35.  The result is returned like
+ * BLU.lhs / ilhs / nzlhs: lhs[m] scattered (zero elsewhere), ilhs[0..*nzlhs) its pattern. */
+int blu_solve_sparse(blu_t *o, int64_t nzrhs, const int64_t *irhs, const double *xrhs,
+                     int64_t *nzlhs, int64_t *ilhs, double *lhs, char trans);
+
+/* BLU::solve_for_update, blu.rs:257-294 -> solve_for_update.rs:72.  xrhs may be NULL for
+ * trans; nzlhs/ilhs/lhs may all be NULL when the solution is not wanted. */
+int blu_solve_for_update(blu_t *o, int64_t nzrhs, const int64_t *irhs, const double *xrhs,
+                         int64_t *nzlhs, int64_t *ilhs, double *lhs, char trans);
+
+/* BLU::update, blu.rs:319-334 -> update.rs:49 */
+int blu_update(blu_t *o, double xtbl);
+
+/* ------------------------------------------------------------------ */
+/* batch API: many independent bases of one dimension on one GPU       */
+/* (what "one BLU instance per core" is on the CPU)      */
+/* ------------------------------------------------------------------ */
+typedef struct blu_b200 blu_batch_t;
+
+/* nmat objects of dimension m whose B has at most bnz_cap entries each. */
+int blu_batch_create(blu_batch_t **out, int64_t nmat, int64_t m, int64_t bnz_cap, int device);
+void blu_batch_destroy(blu_batch_t *b);
+
+/* Column j of basis k is b_i/b_x[b_begin[k*m+j] .. b_end[k*m+j]); b_i/b_x hold `bnz_total`
+ * entries in all.  status[k] (may be NULL) receives the per-basis code; the return value
+ * is BLU_OK unless a call-level error occurred. */
+int blu_batch_factorize(blu_batch_t *b, const int64_t *b_begin, const int64_t *b_end,
+                        const int64_t *b_i, const double *b_x, int64_t bnz_total, int *status);
+/* rhs, lhs: nmat*m, basis k at offset k*m */
+int blu_batch_solve_dense(blu_batch_t *b, const double *rhs, double *lhs, char trans, int *status);
+double blu_batch_get_info(blu_batch_t *b, int64_t k, int what);
+int blu_batch_get_factors(blu_batch_t *b, int64_t k, int64_t *rowperm, int64_t *colperm,
+                          int64_t *l_colptr, int64_t *l_rowidx, double *l_value,
+                          int64_t *u_colptr, int64_t *u_rowidx, double *u_value);
+
+/* Device-resident variants for throughput measurement: upload once, then time kernels only. */
+int blu_batch_upload(blu_batch_t *b, const int64_t *b_begin, const int64_t *b_end,
+                     const int64_t *b_i, const double *b_x, int64_t bnz_total, const double *rhs);
+int blu_batch_factorize_resident(blu_batch_t *b);
+int blu_batch_solve_dense_resident(blu_batch_t *b, char trans);
+int blu_batch_download(blu_batch_t *b, double *lhs, int *status);
+/* cudaStream_t the library launches on (so callers can bracket it with their own events),
+ * and a way to make it use the caller's stream instead */
+void *blu_batch_stream(blu_batch_t *b);
+int blu_batch_set_stream(blu_batch_t *b, void *cuda_stream);
+int blu_batch_synchronize(blu_batch_t *b);
+/* device time of the last factorize / solve kernels, measured with CUDA events on the launching stream */
+double blu_batch_last_kernel_ms(blu_batch_t *b, int which /*0 factorize, 1 solve_dense*/);
+/* number of kernels this library launched since creation */
+int64_t blu_batch_launch_count(blu_batch_t *b);
+
+const char *blu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,87 @@
+/* cuda_emu.cpp -- scheduler of the SIMT emulator (test/debug infrastructure, see cuda_emu.h) */
+#include "cuda_emu.h"
+
+emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+unsigned char *emu_dyn_smem = nullptr;
+
+namespace emu {
+Fiber *fibers = nullptr; Warp *warps = nullptr;
+int nthreads = 0, cur = 0;
+unsigned blk_gen = 0; int blk_arrived = 0, blk_live = 0;
+ucontext_t sched_ctx;
+static std::function<void()> *g_body;
+static const size_t STACK = 256 * 1024;
+
+void yield_wait(unsigned *gen, unsigned mygen) {
+    Fiber &f = fibers[cur];
+    f.state = 1; f.gen = gen; f.mygen = mygen;
+    int me = cur;
+    swapcontext(&f.ctx, &sched_ctx);
+    cur = me;
+    threadIdx.x = (unsigned)me;
+}
+
+static void fiber_main() {
+    (*g_body)();
+    Fiber &f = fibers[cur];
+    f.state = 2;
+    /* an exited thread no longer takes part in barriers */
+    Warp &w = warps[cur >> 5];
+    w.live--; blk_live--;
+    if (w.live > 0 && w.arrived >= w.live) { w.arrived = 0; w.gen++; }
+    if (blk_live > 0 && blk_arrived >= blk_live) { blk_arrived = 0; blk_gen++; }
+    swapcontext(&f.ctx, &sched_ctx);
+}
+
+void launch(emu_dim3 grid, emu_dim3 block, size_t smem, std::function<void()> body) {
+    g_body = &body;
+    nthreads = (int)block.x;
+    blockDim = block; gridDim = grid;
+    int nw = (nthreads + 31) / 32;
+    fibers = (Fiber *)calloc((size_t)nthreads, sizeof(Fiber));
+    warps = (Warp *)calloc((size_t)nw, sizeof(Warp));
+    for (int t = 0; t < nthreads; t++) fibers[t].stack = (char *)malloc(STACK);
+    unsigned char *dyn = (unsigned char *)aligned_alloc(128, ((smem + 127) / 128 + 1) * 128);
+    for (unsigned b = 0; b < grid.x; b++) {
+        blockIdx = emu_dim3(b);
+        memset(dyn, 0xCD, smem); /* shared memory is not zero-initialised on the GPU either */
+        emu_dyn_smem = dyn;
+        blk_gen = 0; blk_arrived = 0; blk_live = nthreads;
+        for (int w = 0; w < nw; w++) {
+            memset(&warps[w], 0, sizeof(Warp));
+            int l = nthreads - 32 * w; warps[w].live = l > 32 ? 32 : l;
+        }
+        for (int t = 0; t < nthreads; t++) {
+            Fiber &f = fibers[t];
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = STACK; f.ctx.uc_link = &sched_ctx;
+            makecontext(&f.ctx, (void (*)())fiber_main, 0);
+            f.state = 0;
+        }
+        int done = 0;
+        while (done < nthreads) {
+            int progressed = 0;
+            for (int t = 0; t < nthreads; t++) {
+                Fiber &f = fibers[t];
+                if (f.state == 2) continue;
+                if (f.state == 1) { if (*f.gen == f.mygen) continue; f.state = 0; }
+                cur = t; threadIdx = emu_dim3((unsigned)t);
+                swapcontext(&sched_ctx, &f.ctx);
+                progressed = 1;
+                if (f.state == 2) done++;
+            }
+            if (!progressed) {
+                fprintf(stderr, "cuda_emu: DEADLOCK in block %u (divergent barrier?)\n", b);
+                for (int t = 0; t < nthreads; t++)
+                    if (fibers[t].state == 1)
+                        fprintf(stderr, "  thread %d waits on %s barrier\n", t,
+                                fibers[t].gen == &blk_gen ? "block" : "warp");
+                abort();
+            }
+        }
+    }
+    for (int t = 0; t < nthreads; t++) free(fibers[t].stack);
+    free(fibers); free(warps); free(dyn);
+    fibers = nullptr; warps = nullptr; emu_dyn_smem = nullptr;
+}
+}
