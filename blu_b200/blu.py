@@ -42,6 +42,8 @@ _INFO_NAMES = ["m", "rank", "bump_size", "bump_nz", "matrix_nz", "l_nz", "u_nz",
                "time_factorize", "time_solve", "time_update", "elim_bytes", "nelim_div", "pivotlen",
                "rankdef", "internal_error", "status", "nrealloc"]
 I = {n: 100 + k for k, n in enumerate(_INFO_NAMES)}
+I.update({f"t_phase{q}": 200 + q for q in range(12)})
+I.update({f"n_kind{q}": 220 + q for q in range(8)})
 
 
 def library_path():

@@ -13,6 +13,9 @@
 typedef blu_u64 u64;
 typedef blu_i64 i64;
 
+#ifdef BLU_EMU
+static inline long long clock64() { return 0; }
+#endif
 #define FULLMASK 0xffffffffu
 #define KEY_INF 0xffffffffffffffffull
 #define STAMP_BITS 40
@@ -96,6 +99,7 @@ struct Shm {
     int cap;                  /* entries of the smem line caches */
     int *cidx, *ridx; double *cval, *work; /* dynamic smem carve-up */
     double elim_bytes; i64 nelim_div;
+    i64 t_phase[12]; i64 n_kind[8];
 };
 
 template <int NT> __device__ __forceinline__ void bsync() {

@@ -242,13 +242,20 @@ template <int NT> __global__ void __launch_bounds__(NT) k_factorize(BluDev D, in
             S.nexpand = 0; S.ngarbage = 0; S.nsearch = 0; S.factor_flops = 0;
             S.elim_bytes = 0.0; S.nelim_div = 0;
             S.w_used = 0; S.w_limit = (int)D.w_mem; S.w_half = 0;
+            for (int q = 0; q < 12; q++) S.t_phase[q] = 0;
+            for (int q = 0; q < 8; q++) S.n_kind[q] = 0;
         }
         bsync<NT>();
         for (int i = tid; i < D.m; i += NT) S.M.marked[i] = 0;
+        const i64 tstart = clock64();
         phase_singletons<NT>(S);
+        i64 t0 = clock64();
         if (S.status == BLU_OK) phase_setup_bump<NT>(S);
+        if (tid == 0) S.t_phase[2] += clock64() - t0;
         if (S.status == BLU_OK) phase_bump<NT>(S);
+        t0 = clock64();
         if (S.status == BLU_OK) phase_build_factors<NT>(S);
+        if (tid == 0) { S.t_phase[9] += clock64() - t0; S.t_phase[11] = clock64() - tstart; }
         bsync<NT>();
         if (tid == 0) {
             BluInfo *I = S.M.info;
@@ -258,6 +265,8 @@ template <int NT> __global__ void __launch_bounds__(NT) k_factorize(BluDev D, in
             I->elim_bytes = S.elim_bytes; I->nelim_div = S.nelim_div;
             I->w_half = S.w_half; I->w_used = S.w_used;
             I->cstamp = S.cstamp; I->rstamp = S.rstamp;
+            for (int q = 0; q < 12; q++) I->t_phase[q] = S.t_phase[q];
+            for (int q = 0; q < 8; q++) I->n_kind[q] = S.n_kind[q];
             int st = S.status;
             if (st == BLU_OK) {
                 I->nupdate = 0; I->nfactorize++;

@@ -16,6 +16,9 @@
  */
 #ifndef BLU_FACTOR_BUMP_CUH
 #define BLU_FACTOR_BUMP_CUH
+#ifndef REGE
+#define REGE 8   /* line entries per lane held in registers by the fast paths (lines <= 32*REGE) */
+#endif
 #include "blu_dev_common.cuh"
 
 /* ------------------------------------------------------------------ */
@@ -349,8 +352,63 @@ template <int NT> __device__ void pivot_general(Shm &S, const bool small) {
         const int j = ridx[k];
         int beg = M.lbeg[j], end = M.lend[j], cap = M.lcap[j];
         const int oldnz = end - beg;
-        int put = beg, where = -1;
-        double cmx = 0.0;
+        int put, where = -1;
+        double cmx = 0.0, xrj;
+        int nT;
+        if (oldnz <= 32 * REGE) {
+            /* register-resident path: every load of the line is issued before the first
+             * dependent use, so one column costs ~2 memory round trips instead of 2 per chunk */
+            int ei[REGE], emk[REGE], toff[REGE]; double ev[REGE];
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) {
+                int pos = beg + e * 32 + lane;
+                bool valid = pos < end;
+                ei[e] = valid ? M.w_idx[pos] : -1;
+                ev[e] = valid ? M.w_val[pos] : 0.0;
+            }
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) emk[e] = ei[e] >= 0 ? M.rowmark[ei[e]] : -1;
+            int tcount = 0; double myx = 0.0; int mine = 0;
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) {
+                if (e * 32 < oldnz) {
+                    int isT = emk[e] == 0;
+                    unsigned tm = __ballot_sync(FULLMASK, isT);
+                    toff[e] = tcount + __popc(tm & lanemask_lt());
+                    if (isT) { if (ei[e] == pr) { where = toff[e]; myx = ev[e]; mine = 1; } else { double a = fabs(ev[e]); if (a > cmx) cmx = a; } }
+                    if (emk[e] > 0) work[emk[e]] = ev[e];
+                    tcount += __popc(tm);
+                } else toff[e] = 0;
+            }
+            unsigned hm = __ballot_sync(FULLMASK, mine);
+            if (hm == 0) { if (lane == 0) BLU_CHECK(S, 0); continue; }
+            const int hl = __ffs((int)hm) - 1;
+            where = __shfl_sync(FULLMASK, where, hl);
+            xrj = __shfl_sync(FULLMASK, myx, hl);
+            nT = tcount;
+            int dstb = beg + 1;
+            if (cap - (beg + nT) < cnz1) {      /* the line moves to the end of the file */
+                int room = cnz1 + slack_of(M.prm, nT + cnz1);
+                int np = 0;
+                if (lane == 0) { np = atomicAdd(&S.w_used, nT - 1 + room); atomicAdd(&S.nexpand, 1); }
+                np = __shfl_sync(FULLMASK, np, 0);
+                dstb = np; cap = np + nT - 1 + room;
+            }
+            /* T with its first element and the pivot-row element exchanged, first dropped */
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) {
+                if (emk[e] == 0) {
+                    int t = toff[e];
+                    if (t != where) {
+                        int slot = t == 0 ? where - 1 : t - 1;
+                        M.w_idx[dstb + slot] = ei[e]; M.w_val[dstb + slot] = ev[e];
+                    }
+                }
+            }
+            beg = dstb; put = dstb + nT - 1;
+            __syncwarp();
+        } else {
+        put = beg;
         for (int base = beg; base < end; base += 32) {
             int pos = base + lane;
             int valid = pos < end;
@@ -368,11 +426,12 @@ template <int NT> __device__ void pivot_general(Shm &S, const bool small) {
         }
         where = warp_max(where);
         __syncwarp();
-        const double xrj = M.w_val[where];
+        if (where < 0) { if (lane == 0) BLU_CHECK(S, 0); continue; }
+        xrj = M.w_val[where];
         __syncwarp();
         if (lane == 0 && where != beg) { M.w_idx[where] = M.w_idx[beg]; M.w_val[where] = M.w_val[beg]; }
         __syncwarp();
-        const int nT = put - beg;
+        nT = put - beg;
         beg += 1;                            /* the pivot-row entry leaves the line */
         if (cap - put < cnz1) {              /* move the line to the end of the file */
             int nz = put - beg;
@@ -383,6 +442,7 @@ template <int NT> __device__ void pivot_general(Shm &S, const bool small) {
             for (int t = lane; t < nz; t += 32) { M.w_idx[np + t] = M.w_idx[beg + t]; M.w_val[np + t] = M.w_val[beg + t]; }
             beg = np; put = np + nz; cap = np + nz + room;
             __syncwarp();
+        }
         }
         const double a = __ddiv_rn(xrj, pivot);
         u64 cmask = 0;
@@ -431,7 +491,39 @@ template <int NT> __device__ void pivot_general(Shm &S, const bool small) {
         const int line = m + i;
         int beg = M.lbeg[line], end = M.lend[line], cap = M.lcap[line];
         const int oldnz = end - beg;
-        int put = beg;
+        int put;
+        if (oldnz <= 32 * REGE) {
+            int rj[REGE], roff[REGE];
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) {
+                int pos = beg + e * 32 + lane;
+                rj[e] = pos < end ? M.w_idx[pos] : -1;
+            }
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) roff[e] = (rj[e] >= 0 && M.colmark[rj[e]] == 0) ? 0 : -1;
+            int kcount = 0;
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) {
+                if (e * 32 < oldnz) {
+                    unsigned km = __ballot_sync(FULLMASK, roff[e] == 0);
+                    if (roff[e] == 0) roff[e] = kcount + __popc(km & lanemask_lt());
+                    kcount += __popc(km);
+                }
+            }
+            int dstb = beg;
+            if (cap - (beg + kcount) < rnz1) {
+                int room = rnz1 + slack_of(M.prm, kcount + rnz1);
+                int np = 0;
+                if (lane == 0) { np = atomicAdd(&S.w_used, kcount + room); atomicAdd(&S.nexpand, 1); }
+                np = __shfl_sync(FULLMASK, np, 0);
+                dstb = np; cap = np + kcount + room;
+            }
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) if (roff[e] >= 0) M.w_idx[dstb + roff[e]] = rj[e];
+            beg = dstb; put = dstb + kcount;
+            __syncwarp();
+        } else {
+        put = beg;
         for (int base = beg; base < end; base += 32) {
             int pos = base + lane;
             int valid = pos < end;
@@ -452,6 +544,7 @@ template <int NT> __device__ void pivot_general(Shm &S, const bool small) {
             for (int t = lane; t < nz; t += 32) M.w_idx[np + t] = M.w_idx[beg + t];
             beg = np; put = np + nz; cap = np + nz + room;
             __syncwarp();
+        }
         }
         if (!small) {
             for (int k = 1 + lane; k <= rnz1; k += 32) M.w_idx[put + k - 1] = ridx[k];
@@ -828,7 +921,9 @@ template <int NT> __device__ void phase_bump(Shm &S) {
     Mat &M = S.M;
     const int m = M.m, tid = threadIdx.x;
     while (S.rank + S.rankdef < m) {
+        i64 t0 = clock64();
         markowitz_search<NT>(S);
+        if (tid == 0) S.t_phase[3] += clock64() - t0;
         if (S.status != BLU_OK) return;
         const int pc = S.pivot_col, pr = S.pivot_row;
         if (pr < 0) {
@@ -850,12 +945,17 @@ template <int NT> __device__ void phase_bump(Shm &S) {
             if (room < nz_row - 1) { if (tid == 0) M.info->addmem_u = nz_row - 1 - room; st = BLU_REALLOCATE; }
             if (st != BLU_OK) { bsync<NT>(); if (tid == 0) S.status = st; bsync<NT>(); return; }
         }
-        if (nz_row == 1) pivot_singleton_row<NT>(S);
-        else if (nz_col == 1) pivot_singleton_col<NT>(S);
-        else if (nz_col == 2) pivot_doubleton_col<NT>(S);
-        else pivot_general<NT>(S, nz_col - 1 <= MAXROW_SMALL);
+        t0 = clock64();
+        int kind;
+        if (nz_row == 1) { pivot_singleton_row<NT>(S); kind = 0; }
+        else if (nz_col == 1) { pivot_singleton_col<NT>(S); kind = 1; }
+        else if (nz_col == 2) { pivot_doubleton_col<NT>(S); kind = 2; }
+        else { pivot_general<NT>(S, nz_col - 1 <= MAXROW_SMALL); kind = nz_col - 1 <= MAXROW_SMALL ? 3 : 4; }
+        if (tid == 0) { S.t_phase[4 + kind] += clock64() - t0; S.n_kind[kind]++; }
         if (S.status != BLU_OK) return;
+        t0 = clock64();
         post_remove_cols<NT>(S, rank);
+        if (tid == 0) S.t_phase[10] += clock64() - t0;
         if (tid == 0) {
             M.pinv[pr] = rank; M.qinv[pc] = rank;
             S.rank = rank + 1;

@@ -285,8 +285,11 @@ template <int NT> __device__ void singleton_rows(Shm &S) {
 template <int NT> __device__ void phase_singletons(Shm &S) {
     Mat &M = S.M;
     const int m = M.m, tid = threadIdx.x;
+    i64 t0 = clock64();
     phase_validate_transpose<NT>(S);
+    if (tid == 0) S.t_phase[0] += clock64() - t0;
     if (S.status != BLU_OK) return;
+    t0 = clock64();
     for (int i = tid; i < m; i += NT) { M.pinv[i] = -1; M.qinv[i] = -1; }
     if (tid == 0) { M.l_begin_p[0] = 0; M.u_begin[0] = 0; S.rank = 0; }
     bsync<NT>();
@@ -297,6 +300,7 @@ template <int NT> __device__ void phase_singletons(Shm &S) {
         if (M.qinv[i] < 0) M.qinv[i] = -1;
     }
     bsync<NT>();
+    if (tid == 0) S.t_phase[1] += clock64() - t0;
 }
 
 /* setup_bump.rs:55-264.  Lines of the W file get `stretch*nz + pad` slack; the bucket

@@ -397,7 +397,10 @@ static double info_value(blu_b200 *o, const BluInfo &I, int what) {
     case BLU_I_INTERNAL_ERROR: return I.internal_error;
     case BLU_I_STATUS: return I.status;
     case BLU_I_NREALLOC: return o->nrealloc;
-    default: return 0.0;
+    default:
+        if (what >= BLU_I_T_PHASE0 && what < BLU_I_T_PHASE0 + 12) return (double)I.t_phase[what - BLU_I_T_PHASE0];
+        if (what >= BLU_I_N_KIND0 && what < BLU_I_N_KIND0 + 8) return (double)I.n_kind[what - BLU_I_N_KIND0];
+        return 0.0;
     }
 }
 extern "C" double blu_batch_get_info(blu_batch_t *o, int64_t k, int what) {

@@ -54,6 +54,8 @@ struct BluInfo {
     double elim_bytes;      /* algorithmic bytes of the elimination */
     double condest_l, condest_u, norm_l, norm_u, normest_l_inv, normest_u_inv;
     double onenorm, infnorm, residual_test;
+    blu_i64 t_phase[12];    /* SM clock cycles per phase (thread 0): 0 validate+transpose 1 singleton queue 2 setup_bump 3 search 4 pivot singleton row 5 singleton col 6 doubleton 7 small 8 any 9 build_factors 10 remove_cols 11 total */
+    blu_i64 n_kind[8];      /* pivots per variant, same numbering minus 4 */
 };
 
 /* Batch-wide device pointers.  Per-slot strides follow from m and the *_mem sizes. */

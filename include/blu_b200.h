@@ -53,7 +53,9 @@ enum {
     BLU_I_CONDEST_U, BLU_I_NORM_L, BLU_I_NORM_U, BLU_I_NORMEST_L_INV, BLU_I_NORMEST_U_INV,
     BLU_I_ONENORM, BLU_I_INFNORM, BLU_I_RESIDUAL_TEST, BLU_I_PIVOT_ERROR, BLU_I_UPDATE_COST,
     BLU_I_TIME_FACTORIZE, BLU_I_TIME_SOLVE, BLU_I_TIME_UPDATE, BLU_I_ELIM_BYTES, BLU_I_NELIM_DIV,
-    BLU_I_PIVOTLEN, BLU_I_RANKDEF, BLU_I_INTERNAL_ERROR, BLU_I_STATUS, BLU_I_NREALLOC
+    BLU_I_PIVOTLEN, BLU_I_RANKDEF, BLU_I_INTERNAL_ERROR, BLU_I_STATUS, BLU_I_NREALLOC,
+    BLU_I_T_PHASE0 = 200, /* +0..11: SM cycles per phase of the factorization kernel (diagnostic) */
+    BLU_I_N_KIND0 = 220   /* +0..4: pivots taken by singleton-row / singleton-col / doubleton / small / any */
 };
 
 /* ------------------------------------------------------------------ */
