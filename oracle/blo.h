@@ -161,6 +161,11 @@ int blo_lu_get_factors(blo_lu *lu, lint *rowperm, lint *colperm,
                        lint *u_colptr, lint *u_rowidx, double *u_value); /* get_factors.rs:48 */
 double blo_lu_update_cost(const blo_lu *lu);                       /* lu.rs:324 */
 
+/* one instance per core over a batch of bases (blo_batch.c); returns the threads used */
+int blo_batch_factorize_solve(lint nmat, lint m, const lint *b_begin, const lint *b_end,
+                              const lint *b_i, const double *b_x, const double *rhs, double *lhs,
+                              char trans, lint store_nz, int nthreads, int check_file_diff, int *status);
+
 /* oracle-only helpers for the tests */
 void blo_trace_enable(blo *o, int on);
 lint blo_trace_len(const blo *o);

@@ -49,8 +49,27 @@ def lib():
         L.blo_trace_data.restype = ctypes.POINTER(Trace); L.blo_trace_data.argtypes = [vp]
         L.blo_lhs.restype = f64p; L.blo_lhs.argtypes = [vp]
         L.blo_ilhs.restype = i64p; L.blo_ilhs.argtypes = [vp]
+        L.blo_batch_factorize_solve.argtypes = [ctypes.c_int64, ctypes.c_int64, i64p, i64p, i64p, f64p, f64p, f64p,
+                                                ctypes.c_char, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                                ctypes.POINTER(ctypes.c_int)]
         _L = L
     return _L
+
+
+def batch_factorize_solve(nmat, m, b_begin, b_end, b_i, b_x, rhs, trans="N", store_nz=0, nthreads=1, check_file_diff=1):
+    """One oracle instance per thread over a batch (oracle/blo_batch.c).  Returns (threads, lhs[nmat,m], status)."""
+    L = lib()
+    bb = np.ascontiguousarray(b_begin, dtype=np.int64); be = np.ascontiguousarray(b_end, dtype=np.int64)
+    bi = np.ascontiguousarray(b_i, dtype=np.int64); bx = np.ascontiguousarray(b_x, dtype=np.float64)
+    r = np.ascontiguousarray(rhs, dtype=np.float64).reshape(-1)
+    x = np.zeros(nmat * m)
+    status = np.zeros(nmat, dtype=np.int32)
+    if store_nz <= 0:
+        store_nz = int((be - bb).reshape(nmat, m).sum(1).max())
+    nt = L.blo_batch_factorize_solve(nmat, m, _pi(bb), _pi(be), _pi(bi), _pf(bx), _pf(r), _pf(x), str(trans).encode()[:1],
+                                     int(store_nz), int(nthreads), int(check_file_diff),
+                                     status.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    return nt, x.reshape(nmat, m), status
 
 
 def _pi(a):

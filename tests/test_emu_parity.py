@@ -1,0 +1,85 @@
+"""CPU tests: the CUDA kernels compiled with g++ under the SIMT emulator of tests/emu
+(barriers, warp votes/shuffles and atomics emulated with fibers) against the oracle.
+This checks kernel LOGIC on the GPU-less build box; the `-m gpu` tests are the parity tests
+proper.  The emulated library is test infrastructure and never part of the product."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from blu_b200 import BLU, BLUBatch, gen, load_library
+from parity import oracle_for, assert_factor_parity
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emu")])
+    return load_library(os.path.join(HERE, "emu", "libblu_emu.so"))
+
+
+def pair(emu, cp, ri, v, m, nt, ofactor=60):
+    o = oracle_for(m, len(v), ofactor)
+    so = o.factorize(cp[:-1], cp[1:], ri, v)
+    g = BLU(m, len(v), lib=emu)
+    g.threads_per_basis = nt
+    sg = g.factorize(cp[:-1], cp[1:], ri, v)
+    assert so == sg
+    return g, o, sg
+
+
+@pytest.mark.parametrize("nt,seed", [(32, 1), (64, 2), (128, 3)])
+def test_emu_factorize_solve(emu, nt, seed):
+    m = 160
+    cp, ri, v = gen.basis(60 + seed, m, 40, 4.0)
+    g, o, st = pair(emu, cp, ri, v, m, nt)
+    assert st == 0
+    assert_factor_parity(g, o)
+    b = gen.rhs(70 + seed, m)
+    for tr in "NT":
+        _, xo = o.solve_dense(b, tr)
+        sg, xg = g.solve_dense(b, tr)
+        assert sg == 0
+        assert np.abs(xg - xo).max() <= 1e-12 * np.abs(xo).max()
+
+
+def test_emu_dense_columns(emu):
+    m = 200
+    cp, ri, v = gen.basis(13, m, 0, 14.0, cap=60)
+    g, o, st = pair(emu, cp, ri, v, m, 64, ofactor=400)
+    assert_factor_parity(g, o)
+    assert g.info("n_kind4") > 0      # pivot_any exercised
+
+
+def test_emu_singular_and_cancellation(emu):
+    import scipy.sparse as sp
+    m = 90
+    rng = np.random.default_rng(3)
+    A = sp.random(m, m, density=0.04, format="csc", random_state=3, data_rvs=lambda n: np.sign(rng.uniform(-1, 1, n)))
+    A.sort_indices()
+    cp, ri, v = A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.copy()
+    g, o, st = pair(emu, cp, ri, v, m, 64)
+    assert st == 2
+    assert_factor_parity(g, o)
+
+
+def test_emu_batch(emu):
+    nmat, m = 3, 100
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 30, 4.0, 9000, 9500)
+    b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()), lib=emu)
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all()
+    st, x, sst = b.solve_dense(rhs, "N")
+    assert st == 0 and (sst == 0).all()
+    for k in range(nmat):
+        cp, ri, v = gen.basis(9000 + k, m, 30, 4.0)
+        o = oracle_for(m, len(v))
+        o.factorize(cp[:-1], cp[1:], ri, v)
+        _, fo = o.get_factors()
+        _, fg = b.get_factors(k)
+        for key in fo:
+            assert np.array_equal(fo[key], fg[key]), key
+        _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
+        assert np.abs(x[k] - xo).max() <= 1e-12 * np.abs(xo).max()
