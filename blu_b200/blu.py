@@ -190,10 +190,20 @@ class BLU(_Base):
         st = self._L.blu_solve_dense(self._h, _pf(r), _pf(x), _ch(trans))
         return st, x
 
+    def _clear_lhs(self):
+        """lu_clear_lhs, blu.rs:380-395: zero what the previous solve scattered."""
+        nz = self.nzlhs
+        if nz:
+            if nz <= int(self.get_param("sparse_thres") * self.m):
+                self.lhs[self.ilhs[:nz]] = 0.0
+            else:
+                self.lhs[:] = 0.0
+            self.nzlhs = 0
+
     # blu.rs:207: result in self.lhs / self.ilhs / self.nzlhs
     def solve_sparse(self, nzrhs, irhs, xrhs, trans="N"):
         ir, xr = _i64(irhs), _f64(xrhs)
-        self.lhs[:] = 0.0   # lu_clear_lhs, blu.rs:380-395
+        self._clear_lhs()
         nz = ctypes.c_int64(0)
         st = self._L.blu_solve_sparse(self._h, int(nzrhs), _pi(ir), _pf(xr), ctypes.byref(nz), _pi(self.ilhs), _pf(self.lhs), _ch(trans))
         self.nzlhs = nz.value
@@ -203,8 +213,10 @@ class BLU(_Base):
     def solve_for_update(self, nzrhs, irhs, xrhs, trans="N", want_solution=0):
         ir = _i64(irhs)
         xr = _f64(xrhs) if xrhs is not None else None
+        self._clear_lhs()
+        # D13 repaired: blu.rs:268-283 passes Some(lhs)
+        # even when want_solution == 0; BASICLU semantics = no solution unless asked for.
         if want_solution:
-            self.lhs[:] = 0.0
             nz = ctypes.c_int64(0)
             st = self._L.blu_solve_for_update(self._h, int(nzrhs), _pi(ir), _pf(xr), ctypes.byref(nz), _pi(self.ilhs), _pf(self.lhs), _ch(trans))
             self.nzlhs = nz.value

@@ -214,7 +214,13 @@ static inline size_t blu_factor_smem_bytes(int cap, int nw) {
     return (size_t)cap * 8 + (size_t)nw * cap * 8 + (size_t)cap * 4 * 2;
 }
 
-template <int NT> __global__ void __launch_bounds__(NT) k_factorize(BluDev D, int cap) {
+#ifndef FACT_MINB
+/* resident CTAs per SM the register allocation is sized for: 1024 threads per SM => 64
+ * registers per thread.  Measured on B200 (profiles/r1b_sweep.txt): 8 CTAs x 128 threads with
+ * a few spills beat 4 CTAs x 128 registers by 30 % -- the kernel is latency-bound. */
+#define FACT_MINB(NT) (1024 / (NT) > 0 ? 1024 / (NT) : 1)
+#endif
+template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factorize(BluDev D, int cap) {
     BLU_DYN_SMEM(dyn);
     __shared__ Shm S;
     const int tid = threadIdx.x;

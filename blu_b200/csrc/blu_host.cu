@@ -17,6 +17,7 @@
 #include <string.h>
 #include <vector>
 #include <algorithm>
+#include <time.h>
 
 #define PADDING 64 /* slack entries after the L/U/W stores: warp-wide terminator scans read ahead */
 
@@ -39,7 +40,9 @@ struct blu_b200 {
     int64_t *db_begin, *db_end, *db_i; double *db_x; int64_t b_cap;
     double *d_rhs, *d_lhs; int *d_status;
     /* sparse-solve staging (object API) */
-    int64_t *d_irhs; double *d_xrhs; int64_t *d_ilhs; int *d_scal;
+    int64_t *d_irhs; double *d_xrhs; int64_t *d_ilhs; double *d_xout; int *d_scal;
+    int *h_scal; int64_t *h_ilhs; double *h_xout;   /* pinned */
+    int info_dirty;             /* device info block is newer than hinfo */
     /* get_factors staging */
     int64_t *gf_i; double *gf_x; int64_t gf_cap;
     std::vector<BluInfo> hinfo;
@@ -103,7 +106,8 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     o->realloc_factor = 1.5;   /* blu.rs:68 */
     o->nthreads = 128; o->cap = 256;
     o->launches = 0; o->nrealloc = 0; o->last_ms[0] = o->last_ms[1] = 0.0;
-    o->have_b = 0;
+    o->have_b = 0; o->info_dirty = 0;
+    o->h_scal = nullptr; o->h_ilhs = nullptr; o->h_xout = nullptr;
     o->time_factorize = o->time_solve = o->time_update = 0.0;
     BluDev &d = o->d;
     memset(&d, 0, sizeof d);
@@ -135,7 +139,7 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     A(d.info, n);
     A(o->db_begin, n * M); A(o->db_end, n * M);
     A(o->d_rhs, n * M); A(o->d_lhs, n * M); A(o->d_status, n);
-    if (single) { A(o->d_irhs, M); A(o->d_xrhs, M); A(o->d_ilhs, M); A(o->d_scal, 16); }
+    if (single) { A(o->d_irhs, M); A(o->d_xrhs, M); A(o->d_ilhs, M); A(o->d_xout, M); A(o->d_scal, 16); }
 #undef A
     o->b_cap = 0; o->db_i = nullptr; o->db_x = nullptr;
     o->gf_i = nullptr; o->gf_x = nullptr; o->gf_cap = 0;
@@ -146,6 +150,11 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
         for (auto &I : o->hinfo) { memset(&I, 0, sizeof I); I.nupdate = -1; I.m = (int)m; I.ftran_for_update = I.btran_for_update = -1; I.update_cost_denom = 1.0; }
         if (cudaMemcpy(d.info, o->hinfo.data(), n * sizeof(BluInfo), cudaMemcpyHostToDevice) != cudaSuccess) st = BLU_ERROR_CUDA;
     }
+    if (st == BLU_OK && single) {
+        if (cudaMallocHost((void **)&o->h_scal, 16 * sizeof(int)) != cudaSuccess ||
+            cudaMallocHost((void **)&o->h_ilhs, M * sizeof(int64_t)) != cudaSuccess ||
+            cudaMallocHost((void **)&o->h_xout, M * sizeof(double)) != cudaSuccess) st = BLU_ERROR_OUT_OF_MEMORY;
+    }
     if (st == BLU_OK && cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) != cudaSuccess) st = BLU_ERROR_CUDA;
     o->own_stream = 1;
 #ifndef BLU_EMU
@@ -153,6 +162,9 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
 #endif
     if (st != BLU_OK) {
         for (void *p : o->allocs) cudaFree(p);
+        if (o->h_scal) cudaFreeHost(o->h_scal);
+        if (o->h_ilhs) cudaFreeHost(o->h_ilhs);
+        if (o->h_xout) cudaFreeHost(o->h_xout);
         delete o;
         return st;
     }
@@ -165,6 +177,9 @@ static void destroy_common(blu_b200 *o) {
     cudaSetDevice(o->device);
     cudaStreamSynchronize(o->stream);
     for (void *p : o->allocs) cudaFree(p);
+    if (o->h_scal) cudaFreeHost(o->h_scal);
+    if (o->h_ilhs) cudaFreeHost(o->h_ilhs);
+    if (o->h_xout) cudaFreeHost(o->h_xout);
 #ifndef BLU_EMU
     cudaEventDestroy(o->ev0); cudaEventDestroy(o->ev1);
 #endif
@@ -223,6 +238,14 @@ static int fetch_info(blu_b200 *o) {
     CK(cudaMemcpyAsync(o->hinfo.data(), o->d.info, (size_t)o->d.nmat * sizeof(BluInfo), cudaMemcpyDeviceToHost, o->stream));
     CK(cudaStreamSynchronize(o->stream));
     return BLU_OK;
+}
+
+static int ensure_info(blu_b200 *o) {
+    if (!o->info_dirty) return BLU_OK;
+    if (cudaSetDevice(o->device) != cudaSuccess) return BLU_ERROR_CUDA;
+    int st = fetch_info(o);
+    if (st == BLU_OK) o->info_dirty = 0;
+    return st;
 }
 
 /* factorize what is resident in db_*; loops on Reallocate like blu.rs:95-118 */
@@ -406,6 +429,7 @@ static double info_value(blu_b200 *o, const BluInfo &I, int what) {
 extern "C" double blu_batch_get_info(blu_batch_t *o, int64_t k, int what) {
     if (!o || k < 0 || k >= o->d.nmat) return 0.0;
     if (what < 100) return blu_get_param(o, what);
+    if (ensure_info(o) != BLU_OK) return 0.0;
     return info_value(o, o->hinfo[(size_t)k], what);
 }
 
@@ -485,6 +509,7 @@ extern "C" int blu_batch_get_factors(blu_batch_t *o, int64_t k, int64_t *rowperm
                                      int64_t *u_colptr, int64_t *u_rowidx, double *u_value) {
     if (!o || k < 0 || k >= o->d.nmat) return BLU_ERROR_INVALID_ARGUMENT;
     CK(cudaSetDevice(o->device));
+    { int st0 = ensure_info(o); if (st0 != BLU_OK) return st0; }
     const BluInfo &I = o->hinfo[(size_t)k];
     if (I.nupdate != 0) return BLU_ERROR_INVALID_CALL;   /* get_factors.rs:59-61 (D9: no panic) */
     const int64_t m = o->d.m, lz = m + I.l_nz, uz = m + I.u_nz;
@@ -558,6 +583,7 @@ extern "C" int blu_get_factors(blu_t *o, int64_t *rowperm, int64_t *colperm,
 
 extern "C" int blu_solve_dense(blu_t *o, const double *rhs, double *lhs, char trans) {
     if (!o || !rhs || !lhs) return BLU_ERROR_INVALID_ARGUMENT;
+    { int st0 = ensure_info(o); if (st0 != BLU_OK) return st0; }
     if (o->hinfo[0].nupdate < 0) return BLU_ERROR_INVALID_CALL;   /* solve_dense.rs:25 */
     int status = BLU_OK;
     int st = blu_batch_solve_dense(o, rhs, lhs, trans, &status);
@@ -573,7 +599,142 @@ extern "C" const char *blu_version(void) {
 #endif
 }
 
-/* ---- not yet on the device: fail loudly (there is no CPU path) ---- */
-extern "C" int blu_solve_sparse(blu_t *, int64_t, const int64_t *, const double *, int64_t *, int64_t *, double *, char) { return BLU_ERROR_INTERNAL; }
-extern "C" int blu_solve_for_update(blu_t *, int64_t, const int64_t *, const double *, int64_t *, int64_t *, double *, char) { return BLU_ERROR_INTERNAL; }
-extern "C" int blu_update(blu_t *, double) { return BLU_ERROR_INTERNAL; }
+/* ------------------------------------------------------------------ */
+/* sparse solves and the update (object API only)                      */
+/* ------------------------------------------------------------------ */
+
+/* lu_realloc_obj, blu.rs:345-377, for a store whose content must survive (an eta or a
+ * spike was appended since the factorization).  which: 0 = L, 1 = U, 2 = W. */
+static int grow_store_keep(blu_b200 *o, int which, int64_t addmem) {
+    BluDev &d = o->d;
+    const double f = o->realloc_factor < 1.0 ? 1.0 : o->realloc_factor;
+    CK(cudaStreamSynchronize(o->stream));
+    blu_i64 &mem = which == 0 ? d.l_mem : which == 1 ? d.u_mem : d.w_mem;
+    const int64_t newmem = (int64_t)(f * (double)(mem + addmem)) + 1;
+    if (newmem > (which == 2 ? 0x1fffffff : 0x3fffffff)) return BLU_ERROR_OUT_OF_MEMORY;
+    int *ni = nullptr; double *nv = nullptr;
+    const size_t mult = which == 2 ? 2 : 1;
+    int st = dalloc(o, &ni, mult * (size_t)newmem + PADDING);
+    if (st == BLU_OK) st = dalloc(o, &nv, mult * (size_t)newmem + PADDING);
+    if (st != BLU_OK) return st;
+    int *&oi = which == 0 ? d.l_idx : which == 1 ? d.u_idx : d.w_idx;
+    double *&ov = which == 0 ? d.l_val : which == 1 ? d.u_val : d.w_val;
+    size_t from = 0;
+    if (which == 2) {
+        /* only the live half moves; it becomes half 0 of the new store */
+        int st2 = fetch_info(o);
+        if (st2 != BLU_OK) return st2;
+        from = (size_t)o->hinfo[0].w_half * (size_t)mem;
+    }
+    CK(cudaMemcpyAsync(ni, oi + from, (size_t)mem * sizeof(int), cudaMemcpyDeviceToDevice, o->stream));
+    CK(cudaMemcpyAsync(nv, ov + from, (size_t)mem * sizeof(double), cudaMemcpyDeviceToDevice, o->stream));
+    CK(cudaStreamSynchronize(o->stream));
+    dfree(o, oi); dfree(o, ov);
+    oi = ni; ov = nv;
+    if (which == 2) {
+        BLU_LAUNCH(k_w_rebase, 1, 128, 0, o->stream, d, (int)from);
+        o->launches++;
+        CK(cudaGetLastError());
+    }
+    mem = newmem;
+    o->nrealloc++;
+    o->info_dirty = 1;
+    return BLU_OK;
+}
+
+static double wall_now() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* common body of blu_solve_sparse and blu_solve_for_update */
+static int sparse_call(blu_b200 *o, int64_t nzrhs, const int64_t *irhs, const double *xrhs,
+                       int64_t *nzlhs, int64_t *ilhs, double *lhs, char trans, int for_update) {
+    if (!o || !o->single) return BLU_ERROR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(o->device));
+    const double tic = wall_now();
+    const int64_t m = o->d.m;
+    const bool tr = trans == 't' || trans == 'T';
+    const int want = nzlhs && ilhs && lhs;
+    if (!for_update && !want) return BLU_ERROR_INVALID_ARGUMENT;
+    const int64_t nup = (for_update && tr) ? 1 : nzrhs;
+    const int64_t ncopy = (nup < 0 || nup > m) ? 0 : nup;
+    if (ncopy > 0 && !irhs) return BLU_ERROR_INVALID_ARGUMENT;
+    if (ncopy > 0) {
+        CK(cudaMemcpyAsync(o->d_irhs, irhs, (size_t)ncopy * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
+        if (xrhs && !(for_update && tr)) CK(cudaMemcpyAsync(o->d_xrhs, xrhs, (size_t)ncopy * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+    }
+    const int nrhs = (nzrhs < 0 || nzrhs > m) ? -1 : (int)nzrhs;
+    const double *dx = (xrhs && !(for_update && tr)) ? o->d_xrhs : nullptr;
+    int status = BLU_ERROR_INTERNAL, nz = 0;
+    for (int attempt = 0; attempt < 40; attempt++) {
+        BLU_LAUNCH(k_solve_sparse, 1, 32, 0, o->stream, o->d, nrhs, (const i64 *)o->d_irhs, dx, trans, for_update, want,
+                   o->d_scal, (i64 *)o->d_ilhs, o->d_xout);
+        o->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(o->h_scal, o->d_scal, 2 * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+        CK(cudaStreamSynchronize(o->stream));
+        status = o->h_scal[0]; nz = o->h_scal[1];
+        o->info_dirty = 1;
+        if (status != BLU_REALLOCATE) break;
+        /* BLU::solve_for_update loops on Reallocate, blu.rs:268-291 */
+        int st = fetch_info(o);
+        if (st != BLU_OK) return st;
+        const BluInfo &I = o->hinfo[0];
+        if (I.addmem_l > 0) st = grow_store_keep(o, 0, I.addmem_l);
+        if (st == BLU_OK && I.addmem_u > 0) st = grow_store_keep(o, 1, I.addmem_u);
+        if (st == BLU_OK && I.addmem_w > 0) st = grow_store_keep(o, 2, I.addmem_w);
+        if (st != BLU_OK) return st;
+        status = BLU_ERROR_INTERNAL;
+    }
+    if (status == BLU_OK && want) {
+        if (nz > 0) {
+            CK(cudaMemcpyAsync(o->h_ilhs, o->d_ilhs, (size_t)nz * sizeof(int64_t), cudaMemcpyDeviceToHost, o->stream));
+            CK(cudaMemcpyAsync(o->h_xout, o->d_xout, (size_t)nz * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+            CK(cudaStreamSynchronize(o->stream));
+            for (int n = 0; n < nz; n++) { ilhs[n] = o->h_ilhs[n]; lhs[o->h_ilhs[n]] = o->h_xout[n]; }
+        }
+        *nzlhs = nz;
+    }
+    o->time_solve += wall_now() - tic;
+    return status;
+}
+
+extern "C" int blu_solve_sparse(blu_t *o, int64_t nzrhs, const int64_t *irhs, const double *xrhs,
+                                int64_t *nzlhs, int64_t *ilhs, double *lhs, char trans) {
+    return sparse_call(o, nzrhs, irhs, xrhs, nzlhs, ilhs, lhs, trans, 0);
+}
+
+extern "C" int blu_solve_for_update(blu_t *o, int64_t nzrhs, const int64_t *irhs, const double *xrhs,
+                                    int64_t *nzlhs, int64_t *ilhs, double *lhs, char trans) {
+    return sparse_call(o, nzrhs, irhs, xrhs, nzlhs, ilhs, lhs, trans, 1);
+}
+
+extern "C" int blu_update(blu_t *o, double xtbl) {
+    if (!o || !o->single) return BLU_ERROR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(o->device));
+    const double tic = wall_now();
+    int status = BLU_ERROR_INTERNAL;
+    for (int attempt = 0; attempt < 40; attempt++) {
+        BLU_LAUNCH(k_update, 1, 32, 0, o->stream, o->d, xtbl, o->d_scal);
+        o->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(o->h_scal, o->d_scal, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+        CK(cudaStreamSynchronize(o->stream));
+        status = o->h_scal[0];
+        o->info_dirty = 1;
+        if (status != BLU_REALLOCATE) break;
+        /* BLU::update loops on Reallocate, blu.rs:319-334 */
+        int st = fetch_info(o);
+        if (st != BLU_OK) return st;
+        const BluInfo &I = o->hinfo[0];
+        if (I.addmem_l > 0) st = grow_store_keep(o, 0, I.addmem_l);
+        if (st == BLU_OK && I.addmem_u > 0) st = grow_store_keep(o, 1, I.addmem_u);
+        if (st == BLU_OK && I.addmem_w > 0) st = grow_store_keep(o, 2, I.addmem_w);
+        if (st != BLU_OK) return st;
+        status = BLU_ERROR_INTERNAL;
+    }
+    o->time_update += wall_now() - tic;
+    return status;
+}

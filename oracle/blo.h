@@ -19,7 +19,8 @@
  * (SURVEY.md section 0): D1 eta_row is its own array; D2-D4 update() reach
  * vectors; D5 64-bit cancellation mask; D6 markowitz loop advance; D7 sentinel
  * refresh after reallocation; D9 get_factors before factorize -> INVALID_CALL;
- * D12 signed arithmetic in update() compression tests.  D8 (search_rows
+ * D12 signed arithmetic in update() compression tests; D13 BLU::solve_for_update
+ * computes no solution when want_solution == 0 (blu.rs:268-283 always passes Some(lhs)).  D8 (search_rows
  * default 0) is REPRODUCED.  D11 (release-mode file_diff asserts in
  * setup_bump) is behind the run-time flag `check_file_diff` (default on, as
  * in the reference).

@@ -96,8 +96,16 @@ int blo_solve_for_update(blo *o, lint nzrhs, const lint *irhs, const double *xrh
     clear_lhs(o);
     for (;;) {
         lint nzlhs = 0;
-        st = blo_lu_solve_for_update(&o->lu, nzrhs, irhs, xrhs, &nzlhs, o->ilhs, o->lhs, trans);
-        if (want_solution) o->nzlhs = nzlhs;
+        /* D13 repaired: blu.rs:268-283 always passes Some(ilhs)/Some(lhs), so with
+         * want_solution == 0 the solution is still scattered into lhs while nzlhs is not
+         * recorded and lu_clear_lhs (blu.rs:380-395) later clears the wrong entries.
+         * BASICLU semantics: no solution unless it was asked for. */
+        if (want_solution) {
+            st = blo_lu_solve_for_update(&o->lu, nzrhs, irhs, xrhs, &nzlhs, o->ilhs, o->lhs, trans);
+            o->nzlhs = nzlhs;
+        } else {
+            st = blo_lu_solve_for_update(&o->lu, nzrhs, irhs, xrhs, NULL, NULL, NULL, trans);
+        }
         if (st != BLO_REALLOCATE) break;
         realloc_obj(o);
     }

@@ -19,7 +19,8 @@ for k in range(4):
     o = Oracle(m, 60 * len(v)); o.set_param("check_file_diff", 0)
     o.factorize(cp[:-1], cp[1:], ri, v); o.solve_dense(rhs[k * m:(k + 1) * m])
 print("oracle ms/matrix (no file_diff)", (time.time() - t) / 4 * 1e3)
-for nt in [64, 128, 256, 512]:
+NTS = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [64, 128, 256, 512]
+for nt in NTS:
     b = BLUBatch(nmat, m, cap)
     b.threads_per_basis = nt
     b.l_mem = 100000; b.u_mem = 100000; b.w_mem = 160000

@@ -54,3 +54,76 @@ def assert_backward_error(cp, ri, v, f, m, rank):
     scaled, plain = backward_error(cp, ri, v, f, m, rank)
     assert scaled <= 1e-14, scaled
     assert plain <= 1e-10, plain
+
+
+SPARSE_STATS = ["nupdate", "nforrest", "u_nz", "r_nz", "l_flops", "u_flops", "r_flops", "pivot_error", "max_eta",
+                "min_pivot", "max_pivot", "nsymperm_total", "nforrest_total", "nupdate_total", "pivotlen", "update_cost"]
+
+
+def assert_same_solution(g, o, what=""):
+    """lhs / ilhs / nzlhs of the last sparse solve: pattern ORDER and values bit-exact."""
+    assert g.nzlhs == o.nzlhs, (what, g.nzlhs, o.nzlhs)
+    n = o.nzlhs
+    assert np.array_equal(g.ilhs[:n], o.ilhs[:n]), f"{what}: ilhs order differs"
+    assert np.array_equal(g.lhs, o.lhs), f"{what}: lhs differs (max {np.abs(g.lhs - o.lhs).max():.3e})"
+
+
+def assert_sparse_stats(g, o, what=""):
+    for n in SPARSE_STATS:
+        assert g.info(n) == o.info(n), (what, n, g.info(n), o.info(n))
+    assert g.info("internal_error") == 0
+
+
+def assert_sparse_solve_parity(g, o, m, seed, sizes=(1, 3, 17, 60)):
+    """solve_sparse 'N' and 'T' for RHS of several densities (both sides of sparse_thres)."""
+    from blu_b200 import gen
+    for k, nz in enumerate(sizes):
+        nz = min(nz, m)
+        idx, val = gen.sparse_rhs(seed + k, m, nz)
+        for tr in "NT":
+            so = o.solve_sparse(nz, idx, val, tr)
+            sg = g.solve_sparse(nz, idx, val, tr)
+            assert so == sg == 0, (nz, tr, so, sg)
+            assert_same_solution(g, o, f"solve_sparse nz={nz} trans={tr}")
+    assert_sparse_stats(g, o, "after solve_sparse")
+
+
+def replay_updates(g, o, m, pool, niter, rng_seed=5, check_dense=True):
+    """Simplex-style replay on both objects in lockstep (C5 of BASELINE.json in miniature):
+    entering column from the pool, leaving position = argmax |lhs| (maxvolume.rs:120-131),
+    solve_for_update 'N' + 'T', update; everything observable must be identical."""
+    pool_cp, pool_ri, pool_v = pool
+    rng = np.random.default_rng(rng_seed)
+    kinds = set()
+    for it in range(niter):
+        idx = pool_ri[pool_cp[it]:pool_cp[it + 1]]
+        val = pool_v[pool_cp[it]:pool_cp[it + 1]]
+        so = o.solve_for_update(len(idx), idx, val, "N", want_solution=1)
+        sg = g.solve_for_update(len(idx), idx, val, "N", want_solution=1)
+        assert so == sg == 0, (it, so, sg)
+        assert_same_solution(g, o, f"it {it} ftran")
+        lhs = o.lhs
+        j = int(np.argmax(np.abs(lhs)))
+        xtbl = lhs[j]
+        want = it % 2
+        so = o.solve_for_update(1, np.array([j]), None, "T", want_solution=want)
+        sg = g.solve_for_update(1, np.array([j]), None, "T", want_solution=want)
+        assert so == sg == 0, (it, so, sg)
+        if want:
+            assert_same_solution(g, o, f"it {it} btran")
+        nf0 = o.info("nforrest")
+        so = o.update(xtbl)
+        sg = g.update(xtbl)
+        assert so == sg, (it, so, sg)
+        assert_sparse_stats(g, o, f"it {it} update")
+        if so != 0:
+            continue
+        kinds.add("ft" if o.info("nforrest") > nf0 else "perm")
+        if check_dense:
+            b = rng.uniform(-1, 1, m)
+            for tr in "NT":
+                _, xo = o.solve_dense(b, tr)
+                sg, xg = g.solve_dense(b, tr)
+                assert sg == 0
+                assert np.abs(xg - xo).max() <= 1e-12 * np.abs(xo).max(), (it, tr)
+    return kinds

@@ -83,3 +83,63 @@ def test_emu_batch(emu):
             assert np.array_equal(fo[key], fg[key]), key
         _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
         assert np.abs(x[k] - xo).max() <= 1e-12 * np.abs(xo).max()
+
+
+def test_emu_solve_sparse(emu):
+    from parity import assert_sparse_solve_parity
+    m = 160
+    cp, ri, v = gen.basis(81, m, 40, 4.0)
+    g, o, st = pair(emu, cp, ri, v, m, 64)
+    assert st == 0
+    assert_sparse_solve_parity(g, o, m, 500)
+
+
+@pytest.mark.parametrize("m,seed,nslack,niter,tight", [(120, 91, 36, 30, False), (80, 5, 60, 60, True), (150, 7, 75, 50, True)])
+def test_emu_update_replay(emu, m, seed, nslack, niter, tight):
+    """solve_for_update + update in lockstep with the oracle: symmetric/unsymmetric permutation
+    updates, Forrest-Tomlin updates, eta/spike/row-file growth (tight = stores start at nnz(B), so the
+    Reallocate protocol of blu.rs:268-291,319-334 runs), U and W compression."""
+    from parity import replay_updates, assert_sparse_solve_parity
+    cp, ri, v = gen.basis(seed, m, nslack, 4.0)
+    pool = gen.basis(seed + 1, m, 0, 3.0)
+    o = oracle_for(m, len(v), 400)
+    g = BLU(m, len(v), lib=emu)
+    g.threads_per_basis = 64
+    if tight:
+        g.l_mem = len(v); g.u_mem = len(v); g.w_mem = len(v)
+    assert o.factorize(cp[:-1], cp[1:], ri, v) == g.factorize(cp[:-1], cp[1:], ri, v) == 0
+    nr0 = g.info("nrealloc")
+    kinds = replay_updates(g, o, m, pool, niter)
+    assert "ft" in kinds and "perm" in kinds
+    if tight:
+        assert g.info("nrealloc") > nr0
+    assert_sparse_solve_parity(g, o, m, 700)
+    assert g.get_factors()[0] == o.get_factors()[0] == -2     # get_factors.rs:59-61
+    # refactorize the same object: counters reset as LU::reset does (lu.rs:329-396)
+    assert o.factorize(cp[:-1], cp[1:], ri, v) == g.factorize(cp[:-1], cp[1:], ri, v) == 0
+    assert_factor_parity(g, o, check_stats=False)
+    assert_sparse_solve_parity(g, o, m, 800, sizes=(2, 30))
+
+
+def test_emu_sparse_status_codes(emu):
+    """The Err sites of solve_sparse.rs:45-58, solve_for_update.rs:82-106 and update.rs:50, in the
+    reference's order of checks."""
+    m = 40
+    cp, ri, v = gen.basis(3, m, 10, 3.0)
+    g = BLU(m, len(v), lib=emu)
+    one, x1 = np.array([0]), np.array([1.0])
+    assert g.solve_sparse(1, one, x1) == -2                       # never factorized
+    assert g.solve_for_update(1, one, None, "N") == -3            # ArgumentMissing comes first
+    assert g.solve_for_update(1, one, x1, "N") == -2
+    assert g.update(1.0) == -2
+    assert g.factorize(cp[:-1], cp[1:], ri, v) == 0
+    assert g.solve_sparse(m + 1, np.arange(m + 1) % m, np.ones(m + 1)) == -4
+    assert g.solve_sparse(-1, one, x1) == -4
+    assert g.solve_sparse(1, np.array([m]), x1) == -4
+    assert g.solve_for_update(1, np.array([m]), None, "T") == -4
+    assert g.update(1.0) == -2                                    # no solve_for_update pair yet
+    assert g.solve_for_update(1, one, x1, "N") == 0
+    assert g.update(1.0) == -2                                    # only the forward half was prepared
+    assert g.solve_for_update(1, one, None, "T") == 0
+    assert g.update(1.0) in (0, -6)
+    assert g.solve_sparse(0, np.zeros(0, np.int64), np.zeros(0)) == 0 and g.nzlhs == 0

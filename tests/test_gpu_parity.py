@@ -183,3 +183,65 @@ def test_zero_and_tiny_pivots():
     g, o, st = run_pair(cp, ri, v, m)
     assert st == 2
     assert_factor_parity(g, o)
+
+
+# ---- sparse solves, solve_for_update, update (a15, a16, a17) ----
+
+@pytest.mark.parametrize("m,seed", [(1000, 1001), (2000, 2003)])
+def test_solve_sparse_parity(m, seed):
+    """Gilbert-Peierls solves, both transposes, RHS densities on both sides of sparse_thres:
+    nzlhs, the ORDER of ilhs and the values of lhs bit-identical to the oracle's."""
+    from parity import assert_sparse_solve_parity
+    cp, ri, v = gen.basis(seed, m, int(0.3 * m), 4.0)
+    g, o, st = run_pair(cp, ri, v, m)
+    assert st == 0
+    assert_sparse_solve_parity(g, o, m, 5000, sizes=(1, 2, 10, 40, m // 10, m))
+
+
+@pytest.mark.parametrize("m,seed,nslack,niter,tight", [(300, 41, 90, 120, False), (500, 7, 250, 200, True),
+                                                        (2000, 2000, 700, 150, False)])
+def test_update_replay_parity(m, seed, nslack, niter, tight):
+    """BASELINE.json configs[4] in miniature: column replacements via solve_for_update('N'),
+    solve_for_update('T'), update with the maxvolume.rs:120-131 leaving rule, in lockstep with the
+    oracle; then refactorize."""
+    from parity import replay_updates, assert_sparse_solve_parity
+    cp, ri, v = gen.basis(seed, m, nslack, 4.0)
+    pool = gen.basis(seed + 1, m, 0, 3.0)
+    o = oracle_for(m, len(v), 400)
+    g = BLU(m, len(v))
+    if tight:
+        g.l_mem = len(v); g.u_mem = len(v); g.w_mem = len(v)
+    assert o.factorize(cp[:-1], cp[1:], ri, v) == g.factorize(cp[:-1], cp[1:], ri, v) == 0
+    kinds = replay_updates(g, o, m, pool, niter, check_dense=(m <= 500))
+    assert "ft" in kinds and "perm" in kinds
+    assert_sparse_solve_parity(g, o, m, 700, sizes=(1, 5, 50))
+    b = gen.rhs(9, m)
+    for tr in "NT":
+        _, xo = o.solve_dense(b, tr)
+        sg, xg = g.solve_dense(b, tr)
+        assert sg == 0 and relerr(xg, xo) <= 1e-12
+    assert g.get_factors()[0] == o.get_factors()[0] == -2
+    assert o.factorize(cp[:-1], cp[1:], ri, v) == g.factorize(cp[:-1], cp[1:], ri, v) == 0
+    assert_factor_parity(g, o, check_stats=False)
+
+
+def test_sparse_status_codes():
+    """solve_sparse.rs:45-58, solve_for_update.rs:82-106, update.rs:50."""
+    m = 40
+    cp, ri, v = gen.basis(3, m, 10, 3.0)
+    g = BLU(m, len(v))
+    one, x1 = np.array([0]), np.array([1.0])
+    assert g.solve_sparse(1, one, x1) == -2
+    assert g.solve_for_update(1, one, None, "N") == -3
+    assert g.solve_for_update(1, one, x1, "N") == -2
+    assert g.update(1.0) == -2
+    assert g.factorize(cp[:-1], cp[1:], ri, v) == 0
+    assert g.solve_sparse(m + 1, np.arange(m + 1) % m, np.ones(m + 1)) == -4
+    assert g.solve_sparse(-1, one, x1) == -4
+    assert g.solve_sparse(1, np.array([m]), x1) == -4
+    assert g.solve_for_update(1, np.array([m]), None, "T") == -4
+    assert g.update(1.0) == -2
+    assert g.solve_for_update(1, one, x1, "N") == 0
+    assert g.update(1.0) == -2
+    assert g.solve_for_update(1, one, None, "T") == 0
+    assert g.update(1.0) in (0, -6)
