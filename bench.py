@@ -188,7 +188,8 @@ def main():
     b = BLUBatch(nmat, M, cap, device=local)
     if args.threads_per_basis:
         b.threads_per_basis = args.threads_per_basis
-    b.l_mem = 100000; b.u_mem = 100000; b.w_mem = 160000
+    # sized so that no basis of the batch asks for more (a Reallocate re-runs the whole batch)
+    b.l_mem = 100000; b.u_mem = 100000; b.w_mem = 500000
     stream = torch.cuda.Stream()
     b.set_stream(stream.cuda_stream)
 
@@ -273,7 +274,11 @@ def main():
         tf = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tf):
             try:
-                roofline["traffic"] = json.load(open(tf)).get("k_factorize_dram_bytes_per_launch")
+                t = json.load(open(tf))
+                # dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch (ncu --set full),
+                # measured per basis on a full wave and scaled to this launch's batch
+                roofline["traffic"] = t["k_factorize_dram_bytes_per_basis"] * nmat
+                roofline["traffic_source"] = t["source"]
             except Exception:
                 pass
         cpu = None

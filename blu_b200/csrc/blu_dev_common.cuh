@@ -21,6 +21,7 @@ static inline long long clock64() { return 0; }
 #define STAMP_BITS 40
 #define MAXROW_SMALL 64 /* pivot.rs:22 */
 #define MAXCAND 32      /* upper bound on maxsearch honoured by the search kernel */
+#define SMARK_MAX 8192   /* largest m whose row/column marks are kept in shared memory */
 
 /* per-slot view of BluDev */
 struct Mat {
@@ -98,6 +99,12 @@ struct Shm {
     int ncand;
     int cap;                  /* entries of the smem line caches */
     int *cidx, *ridx; double *cval, *work; /* dynamic smem carve-up */
+    /* fast path (m <= SMARK_MAX): line headers of the pivot row's columns / pivot column's rows,
+     * and the row/column marks, all in shared memory */
+    int *chb, *che, *chc, *rhb, *rhe, *rhc;
+    unsigned short *rm; unsigned char *cm;
+    int smarks;               /* the shared-memory marks exist */
+    int wc, wr;               /* position of the pivot in its column / row (single writer) */
     double elim_bytes; i64 nelim_div;
     i64 t_phase[12]; i64 n_kind[8];
 };

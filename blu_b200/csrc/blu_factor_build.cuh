@@ -202,16 +202,26 @@ template <int NT> __device__ void phase_build_factors(Shm &S) {
 /* ------------------------------------------------------------------ */
 /* the factorize kernel: one CTA per basis (factorize.rs:34-119)       */
 /* ------------------------------------------------------------------ */
-__device__ __forceinline__ void shm_carve(Shm &S, unsigned char *dyn, int cap, int nw) {
-    /* [cval: cap f64][work: nw*cap f64][cidx: cap i32][ridx: cap i32] */
+__device__ __forceinline__ void shm_carve(Shm &S, unsigned char *dyn, int cap, int nw, int m) {
+    /* [cval: cap f64][work: nw*cap f64][cidx: cap i32][ridx: cap i32]
+     * and when m <= SMARK_MAX: [chb che chc rhb rhe rhc: cap i32 each][rm: m u16][cm: m u8] */
     S.cap = cap;
     S.cval = (double *)dyn;
     S.work = S.cval + cap;
     S.cidx = (int *)(S.work + (size_t)nw * cap);
     S.ridx = S.cidx + cap;
+    S.smarks = m <= SMARK_MAX;
+    if (S.smarks) {
+        S.chb = S.ridx + cap; S.che = S.chb + cap; S.chc = S.che + cap;
+        S.rhb = S.chc + cap; S.rhe = S.rhb + cap; S.rhc = S.rhe + cap;
+        S.rm = (unsigned short *)(S.rhc + cap);
+        S.cm = (unsigned char *)(S.rm + ((m + 1) & ~1));
+    }
 }
-static inline size_t blu_factor_smem_bytes(int cap, int nw) {
-    return (size_t)cap * 8 + (size_t)nw * cap * 8 + (size_t)cap * 4 * 2;
+static inline size_t blu_factor_smem_bytes(int cap, int nw, int m) {
+    size_t n = (size_t)cap * 8 + (size_t)nw * cap * 8 + (size_t)cap * 4 * 2;
+    if (m <= SMARK_MAX) n += (size_t)cap * 4 * 6 + (size_t)((m + 1) & ~1) * 2 + (size_t)((m + 15) & ~15);
+    return n;
 }
 
 #ifndef FACT_MINB
@@ -227,7 +237,7 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
     for (int s = blockIdx.x; s < D.nmat; s += gridDim.x) {
         if (tid == 0) {
             mat_view(S.M, D, s);
-            shm_carve(S, dyn, cap, NT / 32);
+            shm_carve(S, dyn, cap, NT / 32, D.m);
             BluInfo *I = S.M.info;
             /* LU::reset, lu.rs:329-396 (cumulative counters survive) */
             I->m = D.m;
@@ -248,11 +258,13 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
             S.nexpand = 0; S.ngarbage = 0; S.nsearch = 0; S.factor_flops = 0;
             S.elim_bytes = 0.0; S.nelim_div = 0;
             S.w_used = 0; S.w_limit = (int)D.w_mem; S.w_half = 0;
+            S.wc = -1; S.wr = -1;
             for (int q = 0; q < 12; q++) S.t_phase[q] = 0;
             for (int q = 0; q < 8; q++) S.n_kind[q] = 0;
         }
         bsync<NT>();
         for (int i = tid; i < D.m; i += NT) S.M.marked[i] = 0;
+        if (S.smarks) for (int i = tid; i < D.m; i += NT) { S.rm[i] = 0; S.cm[i] = 0; }
         const i64 tstart = clock64();
         phase_singletons<NT>(S);
         i64 t0 = clock64();

@@ -592,6 +592,329 @@ template <int NT> __device__ void pivot_general(Shm &S, const bool small) {
     bsync<NT>();
 }
 
+
+/* ------------------------------------------------------------------ */
+/* pivot_any / pivot_small, shared-memory variant.                     */
+/* Same arithmetic and same storage order as pivot_general; what        */
+/* changes is where the per-step state lives: the pivot column and row, */
+/* the line headers (begin,end,capacity) of every line the step touches */
+/* and the row/column marks are staged in shared memory by ONE parallel */
+/* pass over the pivot column and row (the pass that also bounds the    */
+/* growth, pivot.rs:156-208), so a column update is                     */
+/*   load line -> compute -> store                                      */
+/* instead of header -> line -> mark lookup -> compute -> store.        */
+/* Used when m <= SMARK_MAX and pivot column and row fit the cache.     */
+/* ------------------------------------------------------------------ */
+template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
+    Mat &M = S.M;
+    const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int pc = S.pivot_col, pr = S.pivot_row, rank = S.rank;
+    const double droptol = M.prm.droptol, abstol = M.prm.abstol;
+    const int cbeg = M.lbeg[pc], rbeg = M.lbeg[m + pr];
+    const int cnz1 = M.lend[pc] - cbeg - 1, rnz1 = M.lend[m + pr] - rbeg - 1;
+
+    /* one pass: stage column, row and headers; bound the growth; find the pivot */
+    i64 grow = 0;
+    for (int p = tid; p <= cnz1; p += NT) {
+        const int i = M.w_idx[cbeg + p];
+        S.cidx[p] = i; S.cval[p] = M.w_val[cbeg + p];
+        if (i == pr) S.wc = p;
+        else {
+            const int b = M.lbeg[m + i], e = M.lend[m + i];
+            S.rhb[p] = b; S.rhe[p] = e; S.rhc[p] = M.lcap[m + i];
+            const int nz = e - b;
+            grow += nz + rnz1 + slack_of(M.prm, nz + rnz1);
+        }
+    }
+    for (int k = tid; k <= rnz1; k += NT) {
+        const int j = M.w_idx[rbeg + k];
+        S.ridx[k] = j;
+        if (j == pc) S.wr = k;
+        else {
+            const int b = M.lbeg[j], e = M.lend[j];
+            S.chb[k] = b; S.che[k] = e; S.chc[k] = M.lcap[j];
+            const int nz = e - b;
+            grow += nz + cnz1 + slack_of(M.prm, nz + cnz1);
+        }
+    }
+    grow = block_sum64<NT>(grow, S.kscr);
+    const int wc = S.wc, wr = S.wr;
+    if (wc < 0 || wr < 0) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
+    bsync<NT>();
+    if (tid == 0) {
+        /* pivot to the front of its column and row (pivot.rs:142-154), headers travel along */
+        int ti = S.cidx[0]; S.cidx[0] = S.cidx[wc]; S.cidx[wc] = ti;
+        double tv = S.cval[0]; S.cval[0] = S.cval[wc]; S.cval[wc] = tv;
+        S.rhb[wc] = S.rhb[0]; S.rhe[wc] = S.rhe[0]; S.rhc[wc] = S.rhc[0];
+        ti = S.ridx[0]; S.ridx[0] = S.ridx[wr]; S.ridx[wr] = ti;
+        S.chb[wr] = S.chb[0]; S.che[wr] = S.che[0]; S.chc[wr] = S.chc[0];
+        S.flag_a = 0; S.flag_b = 0;
+    }
+    bsync<NT>();
+    {
+        const int ng0 = S.ngarbage;
+        if (!w_reserve<NT>(S, grow)) return;
+        if (S.ngarbage != ng0) {      /* the lines moved: reload the headers */
+            for (int p = 1 + tid; p <= cnz1; p += NT) { const int i = S.cidx[p]; S.rhb[p] = M.lbeg[m + i]; S.rhe[p] = M.lend[m + i]; S.rhc[p] = M.lcap[m + i]; }
+            for (int k = 1 + tid; k <= rnz1; k += NT) { const int j = S.ridx[k]; S.chb[k] = M.lbeg[j]; S.che[k] = M.lend[j]; S.chc[k] = M.lcap[j]; }
+        }
+    }
+    const double pivot = S.cval[0];
+    const int *cidx = S.cidx, *ridx = S.ridx;
+    const double *cval = S.cval;
+    for (int p = 1 + tid; p <= cnz1; p += NT) S.rm[cidx[p]] = (unsigned short)p;
+    for (int k = tid; k <= rnz1; k += NT) S.cm[ridx[k]] = 1;
+    double *work = S.work + (size_t)wid * S.cap;
+    for (int p = lane; p <= cnz1; p += 32) work[p] = 0.0;
+    bsync<NT>();
+
+    const int ubase = M.u_begin[rank];
+    const i64 cbase = S.cstamp, rbase = S.rstamp;
+    double acc_bytes = 0.0;
+
+    /* column file update, pivot.rs:219-331 / 569-693: one warp per column of the pivot row */
+    for (int k = 1 + wid; k <= rnz1; k += NW) {
+        const int j = ridx[k];
+        int beg = S.chb[k], end = S.che[k], cap = S.chc[k];
+        const int oldnz = end - beg;
+        int put, where = -1;
+        double cmx = 0.0, xrj;
+        int nT;
+        if (oldnz <= 32 * REGE) {
+            int ei[REGE], emk[REGE], toff[REGE]; double ev[REGE];
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) {
+                int pos = beg + e * 32 + lane;
+                bool valid = pos < end;
+                ei[e] = valid ? M.w_idx[pos] : -1;
+                ev[e] = valid ? M.w_val[pos] : 0.0;
+            }
+            int tcount = 0; double myx = 0.0; int mine = 0;
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) {
+                if (e * 32 < oldnz) {
+                    emk[e] = ei[e] >= 0 ? (int)S.rm[ei[e]] : -1;
+                    int isT = emk[e] == 0;
+                    unsigned tm = __ballot_sync(FULLMASK, isT);
+                    toff[e] = tcount + __popc(tm & lanemask_lt());
+                    if (isT) { if (ei[e] == pr) { where = toff[e]; myx = ev[e]; mine = 1; } else { double a = fabs(ev[e]); if (a > cmx) cmx = a; } }
+                    if (emk[e] > 0) work[emk[e]] = ev[e];
+                    tcount += __popc(tm);
+                } else { toff[e] = 0; emk[e] = -1; }
+            }
+            unsigned hm = __ballot_sync(FULLMASK, mine);
+            if (hm == 0) { if (lane == 0) BLU_CHECK(S, 0); continue; }
+            const int hl = __ffs((int)hm) - 1;
+            where = __shfl_sync(FULLMASK, where, hl);
+            xrj = __shfl_sync(FULLMASK, myx, hl);
+            nT = tcount;
+            int dstb = beg + 1;
+            if (cap - (beg + nT) < cnz1) {      /* the line moves to the end of the file */
+                int room = cnz1 + slack_of(M.prm, nT + cnz1);
+                int np = 0;
+                if (lane == 0) { np = atomicAdd(&S.w_used, nT - 1 + room); atomicAdd(&S.nexpand, 1); }
+                np = __shfl_sync(FULLMASK, np, 0);
+                dstb = np; cap = np + nT - 1 + room;
+            }
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) {
+                if (emk[e] == 0) {
+                    int t = toff[e];
+                    if (t != where) {
+                        int slot = t == 0 ? where - 1 : t - 1;
+                        M.w_idx[dstb + slot] = ei[e]; M.w_val[dstb + slot] = ev[e];
+                    }
+                }
+            }
+            beg = dstb; put = dstb + nT - 1;
+            __syncwarp();
+        } else {
+            put = beg;
+            for (int base = beg; base < end; base += 32) {
+                int pos = base + lane;
+                int valid = pos < end;
+                int i = valid ? M.w_idx[pos] : 0;
+                double x = valid ? M.w_val[pos] : 0.0;
+                int mk = valid ? (int)S.rm[i] : 0;
+                int isT = valid && mk == 0;
+                if (valid && mk > 0) work[mk] = x;
+                unsigned tm = __ballot_sync(FULLMASK, isT);
+                int dst = put + __popc(tm & lanemask_lt());
+                if (isT) { if (i == pr) where = dst; else { double a = fabs(x); if (a > cmx) cmx = a; } }
+                __syncwarp();
+                if (isT) { M.w_idx[dst] = i; M.w_val[dst] = x; }
+                put += __popc(tm);
+            }
+            where = warp_max(where);
+            __syncwarp();
+            if (where < 0) { if (lane == 0) BLU_CHECK(S, 0); continue; }
+            xrj = M.w_val[where];
+            __syncwarp();
+            if (lane == 0 && where != beg) { M.w_idx[where] = M.w_idx[beg]; M.w_val[where] = M.w_val[beg]; }
+            __syncwarp();
+            nT = put - beg;
+            beg += 1;
+            if (cap - put < cnz1) {
+                int nz = put - beg;
+                int room = cnz1 + slack_of(M.prm, nT + cnz1);
+                int np = 0;
+                if (lane == 0) { np = atomicAdd(&S.w_used, nz + room); atomicAdd(&S.nexpand, 1); }
+                np = __shfl_sync(FULLMASK, np, 0);
+                for (int t = lane; t < nz; t += 32) { M.w_idx[np + t] = M.w_idx[beg + t]; M.w_val[np + t] = M.w_val[beg + t]; }
+                beg = np; put = np + nz; cap = np + nz + room;
+                __syncwarp();
+            }
+        }
+        const double a = __ddiv_rn(xrj, pivot);
+        u64 cmask = 0;
+        for (int base = 1; base <= cnz1; base += 32) {
+            int p = base + lane;
+            int valid = p <= cnz1;
+            double x = 0.0;
+            if (valid) { x = __dsub_rn(work[p], __dmul_rn(a, cval[p])); work[p] = 0.0; }
+            if (!small) {
+                if (valid) {
+                    M.w_idx[put + p - 1] = cidx[p]; M.w_val[put + p - 1] = x;
+                    double ax = fabs(x); if (ax > cmx) cmx = ax;
+                }
+            } else {
+                int keep = valid && fabs(x) > droptol;
+                unsigned km = __ballot_sync(FULLMASK, keep);
+                unsigned dm = __ballot_sync(FULLMASK, valid && !keep);
+                if (keep) {
+                    int d = put + __popc(km & lanemask_lt());
+                    M.w_idx[d] = cidx[p]; M.w_val[d] = x;
+                    double ax = fabs(x); if (ax > cmx) cmx = ax;
+                }
+                cmask |= (u64)dm << (base - 1);
+                put += __popc(km);
+            }
+        }
+        if (!small) put += cnz1;
+        cmx = warp_maxd(cmx);
+        if (lane == 0) {
+            M.lbeg[j] = beg; M.lend[j] = put; M.lcap[j] = cap;
+            M.colpiv[j] = cmx;
+            M.ckey[j] = mkkey(put - beg, cbase + k);
+            if (small) M.cancelled[k - 1] = cmask;
+            if (fabs(xrj) > droptol) { M.u_idx[ubase + k - 1] = j; M.u_val[ubase + k - 1] = xrj; }
+            else { M.u_idx[ubase + k - 1] = -2; M.u_val[ubase + k - 1] = 0.0; S.flag_a = 1; }
+            if (cmx == 0.0 || cmx < abstol) S.need_remove = 1;
+            acc_bytes += 12.0 * (oldnz + put - beg);
+        }
+        __syncwarp();
+    }
+    if (small) bsync<NT>();      /* the row update needs every column's cancellation mask */
+
+    /* row file update, pivot.rs:335-401 / 697-774: one warp per row of the pivot column */
+    for (int p = 1 + wid; p <= cnz1; p += NW) {
+        const int i = cidx[p];
+        const int line = m + i;
+        int beg = S.rhb[p], end = S.rhe[p], cap = S.rhc[p];
+        const int oldnz = end - beg;
+        int put;
+        if (oldnz <= 32 * REGE) {
+            int rj[REGE], roff[REGE];
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) {
+                int pos = beg + e * 32 + lane;
+                rj[e] = pos < end ? M.w_idx[pos] : -1;
+            }
+            int kcount = 0;
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) {
+                roff[e] = -1;
+                if (e * 32 < oldnz) {
+                    int keep = rj[e] >= 0 && S.cm[rj[e]] == 0;
+                    unsigned km = __ballot_sync(FULLMASK, keep);
+                    if (keep) roff[e] = kcount + __popc(km & lanemask_lt());
+                    kcount += __popc(km);
+                }
+            }
+            int dstb = beg;
+            if (cap - (beg + kcount) < rnz1) {
+                int room = rnz1 + slack_of(M.prm, kcount + rnz1);
+                int np = 0;
+                if (lane == 0) { np = atomicAdd(&S.w_used, kcount + room); atomicAdd(&S.nexpand, 1); }
+                np = __shfl_sync(FULLMASK, np, 0);
+                dstb = np; cap = np + kcount + room;
+            }
+            #pragma unroll
+            for (int e = 0; e < REGE; e++) if (roff[e] >= 0) M.w_idx[dstb + roff[e]] = rj[e];
+            beg = dstb; put = dstb + kcount;
+            __syncwarp();
+        } else {
+            put = beg;
+            for (int base = beg; base < end; base += 32) {
+                int pos = base + lane;
+                int valid = pos < end;
+                int j = valid ? M.w_idx[pos] : 0;
+                int keep = valid && S.cm[j] == 0;
+                unsigned km = __ballot_sync(FULLMASK, keep);
+                __syncwarp();
+                if (keep) M.w_idx[put + __popc(km & lanemask_lt())] = j;
+                put += __popc(km);
+            }
+            __syncwarp();
+            if (cap - put < rnz1) {
+                int nz = put - beg;
+                int room = rnz1 + slack_of(M.prm, nz + rnz1);
+                int np = 0;
+                if (lane == 0) { np = atomicAdd(&S.w_used, nz + room); atomicAdd(&S.nexpand, 1); }
+                np = __shfl_sync(FULLMASK, np, 0);
+                for (int t = lane; t < nz; t += 32) M.w_idx[np + t] = M.w_idx[beg + t];
+                beg = np; put = np + nz; cap = np + nz + room;
+                __syncwarp();
+            }
+        }
+        if (!small) {
+            for (int k = 1 + lane; k <= rnz1; k += 32) M.w_idx[put + k - 1] = ridx[k];
+            put += rnz1;
+        } else {
+            for (int base = 1; base <= rnz1; base += 32) {
+                int k = base + lane;
+                int keep = k <= rnz1 && ((M.cancelled[k - 1] >> (p - 1)) & 1ull) == 0;
+                unsigned km = __ballot_sync(FULLMASK, keep);
+                if (keep) M.w_idx[put + __popc(km & lanemask_lt())] = ridx[k];
+                put += __popc(km);
+            }
+        }
+        if (lane == 0) {
+            M.lbeg[line] = beg; M.lend[line] = put; M.lcap[line] = cap;
+            M.rkey[i] = mkkey(put - beg, rbase + p);
+            acc_bytes += 4.0 * (oldnz + put - beg);
+        }
+        __syncwarp();
+    }
+
+    /* L column, pivot.rs:403-415 (tentative slots, squeezed if something was dropped) */
+    const int lbase = M.l_begin_p[rank];
+    for (int p = 1 + tid; p <= cnz1; p += NT) {
+        double x = __ddiv_rn(cval[p], pivot);
+        if (fabs(x) > droptol) { M.l_idx[lbase + p - 1] = cidx[p]; M.l_val[lbase + p - 1] = x; }
+        else { M.l_idx[lbase + p - 1] = -2; M.l_val[lbase + p - 1] = 0.0; S.flag_b = 1; }
+    }
+    if (acc_bytes != 0.0) atomicAdd(&S.elim_bytes, acc_bytes);
+    bsync<NT>();
+    /* clear marks */
+    for (int p = 1 + tid; p <= cnz1; p += NT) S.rm[cidx[p]] = 0;
+    for (int k = tid; k <= rnz1; k += NT) S.cm[ridx[k]] = 0;
+    if (wid == 0) {
+        int ln = cnz1, un = rnz1;
+        if (S.flag_b) ln = warp_squeeze(M.l_idx, M.l_val, lbase, cnz1);
+        if (S.flag_a) un = warp_squeeze(M.u_idx, M.u_val, ubase, rnz1);
+        if (lane == 0) {
+            M.l_idx[lbase + ln] = -1;
+            finish_step(S, rank, lbase + ln + 1, ubase + un, pivot, cnz1 + 1, rnz1 + 1);
+            S.cstamp = cbase + rnz1 + 1;
+            S.rstamp = rbase + cnz1 + 1;
+            S.wc = -1; S.wr = -1;
+        }
+    }
+    bsync<NT>();
+}
+
 /* ------------------------------------------------------------------ */
 /* pivot_singleton_row, pivot.rs:835-926                               */
 /* ------------------------------------------------------------------ */
@@ -950,7 +1273,12 @@ template <int NT> __device__ void phase_bump(Shm &S) {
         if (nz_row == 1) { pivot_singleton_row<NT>(S); kind = 0; }
         else if (nz_col == 1) { pivot_singleton_col<NT>(S); kind = 1; }
         else if (nz_col == 2) { pivot_doubleton_col<NT>(S); kind = 2; }
-        else { pivot_general<NT>(S, nz_col - 1 <= MAXROW_SMALL); kind = nz_col - 1 <= MAXROW_SMALL ? 3 : 4; }
+        else {
+            const bool small = nz_col - 1 <= MAXROW_SMALL;
+            if (S.smarks && nz_col <= S.cap && nz_row <= S.cap) pivot_general_fast<NT>(S, small);
+            else pivot_general<NT>(S, small);
+            kind = small ? 3 : 4;
+        }
         if (tid == 0) { S.t_phase[4 + kind] += clock64() - t0; S.n_kind[kind]++; }
         if (S.status != BLU_OK) return;
         t0 = clock64();

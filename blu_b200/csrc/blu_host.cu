@@ -214,7 +214,7 @@ static void timer_stop(blu_b200 *o, int which) {
 }
 
 template <int NT> static int launch_factorize_nt(blu_b200 *o) {
-    const size_t smem = blu_factor_smem_bytes(o->cap, NT / 32);
+    const size_t smem = blu_factor_smem_bytes(o->cap, NT / 32, o->d.m);
 #ifndef BLU_EMU
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_factorize<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif

@@ -27,9 +27,17 @@ __device__ __forceinline__ void dev_garbage_perm(Mat &M) {
     }
 }
 
+/* acc += term of lanes 0..n-1 in lane order, one rounding per step: exactly the sum the
+ * reference's sequential dot-product loop produces (lu/solve_dense.rs:64-66,83-85). */
+__device__ __forceinline__ double ordered_acc(double acc, double term, int n) {
+    for (int t = 0; t < n; t++) acc = __dadd_rn(acc, __shfl_sync(FULLMASK, term, t));
+    return acc;
+}
+
 /* One warp per basis.  The sweeps are sequential over the pivot order (as in the
  * reference); the lanes share the dot product / axpy of each step and the pointer
- * loads are batched 32 pivots at a time. */
+ * loads are batched 32 pivots at a time.  Every multiply, add, subtract and divide is
+ * rounded once and sums run in the reference's order, so the result is bit-identical. */
 __global__ void __launch_bounds__(32) k_solve_dense(BluDev D, const double *rhs_all, double *lhs_all, char trans, int *status) {
     __shared__ Mat M;
     const int lane = threadIdx.x & 31;
@@ -59,8 +67,9 @@ __global__ void __launch_bounds__(32) k_solve_dense(BluDev D, const double *rhs_
                     int jj = __shfl_sync(FULLMASK, jp, t), ii = __shfl_sync(FULLMASK, ip, t);
                     int bb = __shfl_sync(FULLMASK, b, t), ee = __shfl_sync(FULLMASK, e, t);
                     double pv = __shfl_sync(FULLMASK, piv, t);
-                    double x = work[jj] / pv;
-                    for (int pos = bb + lane; pos < ee; pos += 32) work[M.w_idx[pos]] -= x * M.w_val[pos];
+                    double x = __ddiv_rn(work[jj], pv);
+                    __syncwarp();
+                    for (int pos = bb + lane; pos < ee; pos += 32) { const int r = M.w_idx[pos]; work[r] = __dsub_rn(work[r], __dmul_rn(x, M.w_val[pos])); }
                     if (lane == 0) lhs[ii] = x;
                     __syncwarp();
                 }
@@ -68,7 +77,8 @@ __global__ void __launch_bounds__(32) k_solve_dense(BluDev D, const double *rhs_
             /* etas backwards, :52-59 */
             for (int t = nforrest - 1; t >= 0; t--) {
                 double x = lhs[M.eta_row[t]];
-                for (int pos = M.r_begin[t] + lane; pos < M.r_begin[t + 1]; pos += 32) lhs[M.l_idx[pos]] -= x * M.l_val[pos];
+                __syncwarp();
+                for (int pos = M.r_begin[t] + lane; pos < M.r_begin[t + 1]; pos += 32) { const int r = M.l_idx[pos]; lhs[r] = __dsub_rn(lhs[r], __dmul_rn(x, M.l_val[pos])); }
                 __syncwarp();
             }
             /* L', :63-73 */
@@ -82,9 +92,12 @@ __global__ void __launch_bounds__(32) k_solve_dense(BluDev D, const double *rhs_
                     ne &= ~(1u << t);
                     int bb = __shfl_sync(FULLMASK, b, t), ee = __shfl_sync(FULLMASK, e, t), ii = __shfl_sync(FULLMASK, ip, t);
                     double x = 0.0;
-                    for (int pos = bb + lane; pos < ee; pos += 32) x += lhs[M.l_idx[pos]] * M.l_val[pos];
-                    x = warp_sumd(x);
-                    if (lane == 0) lhs[ii] -= x;
+                    for (int cb = bb; cb < ee; cb += 32) {
+                        const int pos = cb + lane;
+                        const double term = pos < ee ? __dmul_rn(lhs[M.l_idx[pos]], M.l_val[pos]) : 0.0;
+                        x = ordered_acc(x, term, ee - cb < 32 ? ee - cb : 32);
+                    }
+                    if (lane == 0) lhs[ii] = __dsub_rn(lhs[ii], x);
                     __syncwarp();
                 }
             }
@@ -100,18 +113,25 @@ __global__ void __launch_bounds__(32) k_solve_dense(BluDev D, const double *rhs_
                     ne &= ne - 1;
                     int bb = __shfl_sync(FULLMASK, b, t), ee = __shfl_sync(FULLMASK, e, t), ii = __shfl_sync(FULLMASK, ip, t);
                     double x = 0.0;
-                    for (int pos = bb + lane; pos < ee; pos += 32) x += work[M.l_idx[pos]] * M.l_val[pos];
-                    x = warp_sumd(x);
-                    if (lane == 0) work[ii] -= x;
+                    for (int cb = bb; cb < ee; cb += 32) {
+                        const int pos = cb + lane;
+                        const double term = pos < ee ? __dmul_rn(work[M.l_idx[pos]], M.l_val[pos]) : 0.0;
+                        x = ordered_acc(x, term, ee - cb < 32 ? ee - cb : 32);
+                    }
+                    if (lane == 0) work[ii] = __dsub_rn(work[ii], x);
                     __syncwarp();
                 }
             }
             /* etas, :93-102 */
             for (int t = 0; t < nforrest; t++) {
                 double x = 0.0;
-                for (int pos = M.r_begin[t] + lane; pos < M.r_begin[t + 1]; pos += 32) x += work[M.l_idx[pos]] * M.l_val[pos];
-                x = warp_sumd(x);
-                if (lane == 0) work[M.eta_row[t]] -= x;
+                const int rb = M.r_begin[t], re = M.r_begin[t + 1];
+                for (int cb = rb; cb < re; cb += 32) {
+                    const int pos = cb + lane;
+                    const double term = pos < re ? __dmul_rn(work[M.l_idx[pos]], M.l_val[pos]) : 0.0;
+                    x = ordered_acc(x, term, re - cb < 32 ? re - cb : 32);
+                }
+                if (lane == 0) work[M.eta_row[t]] = __dsub_rn(work[M.eta_row[t]], x);
                 __syncwarp();
             }
             /* U, :106-118 (column-wise axpy form, terminator-delimited) */
@@ -125,12 +145,13 @@ __global__ void __launch_bounds__(32) k_solve_dense(BluDev D, const double *rhs_
                     int jj = __shfl_sync(FULLMASK, jp, t), ii = __shfl_sync(FULLMASK, ip, t);
                     int bb = __shfl_sync(FULLMASK, b, t);
                     double pv = __shfl_sync(FULLMASK, piv, t);
-                    double x = work[ii] / pv;
+                    double x = __ddiv_rn(work[ii], pv);
+                    __syncwarp();
                     for (int pos = bb;; pos += 32) {
                         int idx = M.u_idx[pos + lane];
                         unsigned term = __ballot_sync(FULLMASK, idx < 0);
                         int nvalid = term ? __ffs((int)term) - 1 : 32;
-                        if (lane < nvalid) work[idx] -= x * M.u_val[pos + lane];
+                        if (lane < nvalid) work[idx] = __dsub_rn(work[idx], __dmul_rn(x, M.u_val[pos + lane]));
                         if (term) break;
                     }
                     if (lane == 0) lhs[jj] = x;

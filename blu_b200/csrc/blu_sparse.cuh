@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(32) k_solve_sparse(BluDev D, int nrhs, const i
     }
     if (st != BLU_OK) { if (lane == 0) { scal[0] = st; scal[1] = 0; } return; }
     for (int n = lane; n < nrhs; n += 32) C.irhs[n] = (int)irhs64[n];
-    if (lane == 0) { dev_garbage_perm(M); I->addmem_l = I->addmem_u = I->addmem_w = 0; }
+    if (lane == 0) I->addmem_l = I->addmem_u = I->addmem_w = 0;
     __syncwarp();
 
     int nz = 0;

@@ -125,5 +125,5 @@ def replay_updates(g, o, m, pool, niter, rng_seed=5, check_dense=True):
                 _, xo = o.solve_dense(b, tr)
                 sg, xg = g.solve_dense(b, tr)
                 assert sg == 0
-                assert np.abs(xg - xo).max() <= 1e-12 * np.abs(xo).max(), (it, tr)
+                assert np.array_equal(xg, xo), (it, tr, np.abs(xg - xo).max() / np.abs(xo).max())
     return kinds

@@ -42,7 +42,7 @@ def test_emu_factorize_solve(emu, nt, seed):
         _, xo = o.solve_dense(b, tr)
         sg, xg = g.solve_dense(b, tr)
         assert sg == 0
-        assert np.abs(xg - xo).max() <= 1e-12 * np.abs(xo).max()
+        assert np.array_equal(xg, xo)      # ordered sums: bit-identical, not merely 1e-12
 
 
 def test_emu_dense_columns(emu):
@@ -82,7 +82,7 @@ def test_emu_batch(emu):
         for key in fo:
             assert np.array_equal(fo[key], fg[key]), key
         _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
-        assert np.abs(x[k] - xo).max() <= 1e-12 * np.abs(xo).max()
+        assert np.array_equal(x[k], xo)
 
 
 def test_emu_solve_sparse(emu):
