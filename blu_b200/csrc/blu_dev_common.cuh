@@ -104,6 +104,7 @@ struct Shm {
     int *chb, *che, *chc, *rhb, *rhe, *rhc;
     unsigned short *rm; unsigned char *cm;
     int smarks;               /* the shared-memory marks exist */
+    int dyn_bytes;            /* size of the dynamic shared memory (reused as scratch outside the pivot loop) */
     int wc, wr;               /* position of the pivot in its column / row (single writer) */
     double elim_bytes; i64 nelim_div;
     i64 t_phase[12]; i64 n_kind[8];
@@ -256,6 +257,17 @@ template <int NT> __device__ __forceinline__ double block_mind(double v, double 
     for (int w = 1; w < NW; w++) r = scr[w] < r ? scr[w] : r;
     bsync<NT>();
     return r;
+}
+
+/* pull [p, p+bytes) towards the SM ahead of use: one 128-byte line per lane and round (L2 prefetch) */
+__device__ __forceinline__ void warp_prefetch_l2(const void *p, int bytes) {
+#ifndef BLU_EMU
+    const char *c = (const char *)p;
+    for (int off = (threadIdx.x & 31) * 128; off < bytes; off += 32 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+#else
+    (void)p; (void)bytes;
+#endif
 }
 
 /* record the first failed device-side invariant (kept live like the reference's assert!s) */

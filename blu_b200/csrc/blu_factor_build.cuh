@@ -62,7 +62,9 @@ template <int NT> __device__ void phase_build_factors(Shm &S) {
     /* L row-wise, build_factors.rs:242-274.  Counting in parallel; the scatter runs in
      * pivot order on one warp so every row is filled in ascending pivot step exactly
      * as the reference does (no atomics => deterministic storage order). */
-    int *cnt = M.iwork1;
+    /* per-row / per-column fill pointers live in shared memory when m of them fit (the pivot-loop
+     * buffers are idle here): the ordered scatters below are read-modify-write chains on them */
+    int *cnt = (size_t)m * sizeof(int) <= (size_t)S.dyn_bytes ? (int *)S.cval : M.iwork1;
     for (int i = tid; i < m; i += NT) cnt[i] = 0;
     bsync<NT>();
     for (int g = tid; g < l_nz + m; g += NT) { int i = M.l_idx[g]; if (i >= 0) atomicAdd(&cnt[i], 1); }
@@ -86,22 +88,31 @@ template <int NT> __device__ void phase_build_factors(Shm &S) {
     }
     bsync<NT>();
     if (wid == 0) {
-        for (int k = 0; k < m; k++) {
-            const int b = M.l_begin_p[k], e = M.l_begin_p[k + 1] - 1;
-            if (e <= b) continue;
-            const int ipivot = M.pivotrow[k];
-            for (int g = b + lane; g < e; g += 32) {
-                int r = M.l_idx[g];
-                int dst = cnt[r]; cnt[r] = dst + 1;
-                M.l_idx[dst] = ipivot; M.l_val[dst] = M.l_val[g];
+        /* pivot order, one warp: every row is filled in ascending pivot step exactly as the reference
+         * does.  Column pointers are fetched 32 pivots at a time; empty columns cost nothing. */
+        for (int kb = 0; kb < m; kb += 32) {
+            const int k = kb + lane;
+            const int b = k < m ? M.l_begin_p[k] : 0, e = k < m ? M.l_begin_p[k + 1] - 1 : 0;
+            const int ipv = k < m ? M.pivotrow[k] : 0;
+            unsigned ne = __ballot_sync(FULLMASK, e > b);
+            while (ne) {
+                const int t = __ffs((int)ne) - 1;
+                ne &= ne - 1;
+                const int bb = __shfl_sync(FULLMASK, b, t), ee = __shfl_sync(FULLMASK, e, t), ii = __shfl_sync(FULLMASK, ipv, t);
+                for (int g = bb + lane; g < ee; g += 32) {
+                    const int r = M.l_idx[g];
+                    const double v = M.l_val[g];
+                    const int dst = cnt[r]; cnt[r] = dst + 1;
+                    M.l_idx[dst] = ii; M.l_val[dst] = v;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
     bsync<NT>();
 
     /* U row-wise into the W file in pivot order with slack, build_factors.rs:286-351 */
-    int *ucnt = M.iwork1;      /* per column j: entries of U column j */
+    int *ucnt = cnt;           /* per column j: entries of U column j */
     for (int j = tid; j < m; j += NT) ucnt[j] = 0;
     bsync<NT>();
     {
@@ -163,15 +174,23 @@ template <int NT> __device__ void phase_build_factors(Shm &S) {
     }
     bsync<NT>();
     if (wid == 0) {
-        for (int k = 0; k < m; k++) {
-            const int jp = M.pivotcol[k], ip = M.pivotrow[k];
-            const int b = M.lbeg[jp], e = M.lend[jp];
-            for (int pos = b + lane; pos < e; pos += 32) {
-                int j = M.w_idx[pos];
-                int dst = ucnt[j]; ucnt[j] = dst + 1;
-                M.u_idx[dst] = ip; M.u_val[dst] = M.w_val[pos];
+        for (int kb = 0; kb < m; kb += 32) {
+            const int k = kb + lane;
+            const int jp = k < m ? M.pivotcol[k] : 0, ipv = k < m ? M.pivotrow[k] : 0;
+            const int b = k < m ? M.lbeg[jp] : 0, e = k < m ? M.lend[jp] : 0;
+            unsigned ne = __ballot_sync(FULLMASK, e > b);
+            while (ne) {
+                const int t = __ffs((int)ne) - 1;
+                ne &= ne - 1;
+                const int bb = __shfl_sync(FULLMASK, b, t), ee = __shfl_sync(FULLMASK, e, t), ii = __shfl_sync(FULLMASK, ipv, t);
+                for (int pos = bb + lane; pos < ee; pos += 32) {
+                    const int j = M.w_idx[pos];
+                    const double v = M.w_val[pos];
+                    const int dst = ucnt[j]; ucnt[j] = dst + 1;
+                    M.u_idx[dst] = ii; M.u_val[dst] = v;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
     bsync<NT>();
@@ -211,6 +230,7 @@ __device__ __forceinline__ void shm_carve(Shm &S, unsigned char *dyn, int cap, i
     S.cidx = (int *)(S.work + (size_t)nw * cap);
     S.ridx = S.cidx + cap;
     S.smarks = m <= SMARK_MAX;
+    S.dyn_bytes = (int)(cap * 8 + (size_t)nw * cap * 8 + cap * 4 * 2 + (m <= SMARK_MAX ? (size_t)cap * 4 * 6 + (size_t)((m + 1) & ~1) * 2 + (size_t)((m + 15) & ~15) : 0));
     if (S.smarks) {
         S.chb = S.ridx + cap; S.che = S.chb + cap; S.chc = S.che + cap;
         S.rhb = S.chc + cap; S.rhe = S.rhb + cap; S.rhc = S.rhe + cap;

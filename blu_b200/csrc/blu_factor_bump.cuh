@@ -124,16 +124,25 @@ template <int NT> __device__ void markowitz_search(Shm &S) {
     while (ncand < maxsearch) {
         u64 k0 = KEY_INF, k1 = KEY_INF, k2 = KEY_INF;
         int j0 = -1, j1 = -1, j2 = -1;
-        for (int t = tid; t < nact; t += NT) {
-            int j = M.acols[t];
-            u64 k = M.ckey[j];
-            if (k == KEY_INF || (have_prev && k <= prev)) continue;
-            if (k < k2) {
-                if (k < k1) {
-                    k2 = k1; j2 = j1;
-                    if (k < k0) { k1 = k0; j1 = j0; k0 = k; j0 = j; }
-                    else { k1 = k; j1 = j; }
-                } else { k2 = k; j2 = j; }
+        /* four independent (slot -> column -> key) chains in flight per thread: the loop is a
+         * pure latency chain otherwise (measured: 17k cycles per search before) */
+        for (int t0 = tid; t0 < nact; t0 += 4 * NT) {
+            int jj[4]; u64 kk[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) { const int t = t0 + u * NT; jj[u] = t < nact ? M.acols[t] : -1; }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) kk[u] = jj[u] >= 0 ? M.ckey[jj[u]] : KEY_INF;
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const u64 k = kk[u]; const int j = jj[u];
+                if (k == KEY_INF || (have_prev && k <= prev)) continue;
+                if (k < k2) {
+                    if (k < k1) {
+                        k2 = k1; j2 = j1;
+                        if (k < k0) { k1 = k0; j1 = j0; k0 = k; j0 = j; }
+                        else { k1 = k; j1 = j; }
+                    } else { k2 = k; j2 = j; }
+                }
             }
         }
         int got = 0;
@@ -675,6 +684,11 @@ template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
 
     /* column file update, pivot.rs:219-331 / 569-693: one warp per column of the pivot row */
     for (int k = 1 + wid; k <= rnz1; k += NW) {
+        if (k + NW <= rnz1) {      /* next line of this warp: start pulling it in now */
+            const int nb = S.chb[k + NW], nn = S.che[k + NW] - nb;
+            warp_prefetch_l2(M.w_idx + nb, nn * 4);
+            warp_prefetch_l2(M.w_val + nb, nn * 8);
+        }
         const int j = ridx[k];
         int beg = S.chb[k], end = S.che[k], cap = S.chc[k];
         const int oldnz = end - beg;
@@ -809,6 +823,7 @@ template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
 
     /* row file update, pivot.rs:335-401 / 697-774: one warp per row of the pivot column */
     for (int p = 1 + wid; p <= cnz1; p += NW) {
+        if (p + NW <= cnz1) warp_prefetch_l2(M.w_idx + S.rhb[p + NW], (S.rhe[p + NW] - S.rhb[p + NW]) * 4);
         const int i = cidx[p];
         const int line = m + i;
         int beg = S.rhb[p], end = S.rhe[p], cap = S.rhc[p];
