@@ -214,11 +214,13 @@ def main():
     l0 = b.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fact_ms = []
+    norms_ms = []
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(args.steps):
             resident_step()
-            fact_ms.append(b.last_kernel_ms(0))
+            fact_ms.append(b.last_kernel_ms(0) - b.last_kernel_ms(2))   # k_factorize alone (2 = the condest/residual kernel)
+            norms_ms.append(b.last_kernel_ms(2))
         e1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -270,7 +272,9 @@ def main():
         achieved = bytes_f / (avg_fact_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_factorize", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": bytes_f, "avg_launch_ms": avg_fact_ms}
+                    "algorithmic_bytes_per_launch": bytes_f, "avg_launch_ms": avg_fact_ms,
+                    "other_kernels_ms_per_step": {"k_factor_norms (condest x2 + residual_test, factorize.rs:121-147)": float(np.mean(norms_ms)),
+                                                  "k_solve_dense": float(b.last_kernel_ms(1))}}
         tf = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tf):
             try:
@@ -282,7 +286,7 @@ def main():
             except Exception:
                 pass
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported at N=1 only (rank 0)
             import oracle_lib
             cores = host_cores()
             ns = int(min(nmat, max(cores * args.ref_per_core, 8)))

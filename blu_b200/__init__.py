@@ -7,3 +7,4 @@ There is no CPU fallback: without the CUDA library/device every call fails loudl
 """
 from .blu import BLU, BLUBatch, Status, load_library, library_path  # noqa: F401
 from . import gen  # noqa: F401
+from .maxvolume import maxvolume  # noqa: F401

@@ -39,6 +39,7 @@ struct Mat {
     int *lbeg, *lend, *lcap;
     u64 *ckey, *rkey;
     int *l_begin_p, *u_begin, *l_begin, *lt_begin, *lt_begin_p, *p, *r_begin, *eta_row;
+    int *dep_lt, *dep_lc, *dep_uc, *len_uc;
     int *pivotcol, *pivotrow;
     int *rowmark, *colmark, *marked, *iwork1, *pstack, *acols, *tmpi;
     u64 *cancelled;
@@ -66,6 +67,7 @@ __device__ __forceinline__ void mat_view(Mat &M, const BluDev &D, int s) {
     M.l_begin = D.l_begin + S * (m + 1); M.lt_begin = D.lt_begin + S * (m + 1);
     M.lt_begin_p = D.lt_begin_p + S * (m + 1); M.p = D.p + S * (m + 1);
     M.r_begin = D.r_begin + S * (m + 1); M.eta_row = D.eta_row + S * (m + 1);
+    M.dep_lt = D.dep_lt + S * m; M.dep_lc = D.dep_lc + S * m; M.dep_uc = D.dep_uc + S * m; M.len_uc = D.len_uc + S * m;
     M.pivotcol = D.pivotcol + S * (2 * m + 2); M.pivotrow = D.pivotrow + S * (2 * m + 2);
     M.rowmark = D.rowmark + S * m; M.colmark = D.colmark + S * m; M.marked = D.marked + S * m;
     M.iwork1 = D.iwork1 + S * (2 * m + 2); M.pstack = D.pstack + S * m;
@@ -267,6 +269,16 @@ __device__ __forceinline__ void warp_prefetch_l2(const void *p, int bytes) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
 #else
     (void)p; (void)bytes;
+#endif
+}
+
+/* one address per lane: start pulling the line that holds *p into L1 (used by the sequential sweeps:
+ * the 32 line starts of the next 32 pivots are requested together, long before they are needed) */
+__device__ __forceinline__ void lane_prefetch(const void *p) {
+#ifndef BLU_EMU
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
 #endif
 }
 

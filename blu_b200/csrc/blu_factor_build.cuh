@@ -208,6 +208,56 @@ template <int NT> __device__ void phase_build_factors(Shm &S) {
         pv = fabs(pv);
         mx = fmax(mx, pv); mn = fmin(mn, pv);
     }
+    /* how far back (forward) each row of L / column of L / column of U reaches in the pivot order: lets
+     * the dot-product sweeps of the dense solves and of condest/residual_test run a whole batch of
+     * pivots side by side whenever they do not depend on each other (blu_solve.cuh, dev_dot_sweep) */
+    for (int k = tid; k < m; k += NT) {
+        int d = -1;
+        for (int pos = M.lt_begin_p[k]; M.l_idx[pos] >= 0; pos++) { const int q = M.prank[M.l_idx[pos]]; d = q > d ? q : d; }
+        M.dep_lt[k] = d;
+        d = m;
+        for (int pos = M.l_begin_p[k]; M.l_idx[pos] >= 0; pos++) { const int q = M.prank[M.l_idx[pos]]; d = q < d ? q : d; }
+        M.dep_lc[k] = d;
+        d = -1;
+        int n = 0;
+        for (int pos = M.u_begin[M.pivotrow[k]]; M.u_idx[pos] >= 0; pos++, n++) { const int q = M.prank[M.u_idx[pos]]; d = q > d ? q : d; }
+        M.dep_uc[k] = d; M.len_uc[k] = n;
+    }
+    /* The row-wise copy of B is dead after the bump set-up: re-sort every row by the pivot position of
+     * its column, so that residual_test / matrix_norm (which the reference accumulates column by column
+     * in pivot order, residual_test.rs:60-70, matrix_norm.rs:20-33) can be evaluated row by row, all
+     * rows in parallel, with every row's terms in exactly the reference's order. */
+    for (int i = tid; i < m; i += NT) {
+        const int rb = M.bt_ptr[i], n = M.bt_ptr[i + 1] - rb;
+        if (n > 1 && n <= 32) {
+            for (int a = 1; a < n; a++) {
+                const int j = M.bt_idx[rb + a]; const double x = M.bt_val[rb + a];
+                const int key = M.qrank[j];
+                int q = a - 1;
+                while (q >= 0 && M.qrank[M.bt_idx[rb + q]] > key) { M.bt_idx[rb + q + 1] = M.bt_idx[rb + q]; M.bt_val[rb + q + 1] = M.bt_val[rb + q]; q--; }
+                M.bt_idx[rb + q + 1] = j; M.bt_val[rb + q + 1] = x;
+            }
+        }
+    }
+    bsync<NT>();
+    {   /* long rows: one warp each, rank sort on the keys (distinct: one entry per column); scratch = tmpi / work1 */
+        for (int i = 0; i < m; i++) {          /* uniform scan: every thread walks the same pointers */
+            const int rb = M.bt_ptr[i], n = M.bt_ptr[i + 1] - rb;
+            if (n <= 32) continue;
+            int *sidx = M.tmpi, *skey = M.tmpi + 2 * m; double *sval = M.work1;
+            for (int e = tid; e < n; e += NT) skey[e] = M.qrank[M.bt_idx[rb + e]];
+            bsync<NT>();
+            for (int e = tid; e < n; e += NT) {
+                const int ke = skey[e];
+                int rnk = 0;
+                for (int f = 0; f < n; f++) rnk += skey[f] < ke;
+                sidx[rnk] = M.bt_idx[rb + e]; sval[rnk] = M.bt_val[rb + e];
+            }
+            bsync<NT>();
+            for (int e = tid; e < n; e += NT) { M.bt_idx[rb + e] = sidx[e]; M.bt_val[rb + e] = sval[e]; }
+            bsync<NT>();
+        }
+    }
     mx = block_maxd<NT>(mx, S.dscr);
     mn = block_mind<NT>(mn, S.dscr);
     if (tid == 0) {
@@ -245,10 +295,11 @@ static inline size_t blu_factor_smem_bytes(int cap, int nw, int m) {
 }
 
 #ifndef FACT_MINB
-/* resident CTAs per SM the register allocation is sized for: 1024 threads per SM => 64
- * registers per thread.  Measured on B200 (profiles/r1b_sweep.txt): 8 CTAs x 128 threads with
- * a few spills beat 4 CTAs x 128 registers by 30 % -- the kernel is latency-bound. */
-#define FACT_MINB(NT) (1024 / (NT) > 0 ? 1024 / (NT) : 1)
+/* resident CTAs per SM the register allocation is sized for.  Measured on B200 with 128-thread
+ * CTAs (profiles/r1b_sweep.txt, r1h_sweep.txt): 4 CTAs/SM (128 registers) 7.3 k bases/s, 6 (80) 8.6 k,
+ * 7 (72) 10.1 k, 8 (64, more spills) 9.5 k, 9 (56) 7.6 k -- the kernel is latency-bound, so occupancy
+ * pays until the spills cost more than the extra warps hide. */
+#define FACT_MINB(NT) (896 / (NT) > 0 ? 896 / (NT) : 1)
 #endif
 template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factorize(BluDev D, int cap) {
     BLU_DYN_SMEM(dyn);

@@ -43,6 +43,8 @@ struct blu_b200 {
     int64_t *d_irhs; double *d_xrhs; int64_t *d_ilhs; double *d_xout; int *d_scal;
     int *h_scal; int64_t *h_ilhs; double *h_xout;   /* pinned */
     int info_dirty;             /* device info block is newer than hinfo */
+    int norms;                  /* run condest/residual_test after every factorization (factorize.rs:121-147) */
+    double last_norms_ms;
     /* get_factors staging */
     int64_t *gf_i; double *gf_x; int64_t gf_cap;
     std::vector<BluInfo> hinfo;
@@ -105,8 +107,9 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     o->device = device; o->single = single;
     o->realloc_factor = 1.5;   /* blu.rs:68 */
     o->nthreads = 128; o->cap = 256;
+    if (const char *e = getenv("BLU_B200_CAP")) { int c = atoi(e); if (c >= 64 && c <= 4096) o->cap = c & ~31; }   /* tuning knob: entries of the shared-memory line caches */
     o->launches = 0; o->nrealloc = 0; o->last_ms[0] = o->last_ms[1] = 0.0;
-    o->have_b = 0; o->info_dirty = 0;
+    o->have_b = 0; o->info_dirty = 0; o->norms = 1; o->last_norms_ms = 0.0;
     o->h_scal = nullptr; o->h_ilhs = nullptr; o->h_xout = nullptr;
     o->time_factorize = o->time_solve = o->time_update = 0.0;
     BluDev &d = o->d;
@@ -131,6 +134,7 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     A(d.l_begin_p, n * (M + 1)); A(d.u_begin, n * (M + 1)); A(d.l_begin, n * (M + 1));
     A(d.lt_begin, n * (M + 1)); A(d.lt_begin_p, n * (M + 1)); A(d.p, n * (M + 1));
     A(d.r_begin, n * (M + 1)); A(d.eta_row, n * (M + 1));
+    A(d.dep_lt, n * M); A(d.dep_lc, n * M); A(d.dep_uc, n * M); A(d.len_uc, n * M);
     A(d.pivotcol, n * (2 * M + 2)); A(d.pivotrow, n * (2 * M + 2));
     A(d.rowmark, n * M); A(d.colmark, n * M); A(d.marked, n * M);
     A(d.iwork1, n * (2 * M + 2)); A(d.pstack, n * M); A(d.acols, n * M); A(d.tmpi, n * (4 * M + 4));
@@ -216,7 +220,8 @@ static void timer_stop(blu_b200 *o, int which) {
 template <int NT> static int launch_factorize_nt(blu_b200 *o) {
     const size_t smem = blu_factor_smem_bytes(o->cap, NT / 32, o->d.m);
 #ifndef BLU_EMU
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_factorize<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    /* static + dynamic shared memory beyond 48 KB needs the opt-in (the static part is ~2.2 KB) */
+    if (smem > 40 * 1024) CK(cudaFuncSetAttribute(k_factorize<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
     BLU_LAUNCH(k_factorize<NT>, o->d.nmat, NT, smem, o->stream, o->d, o->cap);
     o->launches++;
@@ -266,7 +271,21 @@ static int factorize_resident(blu_b200 *o) {
         for (auto &I : o->hinfo) {
             if (I.status == BLU_REALLOCATE) { need = 1; al = std::max<int64_t>(al, I.addmem_l); au = std::max<int64_t>(au, I.addmem_u); aw = std::max<int64_t>(aw, I.addmem_w); }
         }
-        if (!need) { o->last_ms[0] = total_ms; return BLU_OK; }
+        if (!need) {
+            /* factorize.rs:121-147: condest(L), condest(U), residual_test (+ matrix_norm) */
+            if (o->norms) {
+                timer_start(o);
+                BLU_LAUNCH(k_factor_norms, d.nmat, 128, 0, o->stream, d);
+                o->launches++;
+                CK(cudaGetLastError());
+                timer_stop(o, 0);
+                total_ms += o->last_ms[0];
+                o->last_norms_ms = o->last_ms[0];
+                if ((st = fetch_info(o)) != BLU_OK) return st;
+            }
+            o->last_ms[0] = total_ms;
+            return BLU_OK;
+        }
         /* lu_realloc_obj, blu.rs:345-377 */
         double f = o->realloc_factor < 1.0 ? 1.0 : o->realloc_factor;
         if (al > 0) d.l_mem = (int64_t)(f * (double)(d.l_mem + al)) + 1;
@@ -294,13 +313,15 @@ extern "C" int blu_batch_upload(blu_batch_t *o, const int64_t *b_begin, const in
     CK(cudaSetDevice(o->device));
     const size_t n = (size_t)o->d.nmat, m = (size_t)o->d.m;
     if (b_begin) {
-        if (!b_end || !b_i || !b_x || bnz_total < 0) return BLU_ERROR_INVALID_ARGUMENT;
+        if (!b_end || bnz_total < 0 || (bnz_total > 0 && (!b_i || !b_x))) return BLU_ERROR_INVALID_ARGUMENT;
         int st = ensure_b_cap(o, bnz_total);
         if (st != BLU_OK) return st;
         CK(cudaMemcpyAsync(o->db_begin, b_begin, n * m * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
         CK(cudaMemcpyAsync(o->db_end, b_end, n * m * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
-        CK(cudaMemcpyAsync(o->db_i, b_i, (size_t)bnz_total * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
-        CK(cudaMemcpyAsync(o->db_x, b_x, (size_t)bnz_total * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+        if (bnz_total > 0) {
+            CK(cudaMemcpyAsync(o->db_i, b_i, (size_t)bnz_total * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
+            CK(cudaMemcpyAsync(o->db_x, b_x, (size_t)bnz_total * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+        }
         o->have_b = 1;
     }
     if (rhs) CK(cudaMemcpyAsync(o->d_rhs, rhs, n * m * sizeof(double), cudaMemcpyHostToDevice, o->stream));
@@ -339,7 +360,7 @@ extern "C" int blu_batch_download(blu_batch_t *o, double *lhs, int *status) {
 
 extern "C" int blu_batch_factorize(blu_batch_t *o, const int64_t *b_begin, const int64_t *b_end,
                                    const int64_t *b_i, const double *b_x, int64_t bnz_total, int *status) {
-    if (!o || !b_begin || !b_end || !b_i || !b_x) return BLU_ERROR_INVALID_ARGUMENT;
+    if (!o || !b_begin || !b_end) return BLU_ERROR_INVALID_ARGUMENT;
     int st = blu_batch_upload(o, b_begin, b_end, b_i, b_x, bnz_total, nullptr);
     if (st != BLU_OK) return st;
     st = factorize_resident(o);
@@ -370,7 +391,7 @@ extern "C" int blu_batch_synchronize(blu_batch_t *o) {
     CK(cudaStreamSynchronize(o->stream));
     return BLU_OK;
 }
-extern "C" double blu_batch_last_kernel_ms(blu_batch_t *o, int which) { return o && which >= 0 && which < 2 ? o->last_ms[which] : 0.0; }
+extern "C" double blu_batch_last_kernel_ms(blu_batch_t *o, int which) { return !o ? 0.0 : which == 2 ? o->last_norms_ms : (which >= 0 && which < 2 ? o->last_ms[which] : 0.0); }
 extern "C" int64_t blu_batch_launch_count(blu_batch_t *o) { return o ? o->launches : 0; }
 
 static double info_value(blu_b200 *o, const BluInfo &I, int what) {
@@ -423,6 +444,7 @@ static double info_value(blu_b200 *o, const BluInfo &I, int what) {
     default:
         if (what >= BLU_I_T_PHASE0 && what < BLU_I_T_PHASE0 + 12) return (double)I.t_phase[what - BLU_I_T_PHASE0];
         if (what >= BLU_I_N_KIND0 && what < BLU_I_N_KIND0 + 8) return (double)I.n_kind[what - BLU_I_N_KIND0];
+        if (what >= BLU_I_NORMS_CYC0 && what < BLU_I_NORMS_CYC0 + 16) return (double)I.norms_cycles[what - BLU_I_NORMS_CYC0];
         return 0.0;
     }
 }
@@ -448,6 +470,7 @@ extern "C" int blu_set_param(blu_t *o, int what, double v) {
     case BLU_P_SPARSE_THRES: p.sparse_thres = v; break;
     case BLU_P_SEARCH_ROWS: p.search_rows = (int)v; break;
     case BLU_P_REALLOC_FACTOR: o->realloc_factor = v; break;
+    case BLU_P_NORMS: o->norms = v != 0.0; break;
     case BLU_P_THREADS_PER_BASIS: {
         int t = (int)v;
         if (t != 32 && t != 64 && t != 128 && t != 256 && t != 512 && t != 1024) return BLU_ERROR_INVALID_ARGUMENT;
@@ -486,6 +509,7 @@ extern "C" double blu_get_param(const blu_t *o, int what) {
     case BLU_P_SPARSE_THRES: return p.sparse_thres;
     case BLU_P_SEARCH_ROWS: return p.search_rows;
     case BLU_P_REALLOC_FACTOR: return o->realloc_factor;
+    case BLU_P_NORMS: return o->norms;
     case BLU_P_L_MEM: return (double)o->d.l_mem;
     case BLU_P_U_MEM: return (double)o->d.u_mem;
     case BLU_P_W_MEM: return (double)o->d.w_mem;
@@ -539,7 +563,7 @@ extern "C" int blu_create(blu_t **out, int64_t m, int64_t b_nz, int device) { re
 extern "C" void blu_destroy(blu_t *o) { destroy_common(o); }
 
 extern "C" int blu_factorize(blu_t *o, const int64_t *b_begin, const int64_t *b_end, const int64_t *b_i, const double *b_x) {
-    if (!o || !b_begin || !b_end || !b_i || !b_x) return BLU_ERROR_INVALID_ARGUMENT;
+    if (!o || !b_begin || !b_end) return BLU_ERROR_INVALID_ARGUMENT;   /* b_i / b_x may be null when B has no entries */
     if (o->d.nmat != 1) return BLU_ERROR_INVALID_CALL;
     const int64_t m = o->d.m;
     /* gather the referenced columns into a compact staging copy (B may live inside a
@@ -550,6 +574,7 @@ extern "C" int blu_factorize(blu_t *o, const int64_t *b_begin, const int64_t *b_
         if (b_end[j] < b_begin[j]) return BLU_ERROR_INVALID_ARGUMENT;   /* singletons.rs:122-131 */
         o->hb_begin[(size_t)j] = nnz; nnz += b_end[j] - b_begin[j]; o->hb_end[(size_t)j] = nnz;
     }
+    if (nnz > 0 && (!b_i || !b_x)) return BLU_ERROR_INVALID_ARGUMENT;
     o->hb_i.resize((size_t)nnz); o->hb_x.resize((size_t)nnz);
     for (int64_t j = 0; j < m; j++) {
         const int64_t n = b_end[j] - b_begin[j];

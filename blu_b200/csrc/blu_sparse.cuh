@@ -44,11 +44,7 @@ __device__ __forceinline__ double sp_bcastd(double v) { return __shfl_sync(FULLM
 /* acc (+|-)= term of lanes 0..n-1 in lane order, one rounding per step: the value the
  * reference's sequential loop produces. */
 __device__ __forceinline__ double sp_ordered_acc(double acc, double term, int n, bool subtract) {
-    for (int t = 0; t < n; t++) {
-        double v = __shfl_sync(FULLMASK, term, t);
-        acc = subtract ? __dsub_rn(acc, v) : __dadd_rn(acc, v);
-    }
-    return acc;
+    return subtract ? ordered_sub(acc, term, n) : ordered_acc(acc, term, n);
 }
 
 /* update.rs:26-42 with an explicit end: position of j in [start,end) or end.  Warp, uniform. */
@@ -156,6 +152,7 @@ __device__ int sp_solve_triangular(int nz_symb, const int *pattern_symb, const i
         const int b = ok ? begin[ip] : 0;
         const int e = (ok && end) ? end[ip] : 0;
         const double pv = (ok && pivot) ? pivot[ip] : 1.0;
+        if (ok) { lane_prefetch(index + b); lane_prefetch(value + b); }
         const int cnt = nz_symb - nb < 32 ? nz_symb - nb : 32;
         for (int t = 0; t < cnt; t++) {
             const int ii = __shfl_sync(FULLMASK, ip, t), bb = __shfl_sync(FULLMASK, b, t), ee = __shfl_sync(FULLMASK, e, t);
@@ -277,6 +274,7 @@ __device__ int sp_ftran_tail(SpCtx &C, int nz) {
             const int ip = ok ? M.pivotrow[k] : 0, jp = ok ? M.pivotcol[k] : 0;
             const int b = ok ? M.u_begin[ip] : 0;
             const double pv = ok ? M.rowpiv[ip] : 1.0;
+            if (ok) { lane_prefetch(M.u_idx + b); lane_prefetch(M.u_val + b); }
             const int cnt = pivotlen - kb < 32 ? pivotlen - kb : 32;
             for (int t = cnt - 1; t >= 0; t--) {
                 const int ii = __shfl_sync(FULLMASK, ip, t), jj = __shfl_sync(FULLMASK, jp, t), bb = __shfl_sync(FULLMASK, b, t);
@@ -347,6 +345,7 @@ __device__ int sp_btran_tail(SpCtx &C, int nz, int marker) {
             const bool ok = k < m;
             const int ip = ok ? M.p[k] : 0;
             const int b = ok ? M.lt_begin_p[k] : 0;
+            if (ok) { lane_prefetch(M.l_idx + b); lane_prefetch(M.l_val + b); }
             const int cnt = m - kb < 32 ? m - kb : 32;
             for (int t = cnt - 1; t >= 0; t--) {
                 const int ii = __shfl_sync(FULLMASK, ip, t), bb = __shfl_sync(FULLMASK, b, t);

@@ -55,7 +55,8 @@ struct BluInfo {
     double condest_l, condest_u, norm_l, norm_u, normest_l_inv, normest_u_inv;
     double onenorm, infnorm, residual_test;
     blu_i64 t_phase[12];    /* SM clock cycles per phase (thread 0): 0 validate+transpose 1 singleton queue 2 setup_bump 3 search 4 pivot singleton row 5 singleton col 6 doubleton 7 small 8 any 9 build_factors 10 remove_cols 11 total */
-    blu_i64 n_kind[8];      /* pivots per variant, same numbering minus 4 */
+    blu_i64 n_kind[8];
+    blu_i64 norms_cycles[16]; /* SM cycles of the four warps of k_factor_norms: condest(L), condest(U), residual forward + norms, residual transposed */      /* pivots per variant, same numbering minus 4 */
 };
 
 /* Batch-wide device pointers.  Per-slot strides follow from m and the *_mem sizes. */
@@ -80,6 +81,8 @@ struct BluDev {
     blu_u64 *ckey, *rkey;       /* m each */
     int *l_begin_p, *u_begin;   /* m+1 each */
     int *l_begin, *lt_begin, *lt_begin_p, *p, *r_begin, *eta_row; /* m+1 each */
+    int *len_uc;                  /* m: entries of the U column of pivot k */
+    int *dep_lt, *dep_lc, *dep_uc; /* m each: furthest pivot position a row of L / column of L / column of U depends on (wavefront sweeps) */
     int *pivotcol, *pivotrow;   /* 2m+2 each */
     /* workspaces */
     int *rowmark, *colmark;     /* m each, zero between steps */

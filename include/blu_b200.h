@@ -45,6 +45,7 @@ enum {
     BLU_P_STRETCH, BLU_P_COMPRESS_THRES, BLU_P_SPARSE_THRES, BLU_P_SEARCH_ROWS,
     BLU_P_REALLOC_FACTOR, BLU_P_L_MEM, BLU_P_U_MEM, BLU_P_W_MEM,
     BLU_P_THREADS_PER_BASIS,            /* CTA size of the factorization kernel (32..1024) */
+    BLU_P_NORMS,                        /* 1 (default): factorize also runs condest x2 + residual_test as factorize.rs:121-147 does; 0: skip them (their getters then read 0) */
     BLU_I_M = 100, BLU_I_RANK, BLU_I_BUMP_SIZE, BLU_I_BUMP_NZ, BLU_I_MATRIX_NZ, BLU_I_L_NZ,
     BLU_I_U_NZ, BLU_I_R_NZ, BLU_I_NSEARCH_PIVOT, BLU_I_NEXPAND, BLU_I_NGARBAGE,
     BLU_I_FACTOR_FLOPS, BLU_I_MIN_PIVOT, BLU_I_MAX_PIVOT, BLU_I_MAX_ETA, BLU_I_NUPDATE,
@@ -55,7 +56,8 @@ enum {
     BLU_I_TIME_FACTORIZE, BLU_I_TIME_SOLVE, BLU_I_TIME_UPDATE, BLU_I_ELIM_BYTES, BLU_I_NELIM_DIV,
     BLU_I_PIVOTLEN, BLU_I_RANKDEF, BLU_I_INTERNAL_ERROR, BLU_I_STATUS, BLU_I_NREALLOC,
     BLU_I_T_PHASE0 = 200, /* +0..11: SM cycles per phase of the factorization kernel (diagnostic) */
-    BLU_I_N_KIND0 = 220   /* +0..4: pivots taken by singleton-row / singleton-col / doubleton / small / any */
+    BLU_I_N_KIND0 = 220,  /* +0..4: pivots taken by singleton-row / singleton-col / doubleton / small / any */
+    BLU_I_NORMS_CYC0 = 230 /* +0..3: SM cycles of condest(L), condest(U), residual forward, residual transposed (diagnostic) */
 };
 
 /* ------------------------------------------------------------------ */
@@ -131,7 +133,7 @@ void *blu_batch_stream(blu_batch_t *b);
 int blu_batch_set_stream(blu_batch_t *b, void *cuda_stream);
 int blu_batch_synchronize(blu_batch_t *b);
 /* device time of the last factorize / solve kernels, measured with CUDA events on the launching stream */
-double blu_batch_last_kernel_ms(blu_batch_t *b, int which /*0 factorize, 1 solve_dense*/);
+double blu_batch_last_kernel_ms(blu_batch_t *b, int which /*0 factorize (all kernels of the call), 1 solve_dense, 2 the condest/residual_test kernel alone*/);
 /* number of kernels this library launched since creation */
 int64_t blu_batch_launch_count(blu_batch_t *b);
 

@@ -42,6 +42,7 @@ def lib():
         L.blo_solve_for_update.argtypes = [vp, ctypes.c_int64, i64p, f64p, ctypes.c_char, ctypes.c_int64]
         L.blo_update.argtypes = [vp, ctypes.c_double]
         L.blo_get_factors.argtypes = [vp, i64p, i64p, i64p, i64p, f64p, i64p, i64p, f64p]
+        L.blo_maxvolume.argtypes = [vp, ctypes.c_int64, i64p, i64p, f64p, i64p, i64p, ctypes.c_double, i64p]
         L.blo_get_info.restype = ctypes.c_double; L.blo_get_info.argtypes = [vp, ctypes.c_int]
         L.blo_set_param.argtypes = [vp, ctypes.c_int, ctypes.c_double]
         L.blo_trace_enable.argtypes = [vp, ctypes.c_int]
@@ -133,6 +134,14 @@ class Oracle:
 
     def update(self, xtbl):
         return self._L.blo_update(self._h, float(xtbl))
+
+    def maxvolume(self, ncol, a_p, a_i, a_x, basis, isbasic, volumetol):
+        """maxvolume.rs:64-224; basis / isbasic (int64 arrays) are updated in place.  Returns (status, nupdate)."""
+        ap = np.ascontiguousarray(a_p, dtype=np.int64); ai = np.ascontiguousarray(a_i, dtype=np.int64)
+        ax = np.ascontiguousarray(a_x, dtype=np.float64)
+        nup = ctypes.c_int64(0)
+        st = self._L.blo_maxvolume(self._h, int(ncol), _pi(ap), _pi(ai), _pf(ax), _pi(basis), _pi(isbasic), float(volumetol), ctypes.byref(nup))
+        return st, nup.value
 
     @property
     def nzlhs(self):

@@ -3,7 +3,10 @@ import numpy as np
 from oracle_lib import Oracle
 
 STATS = ["rank", "bump_size", "bump_nz", "matrix_nz", "l_nz", "u_nz", "factor_flops", "nsearch_pivot",
-         "min_pivot", "max_pivot", "nelim_div"]
+         "min_pivot", "max_pivot", "nelim_div",
+         # the tail of factorize (factorize.rs:121-147): condest x2, residual_test, matrix_norm
+         "condest_l", "condest_u", "norm_l", "norm_u", "normest_l_inv", "normest_u_inv", "onenorm", "infnorm",
+         "residual_test", "update_cost"]
 
 
 def oracle_for(m, nnz, factor=60):
@@ -127,3 +130,30 @@ def replay_updates(g, o, m, pool, niter, rng_seed=5, check_dense=True):
                 assert sg == 0
                 assert np.array_equal(xg, xo), (it, tr, np.abs(xg - xo).max() / np.abs(xo).max())
     return kinds
+
+
+def assert_maxvolume_parity(g, o, m, ncol, seed, volumetol=1.0):
+    """maxvolume.rs:64-224 on both sides: same basis, same number of updates, same final solves."""
+    from blu_b200 import gen, maxvolume
+    # A = [slack-heavy starting basis | ncol - m candidate columns]
+    cp, ri, v = gen.basis(seed, m, m // 2, 3.0)
+    pcp, pri, pv = gen.basis(seed + 1, m, 0, 3.0)
+    extra = ncol - m
+    a_p = np.concatenate([cp, cp[-1] + pcp[1:extra + 1]])
+    a_i = np.concatenate([ri, pri[:pcp[extra]]])
+    a_x = np.concatenate([v, 3.0 * pv[:pcp[extra]]])       # candidates large enough to enter the basis
+    bo, bg = np.arange(m, dtype=np.int64), np.arange(m, dtype=np.int64)
+    io = np.zeros(ncol, dtype=np.int64); io[:m] = 1
+    ig = io.copy()
+    so, no = o.maxvolume(ncol, a_p, a_i, a_x, bo, io, volumetol)
+    sg, ng = maxvolume(g, ncol, a_p, a_i, a_x, bg, ig, volumetol)
+    assert (so, no) == (sg, ng), (so, no, sg, ng)
+    assert np.array_equal(bo, bg) and np.array_equal(io, ig)
+    for n in ("nupdate", "nforrest", "nfactorize", "nupdate_total", "nforrest_total", "nsymperm_total", "pivot_error"):
+        assert g.info(n) == o.info(n), n
+    b = gen.rhs(seed + 2, m)
+    for tr in "NT":
+        _, xo = o.solve_dense(b, tr)
+        _, xg = g.solve_dense(b, tr)
+        assert np.array_equal(xg, xo), tr
+    return no

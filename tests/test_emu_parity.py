@@ -143,3 +143,29 @@ def test_emu_sparse_status_codes(emu):
     assert g.solve_for_update(1, one, None, "T") == 0
     assert g.update(1.0) in (0, -6)
     assert g.solve_sparse(0, np.zeros(0, np.int64), np.zeros(0)) == 0 and g.nzlhs == 0
+
+
+def test_emu_maxvolume(emu):
+    """the maxvolume driver (host loop above the ABI) against the oracle's."""
+    from parity import assert_maxvolume_parity
+    m, ncol = 60, 100
+    g = BLU(m, 600, lib=emu)
+    g.threads_per_basis = 64
+    o = oracle_for(m, 600, 400)
+    nup = assert_maxvolume_parity(g, o, m, ncol, 300)
+    assert nup > 0
+    assert maxvolume_invalid(g)
+
+
+def maxvolume_invalid(g):
+    from blu_b200 import maxvolume
+    st, n = maxvolume(g, 0, np.zeros(1, np.int64), np.zeros(0, np.int64), np.zeros(0), np.zeros(0, np.int64), np.zeros(0, np.int64), 0.5)
+    return st == -4 and n == 0                                   # maxvolume.rs:83-90
+
+
+@pytest.mark.parametrize("case", ["m1", "identity", "empty", "empty_cols", "dense40", "one_dense_row_col", "nonsquare_store"])
+def test_emu_edge_shapes(emu, case, monkeypatch):
+    """tests/test_gpu_parity.py::test_edge_shapes under the SIMT emulator."""
+    import test_gpu_parity as tg
+    monkeypatch.setattr(tg, "BLU", lambda m, nnz: BLU(m, nnz, lib=emu))
+    tg.test_edge_shapes(case)

@@ -245,3 +245,74 @@ def test_sparse_status_codes():
     assert g.update(1.0) == -2
     assert g.solve_for_update(1, one, None, "T") == 0
     assert g.update(1.0) in (0, -6)
+
+
+def test_maxvolume_driver():
+    """maxvolume.rs:64-224 as host code above the C ABI, against the oracle's driver."""
+    from parity import assert_maxvolume_parity
+    m, ncol = 400, 700
+    g = BLU(m, 4000)
+    o = oracle_for(m, 4000, 400)
+    assert assert_maxvolume_parity(g, o, m, ncol, 300) > 0
+
+
+@pytest.mark.parametrize("case", ["m1", "identity", "empty", "empty_cols", "dense40", "one_dense_row_col", "nonsquare_store"])
+def test_edge_shapes(case):
+    """Degenerate and ragged inputs: m = 1, pure slack basis, all-zero matrix (rank 0), empty columns,
+    a fully dense block (every pivot through pivot_small/any from step one), an arrow matrix (one dense
+    row and column), and B given as non-contiguous (begin, end) ranges inside a larger store
+    (factorize.rs:28-30, the maxvolume.rs:180-224 calling convention)."""
+    rng = np.random.default_rng(11)
+    if case == "m1":
+        m = 1; cp, ri, v = np.array([0, 1]), np.array([0]), np.array([-2.5])
+    elif case == "identity":
+        m = 50; cp, ri, v = np.arange(m + 1), rng.permutation(m), np.ones(m)
+    elif case == "empty":
+        m = 7; cp, ri, v = np.zeros(m + 1, np.int64), np.zeros(0, np.int64), np.zeros(0)
+    elif case == "empty_cols":
+        m = 80
+        cp, ri, v = gen.basis(5, m, 20, 3.0)
+        keep = np.ones(len(v), bool)
+        for j in (3, 40, 79):
+            keep[cp[j]:cp[j + 1]] = False
+        lens = np.diff(cp); lens[[3, 40, 79]] = 0
+        cp, ri, v = np.concatenate([[0], np.cumsum(lens)]), ri[keep], v[keep]
+    elif case == "dense40":
+        m = 40
+        A = rng.uniform(0.1, 1.0, (m, m)) * np.where(rng.random((m, m)) < 0.5, -1, 1)
+        cp, ri, v = np.arange(0, m * m + 1, m), np.tile(np.arange(m), m), A.T.reshape(-1).copy()
+    elif case == "one_dense_row_col":
+        m = 120
+        A = sp.lil_matrix((m, m))
+        A.setdiag(1.0 + rng.random(m))
+        A[0, :] = rng.uniform(0.1, 1, m); A[:, 0] = rng.uniform(0.1, 1, (m, 1))
+        A = A.tocsc(); A.sort_indices()
+        cp, ri, v = A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.copy()
+    else:
+        m = 60
+        cp0, ri0, v0 = gen.basis(8, 2 * m, 30, 3.0)          # a 2m-column store, rows folded into m
+        ri0 = ri0 % m
+        cols = rng.permutation(2 * m)[:m]
+        # drop duplicate rows inside a column after folding
+        begins, ends, ri, v = [], [], [], []
+        off = 0
+        for j in range(2 * m):
+            r, idx = np.unique(ri0[cp0[j]:cp0[j + 1]], return_index=True)
+            ri.append(r); v.append(v0[cp0[j]:cp0[j + 1]][idx])
+            begins.append(off); off += len(r); ends.append(off)
+        begins, ends = np.array(begins)[cols], np.array(ends)[cols]
+        ri, v = np.concatenate(ri), np.concatenate(v)
+        o = oracle_for(m, len(v))
+        g = BLU(m, len(v))
+        so, sg = o.factorize(begins, ends, ri, v), g.factorize(begins, ends, ri, v)
+        assert so == sg
+        assert_factor_parity(g, o)
+        return
+    cp, ri, v = np.asarray(cp, np.int64), np.asarray(ri, np.int64), np.asarray(v, np.float64)
+    g, o, st = run_pair(cp, ri, v, m, ofactor=400)
+    assert_factor_parity(g, o)
+    b = gen.rhs(5, m)
+    for tr in "NT":
+        so, xo = o.solve_dense(b, tr)
+        sg, xg = g.solve_dense(b, tr)
+        assert so == sg and np.array_equal(xg, xo, equal_nan=True)
