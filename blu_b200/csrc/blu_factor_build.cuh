@@ -305,7 +305,7 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
     BLU_DYN_SMEM(dyn);
     __shared__ Shm S;
     const int tid = threadIdx.x;
-    for (int s = blockIdx.x; s < D.nmat; s += gridDim.x) {
+    for (int s = D.slot0 + blockIdx.x; s < D.slot0 + D.nslot; s += gridDim.x) {
         if (tid == 0) {
             mat_view(S.M, D, s);
             shm_carve(S, dyn, cap, NT / 32, D.m);

@@ -44,6 +44,8 @@ struct blu_b200 {
     int *h_scal; int64_t *h_ilhs; double *h_xout;   /* pinned */
     int info_dirty;             /* device info block is newer than hinfo */
     int norms;                  /* run condest/residual_test after every factorization (factorize.rs:121-147) */
+    cudaStream_t copy_stream, chunk_stream[4]; cudaEvent_t ev_up[16], ev_ch[4]; int have_pipe;   /* pipelined upload (blu_batch_factorize) */
+    blu_i64 *d_chunk_end, *h_chunk_end;                                /* per-chunk max(b_end) */
     double last_norms_ms;
     /* get_factors staging */
     int64_t *gf_i; double *gf_x; int64_t gf_cap;
@@ -110,11 +112,13 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     if (const char *e = getenv("BLU_B200_CAP")) { int c = atoi(e); if (c >= 64 && c <= 4096) o->cap = c & ~31; }   /* tuning knob: entries of the shared-memory line caches */
     o->launches = 0; o->nrealloc = 0; o->last_ms[0] = o->last_ms[1] = 0.0;
     o->have_b = 0; o->info_dirty = 0; o->norms = 1; o->last_norms_ms = 0.0;
+    o->have_pipe = 0; o->d_chunk_end = nullptr; o->h_chunk_end = nullptr;
     o->h_scal = nullptr; o->h_ilhs = nullptr; o->h_xout = nullptr;
     o->time_factorize = o->time_solve = o->time_update = 0.0;
     BluDev &d = o->d;
     memset(&d, 0, sizeof d);
     d.m = (int)m; d.nmat = (int)nmat; d.bnz_cap = bnz_cap < 1 ? 1 : bnz_cap;
+    d.slot0 = 0; d.nslot = (int)nmat;
     /* lu.rs:245-259.  The reference starts every store at b_nz and grows on demand; the
      * device build starts larger because a Reallocate costs a full re-run here. */
     d.l_mem = d.u_mem = 8 * d.bnz_cap + 4 * m;
@@ -187,6 +191,14 @@ static void destroy_common(blu_b200 *o) {
 #ifndef BLU_EMU
     cudaEventDestroy(o->ev0); cudaEventDestroy(o->ev1);
 #endif
+    if (o->have_pipe) {
+#ifndef BLU_EMU
+        for (int i = 0; i < 16; i++) cudaEventDestroy(o->ev_up[i]);
+        for (int i = 0; i < 4; i++) { cudaEventDestroy(o->ev_ch[i]); cudaStreamDestroy(o->chunk_stream[i]); }
+#endif
+        cudaStreamDestroy(o->copy_stream);
+        cudaFreeHost(o->h_chunk_end);
+    }
     if (o->own_stream) cudaStreamDestroy(o->stream);
     delete o;
 }
@@ -217,25 +229,26 @@ static void timer_stop(blu_b200 *o, int which) {
 #endif
 }
 
-template <int NT> static int launch_factorize_nt(blu_b200 *o) {
+template <int NT> static int launch_factorize_nt(blu_b200 *o, cudaStream_t stream, int slot0, int nslot) {
     const size_t smem = blu_factor_smem_bytes(o->cap, NT / 32, o->d.m);
 #ifndef BLU_EMU
     /* static + dynamic shared memory beyond 48 KB needs the opt-in (the static part is ~2.2 KB) */
     if (smem > 40 * 1024) CK(cudaFuncSetAttribute(k_factorize<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-    BLU_LAUNCH(k_factorize<NT>, o->d.nmat, NT, smem, o->stream, o->d, o->cap);
+    BluDev dv = o->d; dv.slot0 = slot0; dv.nslot = nslot;
+    BLU_LAUNCH(k_factorize<NT>, nslot, NT, smem, stream, dv, o->cap);
     o->launches++;
     CK(cudaGetLastError());
     return BLU_OK;
 }
-static int launch_factorize(blu_b200 *o) {
+static int launch_factorize(blu_b200 *o, cudaStream_t stream, int slot0, int nslot) {
     switch (o->nthreads) {
-    case 32: return launch_factorize_nt<32>(o);
-    case 64: return launch_factorize_nt<64>(o);
-    case 256: return launch_factorize_nt<256>(o);
-    case 512: return launch_factorize_nt<512>(o);
-    case 1024: return launch_factorize_nt<1024>(o);
-    default: return launch_factorize_nt<128>(o);
+    case 32: return launch_factorize_nt<32>(o, stream, slot0, nslot);
+    case 64: return launch_factorize_nt<64>(o, stream, slot0, nslot);
+    case 256: return launch_factorize_nt<256>(o, stream, slot0, nslot);
+    case 512: return launch_factorize_nt<512>(o, stream, slot0, nslot);
+    case 1024: return launch_factorize_nt<1024>(o, stream, slot0, nslot);
+    default: return launch_factorize_nt<128>(o, stream, slot0, nslot);
     }
 }
 
@@ -262,7 +275,7 @@ static int factorize_resident(blu_b200 *o) {
     double total_ms = 0.0;
     for (int attempt = 0; attempt < 40; attempt++) {
         timer_start(o);
-        int st = launch_factorize(o);
+        int st = launch_factorize(o, o->stream, 0, d.nmat);
         if (st != BLU_OK) return st;
         timer_stop(o, 0);
         total_ms += o->last_ms[0];
@@ -358,12 +371,115 @@ extern "C" int blu_batch_download(blu_batch_t *o, double *lhs, int *status) {
     return BLU_OK;
 }
 
+/* max(b_end) over the columns of each chunk of bases: tells which part of b_i / b_x a chunk needs */
+__global__ void k_chunk_ranges(const blu_i64 *b_end, blu_i64 cols_per_chunk, blu_i64 ncols, blu_i64 *out) {
+    __shared__ blu_i64 sm[256];
+    const blu_i64 c0 = (blu_i64)blockIdx.x * cols_per_chunk;
+    blu_i64 c1 = c0 + cols_per_chunk; if (c1 > ncols) c1 = ncols;
+    blu_i64 mx = 0;
+    for (blu_i64 q = c0 + threadIdx.x; q < c1; q += blockDim.x) { const blu_i64 e = b_end[q]; mx = e > mx ? e : mx; }
+    sm[threadIdx.x] = mx;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) { if ((int)threadIdx.x < d && sm[threadIdx.x + d] > sm[threadIdx.x]) sm[threadIdx.x] = sm[threadIdx.x + d]; __syncthreads(); }
+    if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
+}
+
+/* Upload B in pieces on a copy stream and start the factorization of a chunk of bases as soon as the
+ * part of b_i / b_x its columns point into has arrived, so that only the first piece of the transfer is
+ * exposed.  Returns BLU_OK when every basis finished without asking for more memory; BLU_REALLOCATE
+ * when the classic path (grow + re-run, B is resident by then) has to take over. */
+#ifndef BLU_EMU
+static int factorize_pipelined(blu_b200 *o, const int64_t *b_begin, const int64_t *b_end,
+                               const int64_t *b_i, const double *b_x, int64_t bnz_total) {
+    BluDev &d = o->d;
+    const int n = d.nmat, NCH = 4, NP = 8;
+    const size_t m = (size_t)d.m;
+    if (!o->have_pipe) {
+        CK(cudaStreamCreateWithFlags(&o->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 16; i++) CK(cudaEventCreateWithFlags(&o->ev_up[i], cudaEventDisableTiming));
+        for (int i = 0; i < 4; i++) { CK(cudaStreamCreateWithFlags(&o->chunk_stream[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&o->ev_ch[i], cudaEventDisableTiming)); }
+        CK(cudaMallocHost((void **)&o->h_chunk_end, 16 * sizeof(blu_i64)));
+        int st = dalloc(o, &o->d_chunk_end, 16);
+        if (st != BLU_OK) return st;
+        o->have_pipe = 1;
+    }
+    int st = ensure_b_cap(o, bnz_total);
+    if (st != BLU_OK) return st;
+    cudaStream_t cs = o->copy_stream;
+    /* whatever the caller queued on the compute stream before must not be overtaken */
+    CK(cudaEventRecord(o->ev_up[15], o->stream));
+    CK(cudaStreamWaitEvent(cs, o->ev_up[15], 0));
+    CK(cudaMemcpyAsync(o->db_begin, b_begin, (size_t)n * m * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(o->db_end, b_end, (size_t)n * m * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+    const int per = (n + NCH - 1) / NCH;
+    k_chunk_ranges<<<NCH, 256, 0, cs>>>((const blu_i64 *)o->db_end, (blu_i64)per * (blu_i64)m, (blu_i64)n * (blu_i64)m, o->d_chunk_end);
+    o->launches++;
+    CK(cudaMemcpyAsync(o->h_chunk_end, o->d_chunk_end, NCH * sizeof(blu_i64), cudaMemcpyDeviceToHost, cs));
+    CK(cudaEventRecord(o->ev_up[14], cs));
+    const int64_t psz = (bnz_total + NP - 1) / NP;
+    for (int p = 0; p < NP; p++) {
+        const int64_t lo = (int64_t)p * psz, hi = std::min<int64_t>(bnz_total, lo + psz);
+        if (hi > lo) {
+            CK(cudaMemcpyAsync(o->db_i + lo, b_i + lo, (size_t)(hi - lo) * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(o->db_x + lo, b_x + lo, (size_t)(hi - lo) * sizeof(double), cudaMemcpyHostToDevice, cs));
+        }
+        CK(cudaEventRecord(o->ev_up[p], cs));
+    }
+    o->have_b = 1;
+    CK(cudaEventSynchronize(o->ev_up[14]));        /* the chunk ranges are on the host now */
+    d.b_begin = (const blu_i64 *)o->db_begin; d.b_end = (const blu_i64 *)o->db_end;
+    d.b_i = (const blu_i64 *)o->db_i; d.b_x = o->db_x;
+    timer_start(o);
+    for (int c = 0; c < NCH; c++) {
+        const int s0 = c * per, ns = std::min(per, n - s0);
+        if (ns <= 0) break;
+        int64_t need = o->h_chunk_end[c];
+        if (need > bnz_total) need = bnz_total;     /* out-of-range pointers are the kernel's business (InvalidArgument) */
+        const int p = psz > 0 && need > 0 ? (int)std::min<int64_t>(NP - 1, (need - 1) / psz) : 0;
+        /* each chunk on its own stream: the next chunk fills the SMs while this one drains */
+        cudaStream_t ks = o->chunk_stream[c];
+        CK(cudaStreamWaitEvent(ks, o->ev0, 0));
+        CK(cudaStreamWaitEvent(ks, o->ev_up[p], 0));
+        if ((st = launch_factorize(o, ks, s0, ns)) != BLU_OK) return st;
+        CK(cudaEventRecord(o->ev_ch[c], ks));
+        CK(cudaStreamWaitEvent(o->stream, o->ev_ch[c], 0));
+    }
+    CK(cudaStreamWaitEvent(o->stream, o->ev_up[NP - 1], 0));
+    timer_stop(o, 0);
+    double total_ms = o->last_ms[0];
+    if ((st = fetch_info(o)) != BLU_OK) return st;
+    for (auto &I : o->hinfo) if (I.status == BLU_REALLOCATE) return BLU_REALLOCATE;
+    if (o->norms) {
+        timer_start(o);
+        BLU_LAUNCH(k_factor_norms, d.nmat, 128, 0, o->stream, d);
+        o->launches++;
+        CK(cudaGetLastError());
+        timer_stop(o, 0);
+        total_ms += o->last_ms[0];
+        o->last_norms_ms = o->last_ms[0];
+        if ((st = fetch_info(o)) != BLU_OK) return st;
+    }
+    o->last_ms[0] = total_ms;
+    return BLU_OK;
+}
+#endif
+
 extern "C" int blu_batch_factorize(blu_batch_t *o, const int64_t *b_begin, const int64_t *b_end,
                                    const int64_t *b_i, const double *b_x, int64_t bnz_total, int *status) {
     if (!o || !b_begin || !b_end) return BLU_ERROR_INVALID_ARGUMENT;
-    int st = blu_batch_upload(o, b_begin, b_end, b_i, b_x, bnz_total, nullptr);
-    if (st != BLU_OK) return st;
-    st = factorize_resident(o);
+    int st;
+#ifndef BLU_EMU
+    if (o->d.nmat >= 256 && bnz_total > 0 && b_i && b_x) {
+        CK(cudaSetDevice(o->device));
+        st = factorize_pipelined(o, b_begin, b_end, b_i, b_x, bnz_total);
+        if (st == BLU_REALLOCATE) st = factorize_resident(o);      /* B is resident: grow and re-run */
+    } else
+#endif
+    {
+        st = blu_batch_upload(o, b_begin, b_end, b_i, b_x, bnz_total, nullptr);
+        if (st != BLU_OK) return st;
+        st = factorize_resident(o);
+    }
     if (st != BLU_OK) return st;
     if (status) for (int k = 0; k < o->d.nmat; k++) status[k] = o->hinfo[k].status;
     return BLU_OK;

@@ -122,7 +122,7 @@ struct NoBatchEnd { __device__ __forceinline__ void operator()(int) const {} };
 __global__ void __launch_bounds__(32) k_solve_dense(BluDev D, const double *rhs_all, double *lhs_all, char trans, int *status) {
     __shared__ Mat M;
     const int lane = threadIdx.x & 31;
-    for (int s = blockIdx.x; s < D.nmat; s += gridDim.x) {
+    for (int s = D.slot0 + blockIdx.x; s < D.slot0 + D.nslot; s += gridDim.x) {
         if (lane == 0) mat_view(M, D, s);
         __syncwarp();
         const int m = M.m;
@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(128, NORMS_MINB) k_factor_norms(BluDev D) {
     __shared__ Mat M;
     __shared__ double sres[8];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int s = blockIdx.x; s < D.nmat; s += gridDim.x) {
+    for (int s = D.slot0 + blockIdx.x; s < D.slot0 + D.nslot; s += gridDim.x) {
         __syncthreads();
         if (tid == 0) mat_view(M, D, s);
         __syncthreads();

@@ -62,6 +62,7 @@ struct BluInfo {
 /* Batch-wide device pointers.  Per-slot strides follow from m and the *_mem sizes. */
 struct BluDev {
     int m, nmat;
+    int slot0, nslot;   /* the range of slots this launch works on (a batch can be processed in pipelined chunks) */
     blu_i64 l_mem, u_mem, w_mem, bnz_cap;
     BluParams prm;
     /* input B */

@@ -316,3 +316,38 @@ def test_edge_shapes(case):
         so, xo = o.solve_dense(b, tr)
         sg, xg = g.solve_dense(b, tr)
         assert so == sg and np.array_equal(xg, xo, equal_nan=True)
+
+
+@pytest.mark.parametrize("layout", ["in_order", "reversed"])
+def test_batch_pipelined_upload(layout):
+    """Batches of >= 256 bases are uploaded in pieces while earlier chunks already factorize
+    (blu_batch_factorize); the result must not depend on it, nor on where the bases sit in b_i / b_x."""
+    nmat, m = 320, 60
+    mats = [gen.basis(4000 + k, m, 20, 3.0) for k in range(nmat)]
+    order = range(nmat) if layout == "in_order" else range(nmat - 1, -1, -1)
+    off = {}
+    pos = 0
+    idxs, vals = [], []
+    for k in order:
+        off[k] = pos
+        idxs.append(mats[k][1]); vals.append(mats[k][2]); pos += len(mats[k][1])
+    bi, bx = np.concatenate(idxs), np.concatenate(vals)
+    bb = np.concatenate([mats[k][0][:-1] + off[k] for k in range(nmat)])
+    be = np.concatenate([mats[k][0][1:] + off[k] for k in range(nmat)])
+    rhs = np.concatenate([gen.rhs(4500 + k, m) for k in range(nmat)])
+    b = BLUBatch(nmat, m, max(len(t[1]) for t in mats))
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all()
+    st, x, sst = b.solve_dense(rhs, "N")
+    assert st == 0 and (sst == 0).all()
+    for k in range(0, nmat, 7):
+        cp, ri, v = mats[k]
+        o = oracle_for(m, len(v))
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        _, fo = o.get_factors()
+        _, fg = b.get_factors(k)
+        for key in fo:
+            assert np.array_equal(fo[key], fg[key]), (k, key)
+        _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
+        assert np.array_equal(x[k], xo)
+        assert b.info(k, "condest_u") == o.info("condest_u") and b.info(k, "residual_test") == o.info("residual_test")
