@@ -373,15 +373,16 @@ extern "C" int blu_batch_download(blu_batch_t *o, double *lhs, int *status) {
 
 /* max(b_end) over the columns of each chunk of bases: tells which part of b_i / b_x a chunk needs */
 __global__ void k_chunk_ranges(const blu_i64 *b_end, blu_i64 cols_per_chunk, blu_i64 ncols, blu_i64 *out) {
+    /* gridDim.x = chunks * gridDim.y-way split: blockIdx.x = chunk, blockIdx.y = slice of the chunk */
     __shared__ blu_i64 sm[256];
     const blu_i64 c0 = (blu_i64)blockIdx.x * cols_per_chunk;
     blu_i64 c1 = c0 + cols_per_chunk; if (c1 > ncols) c1 = ncols;
     blu_i64 mx = 0;
-    for (blu_i64 q = c0 + threadIdx.x; q < c1; q += blockDim.x) { const blu_i64 e = b_end[q]; mx = e > mx ? e : mx; }
+    for (blu_i64 q = c0 + (blu_i64)blockIdx.y * blockDim.x + threadIdx.x; q < c1; q += (blu_i64)gridDim.y * blockDim.x) { const blu_i64 e = b_end[q]; mx = e > mx ? e : mx; }
     sm[threadIdx.x] = mx;
     __syncthreads();
     for (int d = 128; d > 0; d >>= 1) { if ((int)threadIdx.x < d && sm[threadIdx.x + d] > sm[threadIdx.x]) sm[threadIdx.x] = sm[threadIdx.x + d]; __syncthreads(); }
-    if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
+    if (threadIdx.x == 0) atomicMax((unsigned long long *)&out[blockIdx.x], (unsigned long long)(sm[0] > 0 ? sm[0] : 0));
 }
 
 /* Upload B in pieces on a copy stream and start the factorization of a chunk of bases as soon as the
@@ -412,7 +413,8 @@ static int factorize_pipelined(blu_b200 *o, const int64_t *b_begin, const int64_
     CK(cudaMemcpyAsync(o->db_begin, b_begin, (size_t)n * m * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
     CK(cudaMemcpyAsync(o->db_end, b_end, (size_t)n * m * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
     const int per = (n + NCH - 1) / NCH;
-    k_chunk_ranges<<<NCH, 256, 0, cs>>>((const blu_i64 *)o->db_end, (blu_i64)per * (blu_i64)m, (blu_i64)n * (blu_i64)m, o->d_chunk_end);
+    CK(cudaMemsetAsync(o->d_chunk_end, 0, 16 * sizeof(blu_i64), cs));
+    k_chunk_ranges<<<dim3(NCH, 148), 256, 0, cs>>>((const blu_i64 *)o->db_end, (blu_i64)per * (blu_i64)m, (blu_i64)n * (blu_i64)m, o->d_chunk_end);
     o->launches++;
     CK(cudaMemcpyAsync(o->h_chunk_end, o->d_chunk_end, NCH * sizeof(blu_i64), cudaMemcpyDeviceToHost, cs));
     CK(cudaEventRecord(o->ev_up[14], cs));
