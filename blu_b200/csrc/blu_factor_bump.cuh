@@ -16,6 +16,9 @@
  */
 #ifndef BLU_FACTOR_BUMP_CUH
 #define BLU_FACTOR_BUMP_CUH
+#ifndef SEARCH_MERGE
+#define SEARCH_MERGE 0   /* measured on B200: the every-thread merge costs 3 % more than three block-wide minima */
+#endif
 #ifndef REGE
 #define REGE 8   /* line entries per lane held in registers by the fast paths (lines <= 32*REGE) */
 #endif
@@ -146,15 +149,46 @@ template <int NT> __device__ void markowitz_search(Shm &S) {
             }
         }
         int got = 0;
-        for (int r = 0; r < 3 && ncand < maxsearch; r++) {
-            u64 best = block_min64<NT>(k0, S.kscr);
-            if (best == KEY_INF) break;
-            if (k0 == best) {
-                S.cand_col[ncand] = j0;
-                k0 = k1; j0 = j1; k1 = k2; j1 = j2; k2 = KEY_INF; j2 = -1;
+        if (SEARCH_MERGE && 3 * NW <= 40) {
+            /* three smallest of the warp by shuffles, then ONE barrier and a 3-of-(3*NW) merge that every
+             * thread runs for itself (keys are unique): 2 barriers per pass instead of 7.  The per-warp
+             * results sit in the block-reduction scratch (40 entries), hence the bound on NW. */
+            #pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const u64 best = warp_min64(k0);
+                const unsigned own = __ballot_sync(FULLMASK, k0 == best && best != KEY_INF);
+                int jb = -1;
+                if (own) jb = __shfl_sync(FULLMASK, j0, __ffs((int)own) - 1);
+                if (lane == 0) { S.kscr[wid * 3 + r] = best; S.iscr[wid * 3 + r] = jb; }
+                if (k0 == best && best != KEY_INF) { k0 = k1; j0 = j1; k1 = k2; j1 = j2; k2 = KEY_INF; j2 = -1; }
             }
-            prev = best; have_prev = 1;
-            ncand++; got++;
+            bsync<NT>();
+            u64 b0 = KEY_INF, b1 = KEY_INF, b2 = KEY_INF;
+            int c0 = -1, c1 = -1, c2 = -1;
+            for (int q = 0; q < 3 * NW; q++) {
+                const u64 k = S.kscr[q]; const int j = S.iscr[q];
+                if (k < b2) {
+                    if (k < b1) {
+                        b2 = b1; c2 = c1;
+                        if (k < b0) { b1 = b0; c1 = c0; b0 = k; c0 = j; }
+                        else { b1 = k; c1 = j; }
+                    } else { b2 = k; c2 = j; }
+                }
+            }
+            if (b0 != KEY_INF && ncand < maxsearch) { if (tid == 0) S.cand_col[ncand] = c0; prev = b0; have_prev = 1; ncand++; got++; }
+            if (b1 != KEY_INF && ncand < maxsearch) { if (tid == 0) S.cand_col[ncand] = c1; prev = b1; ncand++; got++; }
+            if (b2 != KEY_INF && ncand < maxsearch) { if (tid == 0) S.cand_col[ncand] = c2; prev = b2; ncand++; got++; }
+        } else {
+            for (int r = 0; r < 3 && ncand < maxsearch; r++) {
+                u64 best = block_min64<NT>(k0, S.kscr);
+                if (best == KEY_INF) break;
+                if (k0 == best) {
+                    S.cand_col[ncand] = j0;
+                    k0 = k1; j0 = j1; k1 = k2; j1 = j2; k2 = KEY_INF; j2 = -1;
+                }
+                prev = best; have_prev = 1;
+                ncand++; got++;
+            }
         }
         bsync<NT>();
         if (got < 3) break;     /* fewer live columns than asked for */
@@ -293,6 +327,9 @@ __device__ __forceinline__ void finish_step(Shm &S, int rank, int lput, int uput
     M.ckey[pc] = KEY_INF;
     M.rkey[pr] = KEY_INF;
     S.ndead++;
+    /* factorize_bump.rs:39-43; published by the barrier that ends every pivot variant */
+    M.pinv[pr] = rank; M.qinv[pc] = rank;
+    S.rank = rank + 1;
     S.factor_flops += (i64)(nz_col - 1) * (i64)(nz_row - 1);
     S.elim_bytes += 12.0 * nz_col + 4.0 * nz_row + 12.0 * (nz_col - 1) + 12.0 * (nz_row - 1);
     S.nelim_div += nz_col - 1;
@@ -650,7 +687,7 @@ template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
     grow = block_sum64<NT>(grow, S.kscr);
     const int wc = S.wc, wr = S.wr;
     if (wc < 0 || wr < 0) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
-    bsync<NT>();
+    /* (block_sum64 ended with a barrier: the staged arrays are complete and visible) */
     if (tid == 0) {
         /* pivot to the front of its column and row (pivot.rs:142-154), headers travel along */
         int ti = S.cidx[0]; S.cidx[0] = S.cidx[wc]; S.cidx[wc] = ti;
@@ -1299,11 +1336,6 @@ template <int NT> __device__ void phase_bump(Shm &S) {
         t0 = clock64();
         post_remove_cols<NT>(S, rank);
         if (tid == 0) S.t_phase[10] += clock64() - t0;
-        if (tid == 0) {
-            M.pinv[pr] = rank; M.qinv[pc] = rank;
-            S.rank = rank + 1;
-        }
-        bsync<NT>();
         if (S.status != BLU_OK) return;
     }
 }
