@@ -40,6 +40,7 @@ struct Mat {
     u64 *ckey, *rkey;
     int *l_begin_p, *u_begin, *l_begin, *lt_begin, *lt_begin_p, *p, *r_begin, *eta_row;
     int *dep_lt, *dep_lc, *dep_uc, *len_uc;
+    int *ur_ptr, *ur_idx, *dep_ur; double *ur_val;
     int *pivotcol, *pivotrow;
     int *rowmark, *colmark, *marked, *iwork1, *pstack, *acols, *tmpi;
     u64 *cancelled;
@@ -68,6 +69,7 @@ __device__ __forceinline__ void mat_view(Mat &M, const BluDev &D, int s) {
     M.lt_begin_p = D.lt_begin_p + S * (m + 1); M.p = D.p + S * (m + 1);
     M.r_begin = D.r_begin + S * (m + 1); M.eta_row = D.eta_row + S * (m + 1);
     M.dep_lt = D.dep_lt + S * m; M.dep_lc = D.dep_lc + S * m; M.dep_uc = D.dep_uc + S * m; M.len_uc = D.len_uc + S * m;
+    M.ur_ptr = D.ur_ptr; M.ur_idx = D.ur_idx; M.dep_ur = D.dep_ur; M.ur_val = D.ur_val;   /* single object: slot 0 */
     M.pivotcol = D.pivotcol + S * (2 * m + 2); M.pivotrow = D.pivotrow + S * (2 * m + 2);
     M.rowmark = D.rowmark + S * m; M.colmark = D.colmark + S * m; M.marked = D.marked + S * m;
     M.iwork1 = D.iwork1 + S * (2 * m + 2); M.pstack = D.pstack + S * m;

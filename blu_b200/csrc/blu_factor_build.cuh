@@ -321,7 +321,7 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
             I->pivot_error = 0.0; I->ftran_for_update = I->btran_for_update = -1;
             I->marker = 0; I->pivotlen = 0; I->rankdef = 0;
             I->addmem_l = I->addmem_u = I->addmem_w = 0;
-            I->internal_error = 0; I->elim_bytes = 0.0; I->nelim_div = 0;
+            I->internal_error = 0; I->elim_bytes = 0.0; I->nelim_div = 0; I->have_ur = 0;
             I->condest_l = I->condest_u = I->norm_l = I->norm_u = 0.0;
             I->normest_l_inv = I->normest_u_inv = I->onenorm = I->infnorm = I->residual_test = 0.0;
             S.status = BLU_OK;

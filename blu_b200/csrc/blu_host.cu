@@ -87,6 +87,10 @@ static int alloc_stores(blu_b200 *o) {
     if ((st = dalloc(o, &d.l_val, n * d.l_mem + PADDING))) return st;
     if ((st = dalloc(o, &d.u_idx, n * d.u_mem + PADDING))) return st;
     if ((st = dalloc(o, &d.u_val, n * d.u_mem + PADDING))) return st;
+    if (o->single) {
+        if ((st = dalloc(o, &d.ur_idx, (size_t)d.u_mem + PADDING))) return st;
+        if ((st = dalloc(o, &d.ur_val, (size_t)d.u_mem + PADDING))) return st;
+    }
     if ((st = dalloc(o, &d.w_idx, n * 2 * d.w_mem + PADDING))) return st;
     if ((st = dalloc(o, &d.w_val, n * 2 * d.w_mem + PADDING))) return st;
     return BLU_OK;
@@ -94,6 +98,7 @@ static int alloc_stores(blu_b200 *o) {
 static void free_stores(blu_b200 *o) {
     BluDev &d = o->d;
     dfree(o, d.l_idx); dfree(o, d.l_val); dfree(o, d.u_idx); dfree(o, d.u_val); dfree(o, d.w_idx); dfree(o, d.w_val);
+    dfree(o, d.ur_idx); dfree(o, d.ur_val); d.ur_idx = nullptr; d.ur_val = nullptr;
     d.l_idx = d.u_idx = d.w_idx = nullptr; d.l_val = d.u_val = d.w_val = nullptr;
 }
 
@@ -147,7 +152,7 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     A(d.info, n);
     A(o->db_begin, n * M); A(o->db_end, n * M);
     A(o->d_rhs, n * M); A(o->d_lhs, n * M); A(o->d_status, n);
-    if (single) { A(o->d_irhs, M); A(o->d_xrhs, M); A(o->d_ilhs, M); A(o->d_xout, M); A(o->d_scal, 16); }
+    if (single) { A(o->d_irhs, M); A(o->d_xrhs, M); A(o->d_ilhs, M); A(o->d_xout, M); A(o->d_scal, 16); A(d.ur_ptr, M + 1); A(d.dep_ur, M); }
 #undef A
     o->b_cap = 0; o->db_i = nullptr; o->db_x = nullptr;
     o->gf_i = nullptr; o->gf_x = nullptr; o->gf_cap = 0;
@@ -285,6 +290,11 @@ static int factorize_resident(blu_b200 *o) {
             if (I.status == BLU_REALLOCATE) { need = 1; al = std::max<int64_t>(al, I.addmem_l); au = std::max<int64_t>(au, I.addmem_u); aw = std::max<int64_t>(aw, I.addmem_w); }
         }
         if (!need) {
+            if (o->single && d.ur_idx) {   /* sorted row-wise U for the wavefront U sweeps (object API) */
+                BLU_LAUNCH(k_build_ur, 1, 256, 0, o->stream, d);
+                o->launches++;
+                CK(cudaGetLastError());
+            }
             /* factorize.rs:121-147: condest(L), condest(U), residual_test (+ matrix_norm) */
             if (o->norms) {
                 timer_start(o);
@@ -774,6 +784,18 @@ static int grow_store_keep(blu_b200 *o, int which, int64_t addmem) {
     CK(cudaStreamSynchronize(o->stream));
     dfree(o, oi); dfree(o, ov);
     oi = ni; ov = nv;
+    if (which == 1 && o->single && d.ur_idx) {
+        /* the sorted row-wise copy of U is sized like the U store: grow it too, content kept */
+        int *ri = nullptr; double *rv = nullptr;
+        st = dalloc(o, &ri, (size_t)newmem + PADDING);
+        if (st == BLU_OK) st = dalloc(o, &rv, (size_t)newmem + PADDING);
+        if (st != BLU_OK) return st;
+        CK(cudaMemcpyAsync(ri, d.ur_idx, (size_t)mem * sizeof(int), cudaMemcpyDeviceToDevice, o->stream));
+        CK(cudaMemcpyAsync(rv, d.ur_val, (size_t)mem * sizeof(double), cudaMemcpyDeviceToDevice, o->stream));
+        CK(cudaStreamSynchronize(o->stream));
+        dfree(o, d.ur_idx); dfree(o, d.ur_val);
+        d.ur_idx = ri; d.ur_val = rv;
+    }
     if (which == 2) {
         BLU_LAUNCH(k_w_rebase, 1, 128, 0, o->stream, d, (int)from);
         o->launches++;

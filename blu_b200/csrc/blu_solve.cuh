@@ -60,9 +60,9 @@ __device__ __forceinline__ double dev_line_dot_n(const int *idx, const double *v
 __device__ __forceinline__ void dev_line_prefetch(const int *idx, const double *val, int pos, int len);
 __device__ __forceinline__ void dev_line_axpy_n(const int *idx, const double *val, int pos, int len, double *vec, double x);
 #define SWEEP_SHORT 8   /* lines of up to this many entries are summed by their own lane; longer ones by the whole warp */
-template <typename Head, typename Tail, typename BatchEnd>
-__device__ __forceinline__ void dev_dot_sweep(int m, bool asc, const int *dep, const int *idx, const double *val,
-                                              const double *vec, bool subtract, Head head, Tail tail, BatchEnd batch_end) {
+template <typename Head, typename Init, typename Tail, typename BatchEnd>
+__device__ __forceinline__ void dev_dot_sweep_init(int m, bool asc, const int *dep, const int *idx, const double *val,
+                                                   const double *vec, bool subtract, Head head, Init init, Tail tail, BatchEnd batch_end) {
     const int lane = threadIdx.x & 31;
     for (int s = 0; s < m; s += 32) {
         const int cnt = m - s < 32 ? m - s : 32;
@@ -88,7 +88,7 @@ __device__ __forceinline__ void dev_dot_sweep(int m, bool asc, const int *dep, c
                     int r[SWEEP_SHORT]; double v[SWEEP_SHORT];
                     #pragma unroll
                     for (int q = 0; q < SWEEP_SHORT; q++) { r[q] = q < len ? idx[b + q] : -1; v[q] = q < len ? val[b + q] : 0.0; }
-                    double acc = 0.0;
+                    double acc = init(k);       /* the value the reference's running vector holds before the terms */
                     #pragma unroll
                     for (int q = 0; q < SWEEP_SHORT; q++) {
                         if (q < len) { const double t = __dmul_rn(vec[r[q]], v[q]); acc = subtract ? __dsub_rn(acc, t) : __dadd_rn(acc, t); }
@@ -104,7 +104,10 @@ __device__ __forceinline__ void dev_dot_sweep(int m, bool asc, const int *dep, c
                 const int t = __ffs((int)rlong) - 1;
                 const int bb = __shfl_sync(FULLMASK, b, t), ll = __shfl_sync(FULLMASK, len, t);
                 if (t + 1 < cnt) dev_line_prefetch(idx, val, __shfl_sync(FULLMASK, b, t + 1), __shfl_sync(FULLMASK, len, t + 1));
-                const double acc = dev_line_dot_n(idx, val, bb, ll, vec, 0.0, subtract);
+                double a0 = 0.0;
+                if (lane == t) a0 = init(k);
+                a0 = __shfl_sync(FULLMASK, a0, t);
+                const double acc = dev_line_dot_n(idx, val, bb, ll, vec, a0, subtract);
                 if (lane == t) { tail(k, acc); fin = true; }
                 __syncwarp();
                 done |= 1u << t;
@@ -114,6 +117,12 @@ __device__ __forceinline__ void dev_dot_sweep(int m, bool asc, const int *dep, c
     }
 }
 struct NoBatchEnd { __device__ __forceinline__ void operator()(int) const {} };
+struct ZeroInit { __device__ __forceinline__ double operator()(int) const { return 0.0; } };
+template <typename Head, typename Tail, typename BatchEnd>
+__device__ __forceinline__ void dev_dot_sweep(int m, bool asc, const int *dep, const int *idx, const double *val,
+                                              const double *vec, bool subtract, Head head, Tail tail, BatchEnd batch_end) {
+    dev_dot_sweep_init(m, asc, dep, idx, val, vec, subtract, head, ZeroInit(), tail, batch_end);
+}
 
 /* One warp per basis.  The sweeps are sequential over the pivot order (as in the
  * reference); the lanes share the dot product / axpy of each step and the pointer
@@ -138,7 +147,15 @@ __global__ void __launch_bounds__(32) k_solve_dense(BluDev D, const double *rhs_
         for (int i = lane; i < m; i += 32) work[i] = rhs[i];
         __syncwarp();
         if (is_trans(trans)) {
-            /* U', lu/solve_dense.rs:40-48 */
+            /* U', lu/solve_dense.rs:40-48.  Fresh factorization: column k' of U (ascending pivot order by
+             * construction) lists exactly the terms work[jp_k'] receives, in the order the reference's row
+             * sweep applies them, so the sweep runs as wavefront dot products. */
+            if (fresh) {
+                dev_dot_sweep_init(m, true, M.dep_uc, M.u_idx, M.u_val, lhs, true,
+                                   [&](int k, int *b, int *len) { *b = M.u_begin[M.pivotrow[k]]; *len = M.len_uc[k]; },
+                                   [&](int k) { return work[M.pivotcol[k]]; },
+                                   [&](int k, double acc) { lhs[M.pivotrow[k]] = __ddiv_rn(acc, M.colpiv[M.pivotcol[k]]); }, NoBatchEnd());
+            } else
             for (int kb = 0; kb < m; kb += 32) {
                 int k = kb + lane;
                 int jp = k < m ? M.pivotcol[k] : 0, ip = k < m ? M.pivotrow[k] : 0;
@@ -230,6 +247,18 @@ __global__ void __launch_bounds__(32) k_solve_dense(BluDev D, const double *rhs_
                 __syncwarp();
             }
             /* U, :106-118 (column-wise axpy form, terminator-delimited) */
+            if (fresh && M.ur_ptr && I->have_ur) {
+                /* the same arithmetic row by row: row k of U, columns in descending pivot order, starting
+                 * from the value L left in work[] -- wavefronts of independent pivots */
+                dev_dot_sweep_init(m, false, M.dep_ur, M.ur_idx, M.ur_val, work, true,
+                                   [&](int k, int *b, int *len) { *b = M.ur_ptr[k]; *len = M.ur_ptr[k + 1] - *b; },
+                                   [&](int k) { return work[M.pivotrow[k]]; },
+                                   [&](int k, double acc) {
+                                       const int ip = M.pivotrow[k];
+                                       const double x = __ddiv_rn(acc, M.rowpiv[ip]);
+                                       work[ip] = x; lhs[M.pivotcol[k]] = x;
+                                   }, NoBatchEnd());
+            } else
             for (int kb = ((m - 1) / 32) * 32; kb >= 0; kb -= 32) {
                 int k = kb + lane;
                 int jp = k < m ? M.pivotcol[k] : 0, ip = k < m ? M.pivotrow[k] : 0;
@@ -444,7 +473,7 @@ __device__ __forceinline__ void dev_line_prefetch(const int *idx, const double *
 
 /* lu/condest.rs:15-157 for one triangular factor stored as terminated lines begin[j] */
 __device__ double dev_condest(int m, const int *begin, const int *idx, const double *val, const double *pivot,
-                              const int *perm, bool upper, const int *dep, const int *lens, const int *lptr, double *work, double *norm, double *norminv) {
+                              const int *perm, bool upper, const int *dep, const int *lens, const int *lptr, const int *rowdep, const int *rowptr, const int *rowidx, const double *rowval, double *work, double *norm, double *norminv) {
     const int lane = threadIdx.x & 31;
     /* 1-norm: every lane sums whole columns serially (storage order), the maximum is order-free */
     double u_norm = 0.0;
@@ -526,6 +555,26 @@ __device__ double dev_condest(int m, const int *begin, const int *idx, const dou
             __syncwarp();
         }
     }
+    if (dep && upper && rowdep) {
+        /* U: the backward column-axpy sweep == for every pivot the dot with its ROW of U in descending
+         * pivot order of the columns (ur_*), started from the pass-1 value, then the division */
+        double mytemp = 0.0;
+        dev_dot_sweep_init(m, false, rowdep, rowidx, rowval, work, true,
+                           [&](int k, int *b, int *len) { *b = rowptr[k]; *len = rowptr[k + 1] - rowptr[k]; },
+                           [&](int k) { return work[perm[k]]; },
+                           [&](int k, double acc) { const int j = perm[k]; const double temp = __ddiv_rn(acc, pivot[j]); work[j] = temp; mytemp = fabs(temp); },
+                           [&](int cnt) { y1norm = ordered_acc(y1norm, mytemp, cnt); });
+    } else
+    if (dep && !upper && rowdep) {
+        /* L: the column-axpy sweep (ascending) == for every pivot the dot with its ROW of L (entries in
+         * ascending pivot order by construction), started from the pass-1 value */
+        double mytemp = 0.0;
+        dev_dot_sweep_init(m, true, rowdep, idx, val, work, true,
+                           [&](int k, int *b, int *len) { *b = rowptr[k]; *len = rowptr[k + 1] - rowptr[k] - 1; },
+                           [&](int k) { return work[perm[k]]; },
+                           [&](int k, double temp) { work[perm[k]] = temp; mytemp = fabs(temp); },
+                           [&](int cnt) { y1norm = ordered_acc(y1norm, mytemp, cnt); });
+    } else
     for (int s = 0; s < m; s += 32) {
         const int kk = s + lane;
         const bool ok = kk < m;
@@ -605,6 +654,12 @@ __device__ void dev_residual_forward(Mat &M, int rank, double *rhs, double *lhs,
                       rhs[ii] = r; lhs[ii] = __dsub_rn(r, d);
                   }, NoBatchEnd());
     if (lane == 0) { M.info->norms_cycles[4] = clock64() - tq; } tq = clock64();
+    if (M.ur_ptr && M.info->have_ur) {
+        dev_dot_sweep_init(m, false, M.dep_ur, M.ur_idx, M.ur_val, lhs, true,
+                           [&](int k, int *b, int *len) { *b = M.ur_ptr[k]; *len = M.ur_ptr[k + 1] - *b; },
+                           [&](int k) { return lhs[M.pivotrow[k]]; },
+                           [&](int k, double acc) { const int ip = M.pivotrow[k]; lhs[ip] = __ddiv_rn(acc, M.rowpiv[ip]); }, NoBatchEnd());
+    } else
     for (int s = 0; s < m; s += 32) {
         const int k = m - 1 - (s + lane);
         const int ip = k >= 0 ? M.pivotrow[k] : 0;
@@ -684,14 +739,15 @@ __global__ void __launch_bounds__(128, NORMS_MINB) k_factor_norms(BluDev D) {
         const int m = M.m;
         const size_t mm = (size_t)m;
         double *v = M.gwork + mm;          /* slices 1..7 */
+        const bool have_ur = M.ur_ptr && I->have_ur;
         const i64 tw0 = clock64();
         if (wid == 0) {
             double norm, norminv;
-            const double c = dev_condest(m, M.l_begin, M.l_idx, M.l_val, nullptr, M.p, false, M.dep_lc, nullptr, M.l_begin_p, v, &norm, &norminv);
+            const double c = dev_condest(m, M.l_begin, M.l_idx, M.l_val, nullptr, M.p, false, M.dep_lc, nullptr, M.l_begin_p, M.ur_ptr ? M.dep_lt : nullptr /* batch: tail-dominated factors, the column axpy is cheaper */, M.lt_begin_p, nullptr, nullptr, v, &norm, &norminv);
             if (lane == 0) { I->condest_l = c; I->norm_l = norm; I->normest_l_inv = norminv; }
         } else if (wid == 1) {
             double norm, norminv;
-            const double c = dev_condest(m, M.u_begin, M.u_idx, M.u_val, M.rowpiv, M.p, true, M.dep_uc, M.len_uc, nullptr, v + mm, &norm, &norminv);
+            const double c = dev_condest(m, M.u_begin, M.u_idx, M.u_val, M.rowpiv, M.p, true, M.dep_uc, M.len_uc, nullptr, have_ur ? M.dep_ur : nullptr, M.ur_ptr, M.ur_idx, M.ur_val, v + mm, &norm, &norminv);
             if (lane == 0) { I->condest_u = c; I->norm_u = norm; I->normest_u_inv = norminv; }
         } else if (wid == 2) {
             dev_residual_forward(M, I->rank, v + 2 * mm, v + 3 * mm, v + 4 * mm, sres);
@@ -709,5 +765,62 @@ __global__ void __launch_bounds__(128, NORMS_MINB) k_factor_norms(BluDev D) {
         }
         for (size_t i = tid; i < 7 * mm; i += 128) v[i] = 0.0;
     }
+}
+
+/* Object API: U row-wise with every row in descending pivot order of the column (see blu_types.h).
+ * Counting in parallel, then one ordered scatter that walks the columns of U from the last pivot to the
+ * first -- the order in which the reference's backward sweep visits them.  One CTA. */
+__global__ void __launch_bounds__(256) k_build_ur(BluDev D) {
+    __shared__ Mat M;
+    __shared__ int iscr[40];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) mat_view(M, D, 0);
+    __syncthreads();
+    BluInfo *I = M.info;
+    const int m = M.m;
+    if (!M.ur_ptr || I->nupdate != 0 || (I->status != BLU_OK && I->status != BLU_WARNING_SINGULAR_MATRIX)) return;
+    int *cnt = M.ur_ptr, *fill = M.tmpi;
+    for (int k = tid; k <= m; k += 256) cnt[k] = 0;
+    __syncthreads();
+    for (int k = tid; k < m; k += 256)
+        for (int pos = M.u_begin[M.pivotrow[k]]; M.u_idx[pos] >= 0; pos++) atomicAdd(&cnt[M.prank[M.u_idx[pos]]], 1);
+    __syncthreads();
+    int put = 0;
+    for (int base = 0; base < m; base += 256) {
+        const int k = base + tid;
+        const int c = k < m ? cnt[k] : 0;
+        int tot;
+        const int ex = block_excl_scan<256>(c, &tot, iscr);
+        __syncthreads();
+        if (k < m) { cnt[k] = put + ex; fill[k] = put + ex; }
+        put += tot;
+    }
+    if (tid == 0) cnt[m] = put;
+    __syncthreads();
+    if (wid == 0) {
+        for (int s = 0; s < m; s += 32) {
+            const int k = m - 1 - (s + lane);
+            const int ip = k >= 0 ? M.pivotrow[k] : 0;
+            const int b = k >= 0 ? M.u_begin[ip] : 0;
+            const int ln = k >= 0 ? M.len_uc[k] : 0;
+            const int n = m - s < 32 ? m - s : 32;
+            for (int t = 0; t < n; t++) {
+                const int bb = __shfl_sync(FULLMASK, b, t), ll = __shfl_sync(FULLMASK, ln, t), ii = __shfl_sync(FULLMASK, ip, t);
+                for (int q = lane; q < ll; q += 32) {
+                    const int kk = M.prank[M.u_idx[bb + q]];      /* rows of one column are distinct: no conflict */
+                    const int dst = fill[kk]; fill[kk] = dst + 1;
+                    M.ur_idx[dst] = ii; M.ur_val[dst] = M.u_val[bb + q];
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < m; k += 256) {
+        const int e = M.ur_ptr[k + 1];
+        M.dep_ur[k] = e > M.ur_ptr[k] ? M.prank[M.ur_idx[e - 1]] : m;    /* the closest later pivot the row reaches */
+    }
+    __syncthreads();
+    if (tid == 0) I->have_ur = 1;
 }
 #endif

@@ -1022,7 +1022,7 @@ __global__ void __launch_bounds__(32) k_update(BluDev D, double xtbl, int *scal)
         I->u_nz = u_nz; I->r_nz = r_nz;
         I->min_pivot = pmin; I->max_pivot = pmax; I->max_eta = max_eta_all;
         I->nforrest = nforrest_new;
-        I->btran_for_update = -1; I->ftran_for_update = -1;
+        I->btran_for_update = -1; I->ftran_for_update = -1; I->have_ur = 0;
         I->update_cost_numer += (double)nz_roweta;
         I->nupdate++; I->nupdate_total++;
         scal[0] = C.status;

@@ -40,7 +40,7 @@ struct BluInfo {
     int w_half;             /* which half of W is live */
     int nact;               /* entries of the active-column list */
     int internal_error;     /* line number of a failed device-side invariant, 0 = none */
-    int pad0;
+    int have_ur;            /* the sorted row-wise copy of U (ur_*) matches the current factors */
     blu_i64 matrix_nz, bump_nz, l_nz, u_nz, r_nz;
     blu_i64 nsearch_pivot, nexpand, ngarbage, factor_flops;
     blu_i64 l_flops, u_flops, r_flops;
@@ -83,6 +83,10 @@ struct BluDev {
     int *l_begin_p, *u_begin;   /* m+1 each */
     int *l_begin, *lt_begin, *lt_begin_p, *p, *r_begin, *eta_row; /* m+1 each */
     int *len_uc;                  /* m: entries of the U column of pivot k */
+    /* object API only (null in a batch): U row-wise, every row sorted by DESCENDING pivot position of the
+     * column -- the order in which the reference's backward column sweep touches a row -- so that the U
+     * solves and sweeps can run as wavefront dot products too (k_build_ur) */
+    int *ur_ptr, *ur_idx, *dep_ur; double *ur_val;
     int *dep_lt, *dep_lc, *dep_uc; /* m each: furthest pivot position a row of L / column of L / column of U depends on (wavefront sweeps) */
     int *pivotcol, *pivotrow;   /* 2m+2 each */
     /* workspaces */
