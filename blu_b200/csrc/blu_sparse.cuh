@@ -122,19 +122,61 @@ __device__ int sp_dfs(int i, const int *begin, const int *end, const int *index,
     return top;
 }
 
-/* solve_symbolic.rs:19-40; lane 0 walks, the result is broadcast */
+/* dfs.rs:25-145 run by the whole warp: the control flow is the sequential one (uniform in all lanes, the
+ * stacks are written by lane 0), but "first neighbour that is not marked yet" is found 32 neighbours at
+ * a time -- two dependent round trips per 32 edges instead of per edge.  Same visiting order, hence the
+ * same finishing order, as sp_dfs. */
+__device__ int sp_dfs_warp(int i, const int *begin, const int *end, const int *index, int top,
+                           int *xi, int *pstack, int *marked, int marker) {
+    const int lane = threadIdx.x & 31;
+    if (marked[i] == marker) return top;
+    int head = 0;
+    __syncwarp();
+    if (lane == 0) xi[0] = i;
+    __syncwarp();
+    while (head >= 0) {
+        i = xi[head];
+        if (marked[i] != marker) {
+            __syncwarp();
+            if (lane == 0) { marked[i] = marker; pstack[head] = begin[i]; }
+            __syncwarp();
+        }
+        const int p0 = pstack[head];
+        const int e = end ? end[i] : 0x7fffffff;
+        int found = -1, inext = -1;
+        for (int q = p0; q < e; q += 32) {
+            const bool in = q + lane < e;
+            const int idx = in ? index[q + lane] : -1;
+            unsigned tm = 0; int nvalid = 32;
+            if (!end) { tm = __ballot_sync(FULLMASK, idx < 0); nvalid = tm ? __ffs((int)tm) - 1 : 32; }
+            const bool cand = in && lane < nvalid && marked[idx] != marker;
+            const unsigned cm = __ballot_sync(FULLMASK, cand);
+            if (cm) { const int l = __ffs((int)cm) - 1; found = q + l; inext = __shfl_sync(FULLMASK, idx, l); break; }
+            if (tm) break;
+        }
+        __syncwarp();
+        if (found >= 0) {
+            if (lane == 0) { pstack[head] = found + 1; xi[head + 1] = inext; }
+            head++;
+        } else {
+            head--; top--;
+            if (lane == 0) xi[top] = i;
+        }
+        __syncwarp();
+    }
+    return top;
+}
+
+/* solve_symbolic.rs:19-40 */
 __device__ __forceinline__ int sp_symbolic(int m, const int *begin, const int *end, const int *index,
                                            int nrhs, const int *irhs, int *xi, int *pstack, int *marked, int marker) {
     int top = m;
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
-        for (int n = 0; n < nrhs; n++) {
-            int i = irhs[n];
-            if (marked[i] != marker) top = sp_dfs(i, begin, end, index, top, xi, pstack, marked, marker);
-        }
+    for (int n = 0; n < nrhs; n++) {
+        const int i = irhs[n];
+        if (marked[i] != marker) top = sp_dfs_warp(i, begin, end, index, top, xi, pstack, marked, marker);
+        __syncwarp();
     }
-    top = sp_bcast(top);
-    __syncwarp();
     return top;
 }
 
@@ -275,13 +317,20 @@ __device__ int sp_ftran_tail(SpCtx &C, int nz) {
             const int b = ok ? M.u_begin[ip] : 0;
             const double pv = ok ? M.rowpiv[ip] : 1.0;
             if (ok) { lane_prefetch(M.u_idx + b); lane_prefetch(M.u_val + b); }
-            const int cnt = pivotlen - kb < 32 ? pivotlen - kb : 32;
-            for (int t = cnt - 1; t >= 0; t--) {
+            /* The reference tests work[ipivot] pivot by pivot; here the 32 values of the batch are fetched
+             * together and only the non-zero ones are visited, in sweep order.  Zeros ahead of the next
+             * non-zero cannot change any more (nothing was applied in between); after every applied column
+             * the values still pending are fetched again. */
+            unsigned pend = __ballot_sync(FULLMASK, ok);
+            double wl = ok ? C.work[ip] : 0.0;
+            for (;;) {
+                const unsigned nzm = __ballot_sync(FULLMASK, wl != 0.0) & pend;
+                if (!nzm) break;
+                const int t = 31 - __clz((int)nzm);
+                pend &= (1u << t) - 1u;
                 const int ii = __shfl_sync(FULLMASK, ip, t), jj = __shfl_sync(FULLMASK, jp, t), bb = __shfl_sync(FULLMASK, b, t);
                 const double pp = __shfl_sync(FULLMASK, pv, t);
-                const double w = C.work[ii];
-                __syncwarp();
-                if (w == 0.0) continue;
+                const double w = __shfl_sync(FULLMASK, wl, t);
                 const double x = __ddiv_rn(w, pp);
                 if (lane == 0) C.work[ii] = 0.0;
                 for (int pos = bb;; pos += 32) {
@@ -297,6 +346,7 @@ __device__ int sp_ftran_tail(SpCtx &C, int nz) {
                     nz++;
                 }
                 __syncwarp();
+                wl = ((pend >> lane) & 1u) ? C.work[ip] : 0.0;
             }
         }
         if (lane == 0) C.u_flops += fl;
@@ -346,12 +396,15 @@ __device__ int sp_btran_tail(SpCtx &C, int nz, int marker) {
             const int ip = ok ? M.p[k] : 0;
             const int b = ok ? M.lt_begin_p[k] : 0;
             if (ok) { lane_prefetch(M.l_idx + b); lane_prefetch(M.l_val + b); }
-            const int cnt = m - kb < 32 ? m - kb : 32;
-            for (int t = cnt - 1; t >= 0; t--) {
+            unsigned pend = __ballot_sync(FULLMASK, ok);
+            double wl = ok ? C.xlhs[ip] : 0.0;
+            for (;;) {
+                const unsigned nzm = __ballot_sync(FULLMASK, wl != 0.0) & pend;
+                if (!nzm) break;
+                const int t = 31 - __clz((int)nzm);
+                pend &= (1u << t) - 1u;
                 const int ii = __shfl_sync(FULLMASK, ip, t), bb = __shfl_sync(FULLMASK, b, t);
-                const double x = C.xlhs[ii];
-                __syncwarp();
-                if (x == 0.0) continue;
+                const double x = __shfl_sync(FULLMASK, wl, t);
                 for (int pos = bb;; pos += 32) {
                     const int r = M.l_idx[pos + lane];
                     const unsigned tm = __ballot_sync(FULLMASK, r < 0);
@@ -363,6 +416,7 @@ __device__ int sp_btran_tail(SpCtx &C, int nz, int marker) {
                 if (fabs(x) > droptol) { if (lane == 0) C.ilhs[nz] = ii; nz++; }
                 else if (lane == 0) C.xlhs[ii] = 0.0;
                 __syncwarp();
+                wl = ((pend >> lane) & 1u) ? C.xlhs[ip] : 0.0;
             }
         }
         if (lane == 0) C.l_flops += fl;

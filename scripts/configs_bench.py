@@ -135,24 +135,25 @@ def c5(args):
     pcp, pri, pv = pool
     colptr, rowidx, vals = cp.copy(), [ri[cp[j]:cp[j + 1]] for j in range(m)], [v[cp[j]:cp[j + 1]] for j in range(m)]
     tg = to = 0.0
+    tparts = [0.0, 0.0, 0.0]; oparts = [0.0, 0.0, 0.0]; nzl = 0
     same = True
     nft = 0
     done = 0
     for it in range(nupd):
         idx, val = pri[pcp[it]:pcp[it + 1]], pv[pcp[it]:pcp[it + 1]]
-        s1, d1 = wall(lambda: g.solve_for_update(len(idx), idx, val, "N", 1)); tg += d1
-        s2, d2 = wall(lambda: o.solve_for_update(len(idx), idx, val, "N", 1)); to += d2
-        n_ = o.nzlhs
+        s1, d1 = wall(lambda: g.solve_for_update(len(idx), idx, val, "N", 1)); tg += d1; tparts[0] += d1
+        s2, d2 = wall(lambda: o.solve_for_update(len(idx), idx, val, "N", 1)); to += d2; oparts[0] += d2
+        n_ = o.nzlhs; nzl += n_
         same = same and s1 == s2 == 0 and g.nzlhs == n_ and np.array_equal(g.ilhs[:n_], o.ilhs[:n_]) and np.array_equal(g.lhs, o.lhs)
         lhs = o.lhs
         j = int(np.argmax(np.abs(lhs)))                         # maxvolume.rs:120-131
         xtbl = lhs[j]
         jj = np.array([j])
-        s1, d1 = wall(lambda: g.solve_for_update(1, jj, None, "T", 0)); tg += d1
-        s2, d2 = wall(lambda: o.solve_for_update(1, jj, None, "T", 0)); to += d2
+        s1, d1 = wall(lambda: g.solve_for_update(1, jj, None, "T", 0)); tg += d1; tparts[1] += d1
+        s2, d2 = wall(lambda: o.solve_for_update(1, jj, None, "T", 0)); to += d2; oparts[1] += d2
         nf0 = o.info("nforrest")
-        s1, d1 = wall(lambda: g.update(xtbl)); tg += d1
-        s2, d2 = wall(lambda: o.update(xtbl)); to += d2
+        s1, d1 = wall(lambda: g.update(xtbl)); tg += d1; tparts[2] += d1
+        s2, d2 = wall(lambda: o.update(xtbl)); to += d2; oparts[2] += d2
         same = same and s1 == s2
         if s2 != 0:
             break
@@ -166,8 +167,9 @@ def c5(args):
     same_dense = bool(np.array_equal(xg, xo))
     rec = {"config": f"configs[4]: replay on a {m}-row basis, {done} column replacements (solve_for_update N+T, update)",
            "m": m, "forrest_tomlin_updates": int(nft), "permutation_updates": int(done - nft),
-           "gpu": {"us_per_replacement": 1e6 * tg / max(done, 1)},
-           "cpu_oracle_1thread": {"us_per_replacement": 1e6 * to / max(done, 1)},
+           "gpu": {"us_per_replacement": 1e6 * tg / max(done, 1), "us_ftran_btran_update": [1e6 * t / max(done, 1) for t in tparts]},
+           "cpu_oracle_1thread": {"us_per_replacement": 1e6 * to / max(done, 1), "us_ftran_btran_update": [1e6 * t / max(done, 1) for t in oparts]},
+           "avg_nzlhs_ftran": nzl / max(done, 1),
            "parity": {"every_solution_and_counter_bit_identical": bool(same), "solve_dense_after_replay_bit_identical": same_dense},
            "bound": "latency (one warp per call + one H2D/D2H round trip per call)"}
     yield rec
