@@ -268,7 +268,11 @@ __device__ __forceinline__ void warp_prefetch_l2(const void *p, int bytes) {
 #ifndef BLU_EMU
     const char *c = (const char *)p;
     for (int off = (threadIdx.x & 31) * 128; off < bytes; off += 32 * 128)
+#ifdef PF_L1
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(c + off));
+#else
         asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+#endif
 #else
     (void)p; (void)bytes;
 #endif
