@@ -19,7 +19,7 @@
 #include <algorithm>
 #include <time.h>
 
-#define PADDING 64 /* slack entries after the L/U/W stores: warp-wide terminator scans read ahead */
+#define PADDING 160 /* slack entries after the L/U/W stores: warp-wide terminator scans read up to 96 entries ahead */
 
 struct blu_b200 {
     int device;

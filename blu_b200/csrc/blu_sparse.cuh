@@ -33,7 +33,7 @@
 struct SpCtx {
     Mat M;
     int m, status;
-    int *pattern_symb, *pattern, *marked, *pstack, *irhs, *ilhs;
+    int *pattern_symb, *pattern, *marked, *pstack, *pend, *irhs, *ilhs;
     double *work, *xlhs;
     i64 l_flops, u_flops, r_flops;
 };
@@ -127,24 +127,19 @@ __device__ int sp_dfs(int i, const int *begin, const int *end, const int *index,
  * a time -- two dependent round trips per 32 edges instead of per edge.  Same visiting order, hence the
  * same finishing order, as sp_dfs. */
 __device__ int sp_dfs_warp(int i, const int *begin, const int *end, const int *index, int top,
-                           int *xi, int *pstack, int *marked, int marker) {
+                           int *xi, int *pstack, int *pend, int *marked, int marker) {
     const int lane = threadIdx.x & 31;
     if (marked[i] == marker) return top;
-    int head = 0;
+    /* the node being scanned lives in registers (cur, p, e); the stacks xi / pstack / pend hold its
+     * ancestors (node, resume position, line end), so a pop is one round trip */
+    int head = 0, cur = i;
+    int p = begin[cur], e = end ? end[cur] : 0x7fffffff;
     __syncwarp();
-    if (lane == 0) xi[0] = i;
+    if (lane == 0) marked[cur] = marker;
     __syncwarp();
-    while (head >= 0) {
-        i = xi[head];
-        if (marked[i] != marker) {
-            __syncwarp();
-            if (lane == 0) { marked[i] = marker; pstack[head] = begin[i]; }
-            __syncwarp();
-        }
-        const int p0 = pstack[head];
-        const int e = end ? end[i] : 0x7fffffff;
+    for (;;) {
         int found = -1, inext = -1;
-        for (int q = p0; q < e; q += 32) {
+        for (int q = p; q < e; q += 32) {
             const bool in = q + lane < e;
             const int idx = in ? index[q + lane] : -1;
             unsigned tm = 0; int nvalid = 32;
@@ -154,27 +149,33 @@ __device__ int sp_dfs_warp(int i, const int *begin, const int *end, const int *i
             if (cm) { const int l = __ffs((int)cm) - 1; found = q + l; inext = __shfl_sync(FULLMASK, idx, l); break; }
             if (tm) break;
         }
-        __syncwarp();
         if (found >= 0) {
-            if (lane == 0) { pstack[head] = found + 1; xi[head + 1] = inext; }
+            if (lane == 0) { xi[head] = cur; pstack[head] = found + 1; pend[head] = e; marked[inext] = marker; }
             head++;
+            cur = inext;
+            p = begin[cur]; e = end ? end[cur] : 0x7fffffff;
+            __syncwarp();
         } else {
-            head--; top--;
-            if (lane == 0) xi[top] = i;
+            top--;
+            if (lane == 0) xi[top] = cur;
+            head--;
+            if (head < 0) break;
+            __syncwarp();
+            cur = xi[head]; p = pstack[head]; e = pend[head];
         }
-        __syncwarp();
     }
+    __syncwarp();
     return top;
 }
 
 /* solve_symbolic.rs:19-40 */
 __device__ __forceinline__ int sp_symbolic(int m, const int *begin, const int *end, const int *index,
-                                           int nrhs, const int *irhs, int *xi, int *pstack, int *marked, int marker) {
+                                           int nrhs, const int *irhs, int *xi, int *pstack, int *pend, int *marked, int marker) {
     int top = m;
     __syncwarp();
     for (int n = 0; n < nrhs; n++) {
         const int i = irhs[n];
-        if (marked[i] != marker) top = sp_dfs_warp(i, begin, end, index, top, xi, pstack, marked, marker);
+        if (marked[i] != marker) top = sp_dfs_warp(i, begin, end, index, top, xi, pstack, pend, marked, marker);
         __syncwarp();
     }
     return top;
@@ -204,19 +205,31 @@ __device__ int sp_solve_triangular(int nz_symb, const int *pattern_symb, const i
             if (x == 0.0) continue;
             if (pivot) { x = __ddiv_rn(x, pp); fl++; }
             if (end) {
-                for (int pos = bb + lane; pos < ee; pos += 32) {
-                    const int r = index[pos];
-                    lhs[r] = __dsub_rn(lhs[r], __dmul_rn(x, value[pos]));
+                /* four chunks of the column in flight: the entries of a column hit distinct rows */
+                for (int pos = bb + lane; pos < ee; pos += 128) {
+                    int r[4]; double v[4], w[4];
+                    #pragma unroll
+                    for (int u = 0; u < 4; u++) { const int q = pos + 32 * u; r[u] = q < ee ? index[q] : -1; v[u] = q < ee ? value[q] : 0.0; }
+                    #pragma unroll
+                    for (int u = 0; u < 4; u++) w[u] = r[u] >= 0 ? lhs[r[u]] : 0.0;
+                    #pragma unroll
+                    for (int u = 0; u < 4; u++) if (r[u] >= 0) lhs[r[u]] = __dsub_rn(w[u], __dmul_rn(x, v[u]));
                 }
                 fl += ee - bb;
             } else {
-                for (int pos = bb;; pos += 32) {
-                    const int r = index[pos + lane];
-                    const unsigned tm = __ballot_sync(FULLMASK, r < 0);
-                    const int nvalid = tm ? __ffs((int)tm) - 1 : 32;
-                    if (lane < nvalid) lhs[r] = __dsub_rn(lhs[r], __dmul_rn(x, value[pos + lane]));
-                    fl += nvalid;
-                    if (tm) break;
+                for (int pos = bb;; pos += 64) {
+                    /* two chunks in flight (the stores carry >= 96 entries of slack behind the last line) */
+                    const int r0 = index[pos + lane], r1 = index[pos + 32 + lane];
+                    const double v0 = value[pos + lane], v1 = value[pos + 32 + lane];
+                    const unsigned t0 = __ballot_sync(FULLMASK, r0 < 0);
+                    const int n0 = t0 ? __ffs((int)t0) - 1 : 32;
+                    const unsigned t1 = __ballot_sync(FULLMASK, r1 < 0);
+                    const int n1 = t0 ? 0 : (t1 ? __ffs((int)t1) - 1 : 32);
+                    const double w0 = lane < n0 ? lhs[r0] : 0.0, w1 = lane < n1 ? lhs[r1] : 0.0;
+                    if (lane < n0) lhs[r0] = __dsub_rn(w0, __dmul_rn(x, v0));
+                    if (lane < n1) lhs[r1] = __dsub_rn(w1, __dmul_rn(x, v1));
+                    fl += n0 + n1;
+                    if (t0 || t1) break;
                 }
             }
             const bool keep = fabs(x) > droptol;
@@ -259,7 +272,7 @@ __device__ int sp_ftran_head(SpCtx &C, int nrhs, const double *xrhs) {
     const int m = C.m, lane = threadIdx.x & 31;
     const int nforrest = M.info->nforrest;
     const int marker = sp_next_marker(C);
-    const int top = sp_symbolic(m, M.l_begin, nullptr, M.l_idx, nrhs, C.irhs, C.pattern_symb, C.pstack, C.marked, marker);
+    const int top = sp_symbolic(m, M.l_begin, nullptr, M.l_idx, nrhs, C.irhs, C.pattern_symb, C.pstack, C.pend, C.marked, marker);
     const int nz_symb = m - top;
     for (int n = lane; n < nrhs; n += 32) C.work[C.irhs[n]] = xrhs[n];
     __syncwarp();
@@ -296,7 +309,7 @@ __device__ int sp_ftran_tail(SpCtx &C, int nz) {
     const double droptol = M.prm.droptol;
     if (nz <= nz_sparse) {
         const int mk = sp_next_marker(C);
-        const int top = sp_symbolic(m, M.u_begin, nullptr, M.u_idx, nz, C.pattern, C.pattern_symb, C.pstack, C.marked, mk);
+        const int top = sp_symbolic(m, M.u_begin, nullptr, M.u_idx, nz, C.pattern, C.pattern_symb, C.pstack, C.pend, C.marked, mk);
         nz = sp_solve_triangular(m - top, C.pattern_symb + top, M.u_begin, nullptr, M.u_idx, M.u_val, M.rowpiv,
                                  droptol, C.work, C.ilhs, &C.u_flops);
         for (int n = lane; n < nz; n += 32) {
@@ -384,7 +397,7 @@ __device__ int sp_btran_tail(SpCtx &C, int nz, int marker) {
     }
     if (nz <= nz_sparse) {
         const int mk = sp_next_marker(C);
-        const int top = sp_symbolic(m, M.lt_begin, nullptr, M.l_idx, nz, C.pattern, C.pattern_symb, C.pstack, C.marked, mk);
+        const int top = sp_symbolic(m, M.lt_begin, nullptr, M.l_idx, nz, C.pattern, C.pattern_symb, C.pstack, C.pend, C.marked, mk);
         nz = sp_solve_triangular(m - top, C.pattern_symb + top, M.lt_begin, nullptr, M.l_idx, M.l_val, nullptr,
                                  droptol, C.xlhs, C.ilhs, &C.l_flops);
     } else {
@@ -429,7 +442,7 @@ __device__ __forceinline__ void sp_ctx_init(SpCtx &C, const BluDev &D) {
     Mat &M = C.M;
     C.m = M.m; C.status = BLU_OK;
     C.pattern_symb = M.iwork1; C.pattern = M.iwork1 + M.m;
-    C.marked = M.marked; C.pstack = M.pstack; C.irhs = M.acols; C.ilhs = M.tmpi;
+    C.marked = M.marked; C.pstack = M.pstack; C.pend = M.tmpi + M.m; C.irhs = M.acols; C.ilhs = M.tmpi;
     C.work = M.work0; C.xlhs = M.gwork;
     C.l_flops = C.u_flops = C.r_flops = 0;
 }
@@ -476,7 +489,7 @@ __global__ void __launch_bounds__(32) k_solve_sparse(BluDev D, int nrhs, const i
         if (tr) {
             /* U' sparse, lu/solve_sparse.rs:68-111 */
             int marker = sp_next_marker(C);
-            const int top = sp_symbolic(m, M.lbeg, M.lend, M.w_idx, nrhs, C.irhs, C.pattern_symb, C.pstack, C.marked, marker);
+            const int top = sp_symbolic(m, M.lbeg, M.lend, M.w_idx, nrhs, C.irhs, C.pattern_symb, C.pstack, C.pend, C.marked, marker);
             for (int n = lane; n < nrhs; n += 32) C.work[C.irhs[n]] = xrhs[n];
             __syncwarp();
             nz = sp_solve_triangular(m - top, C.pattern_symb + top, M.lbeg, M.lend, M.w_idx, M.w_val, M.colpiv,
@@ -502,7 +515,7 @@ __global__ void __launch_bounds__(32) k_solve_sparse(BluDev D, int nrhs, const i
         const int jbegin = M.lbeg[jpivot], jend = M.lend[jpivot];
         /* row eta: U' solve seeded with row ipivot of U, nothing dropped; lu/solve_for_update.rs:70-120 */
         int marker = sp_next_marker(C);
-        const int top = sp_symbolic(m, M.lbeg, M.lend, M.w_idx, jend - jbegin, M.w_idx + jbegin, C.pattern_symb, C.pstack, C.marked, marker);
+        const int top = sp_symbolic(m, M.lbeg, M.lend, M.w_idx, jend - jbegin, M.w_idx + jbegin, C.pattern_symb, C.pstack, C.pend, C.marked, marker);
         const int nz_symb = m - top;
         const int room = M.l_mem - M.r_begin[nforrest];
         if (room < nz_symb) {
@@ -515,11 +528,19 @@ __global__ void __launch_bounds__(32) k_solve_sparse(BluDev D, int nrhs, const i
                             C.work, C.pattern, &C.u_flops);
         /* the symbolic pattern with its values becomes the row eta, :124-135 */
         const int rput = M.r_begin[nforrest];
-        for (int t = top + lane; t < m; t += 32) {
-            const int j = C.pattern_symb[t];
-            M.l_idx[rput + (t - top)] = M.pinv[j];
-            M.l_val[rput + (t - top)] = C.work[j];
-            C.work[j] = 0.0;
+        for (int t = top + lane; t < m; t += 32 * 4) {
+            int jj[4], pi[4]; double wv[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) { const int q = t + 32 * u; jj[u] = q < m ? C.pattern_symb[q] : -1; }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) { pi[u] = jj[u] >= 0 ? M.pinv[jj[u]] : 0; wv[u] = jj[u] >= 0 ? C.work[jj[u]] : 0.0; }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) if (jj[u] >= 0) {
+                const int q = t + 32 * u;
+                M.l_idx[rput + (q - top)] = pi[u];
+                M.l_val[rput + (q - top)] = wv[u];
+                C.work[jj[u]] = 0.0;
+            }
         }
         if (lane == 0) { M.r_begin[nforrest + 1] = rput + nz_symb; M.eta_row[nforrest] = ipivot; I->btran_for_update = jpivot; }
         __syncwarp();
@@ -811,10 +832,12 @@ __global__ void __launch_bounds__(32) k_update(BluDev D, double xtbl, int *scal)
 
     /* new pivot, update.rs:485-513 */
     int marker = sp_next_marker(C);
-    for (int pos = rbeg + lane; pos < rend; pos += 32) {
-        const int i = M.l_idx[pos];
-        C.marked[i] = marker;
-        work1[i] = M.l_val[pos];
+    for (int pos = rbeg + lane; pos < rend; pos += 32 * 8) {      /* eight independent loads per lane in flight */
+        int ii[8]; double vv[8];
+        #pragma unroll
+        for (int u = 0; u < 8; u++) { const int q = pos + 32 * u; ii[u] = q < rend ? M.l_idx[q] : -1; vv[u] = q < rend ? M.l_val[q] : 0.0; }
+        #pragma unroll
+        for (int u = 0; u < 8; u++) if (ii[u] >= 0) { C.marked[ii[u]] = marker; work1[ii[u]] = vv[u]; }
     }
     __syncwarp();
     double newpiv = spike_diag;
@@ -955,47 +978,62 @@ __global__ void __launch_bounds__(32) k_update(BluDev D, double xtbl, int *scal)
             __syncwarp();
         }
     } else {
+        /* no diagonal element in the spike, update.rs:667-818: an augmenting path (BFS, lane 0), then the
+         * reach of every path node (depth-first, the whole warp probing 32 edges at a time) decides
+         * whether a purely unsymmetric permutation restores triangularity */
         int dec = 0;
-        if (lane == 0) {
-            int *path = iwork1, *reach = iwork2;
-            const int top = sp_bfs_path(m, jpivot, M.lbeg, M.lend, M.w_idx, path, C.marked, iwork2);
-            if (!(top < m - 1) || path[top] != jpivot) { BLU_CHECK(C, 0); }
-            else {
-                istriangular = 1;
-                rtop = m;
-                marker = ++I->marker;
-                for (int t = top; t < m - 1 && istriangular; t++) {
-                    const int j = path[t], jnext = path[t + 1];
-                    const int where = sp_find1(jnext, M.w_idx, M.lbeg[j], M.lend[j]);
-                    if (where >= M.lend[j]) { BLU_CHECK(C, 0); break; }
-                    M.w_idx[where] = j;      /* take the path edge out for a moment */
-                    rtop = sp_dfs(j, M.lbeg, M.lend, M.w_idx, rtop, reach, C.pstack, C.marked, marker);
-                    reach[rtop] = jnext;
-                    M.w_idx[where] = jnext;
-                    istriangular = C.marked[jnext] != marker;
+        int *path = iwork1, *reach = iwork2;
+        int top = 0;
+        if (lane == 0) top = sp_bfs_path(m, jpivot, M.lbeg, M.lend, M.w_idx, path, C.marked, iwork2);
+        top = sp_bcast(top);
+        __syncwarp();
+        if (!(top < m - 1) || path[top] != jpivot) { if (lane == 0) BLU_CHECK(C, 0); __syncwarp(); }
+        else {
+            istriangular = 1;
+            rtop = m;
+            marker = sp_next_marker(C);
+            for (int t = top; t < m - 1 && istriangular; t++) {
+                const int j = path[t], jnext = path[t + 1];
+                const int le = M.lend[j];
+                const int where = sp_find(jnext, M.w_idx, M.lbeg[j], le);
+                if (where >= le) { if (lane == 0) BLU_CHECK(C, 0); __syncwarp(); break; }
+                if (lane == 0) M.w_idx[where] = j;      /* take the path edge out for a moment */
+                __syncwarp();
+                rtop = sp_dfs_warp(j, M.lbeg, M.lend, M.w_idx, rtop, reach, C.pstack, C.pend, C.marked, marker);
+                if (lane == 0) { reach[rtop] = jnext; M.w_idx[where] = jnext; }
+                __syncwarp();
+                istriangular = C.marked[jnext] != marker;
+            }
+            if (istriangular && C.status == BLU_OK) {
+                const int j = path[m - 1];
+                rtop = sp_dfs_warp(j, M.lbeg, M.lend, M.w_idx, rtop, reach, C.pstack, C.pend, C.marked, marker);
+                if (lane == 0) { reach[rtop] = jpivot; C.marked[j]--; }
+                __syncwarp();
+                int hit = 0;
+                for (int pos = M.u_begin[ipivot];; pos += 32) {
+                    const int r = M.u_idx[pos + lane];
+                    const unsigned tm = __ballot_sync(FULLMASK, r < 0);
+                    const int nvalid = tm ? __ffs((int)tm) - 1 : 32;
+                    if (lane < nvalid && C.marked[qmap[r]] == marker) hit = 1;
+                    if (tm) break;
                 }
-                if (istriangular && C.status == BLU_OK) {
-                    const int j = path[m - 1];
-                    rtop = sp_dfs(j, M.lbeg, M.lend, M.w_idx, rtop, reach, C.pstack, C.marked, marker);
-                    reach[rtop] = jpivot;
-                    C.marked[j]--;
-                    for (int pos = M.u_begin[ipivot]; M.u_idx[pos] >= 0; pos++)
-                        if (C.marked[qmap[M.u_idx[pos]]] == marker) istriangular = 0;
-                    C.marked[j]++;
-                }
-                if (istriangular && C.status == BLU_OK) {
-                    const int nswap = m - top - 1;
-                    sp_permute(C, path + top, nswap, &pmin, &pmax);
-                    dec = 1;
-                    nreach = m - rtop;
-                    for (int n = 0; n < nreach; n++) iwork1[rtop + n] = pmap[reach[rtop + n]];
-                }
+                if (__any_sync(FULLMASK, hit)) istriangular = 0;
+                __syncwarp();
+                if (lane == 0) C.marked[j]++;
+                __syncwarp();
+            }
+            if (istriangular && C.status == BLU_OK) {
+                const int nswap = m - top - 1;
+                if (lane == 0) sp_permute(C, path + top, nswap, &pmin, &pmax);
+                __syncwarp();
+                dec = 1;
+                nreach = m - rtop;
+                for (int n = lane; n < nreach; n += 32) iwork1[rtop + n] = pmap[reach[rtop + n]];
+                __syncwarp();
             }
         }
-        __syncwarp();
-        istriangular = sp_bcast(istriangular); nreach = sp_bcast(nreach); rtop = sp_bcast(rtop);
         pmin = sp_bcastd(pmin); pmax = sp_bcastd(pmax);
-        u_nz -= sp_bcast(dec);
+        u_nz -= dec;
         use_reach = istriangular;
         if (C.status != BLU_OK) { if (lane == 0) scal[0] = C.status; return; }
     }
