@@ -189,7 +189,7 @@ def main():
     if args.threads_per_basis:
         b.threads_per_basis = args.threads_per_basis
     # sized so that no basis of the batch asks for more (a Reallocate re-runs the whole batch)
-    b.l_mem = 100000; b.u_mem = 100000; b.w_mem = 500000
+    b.l_mem = 100000; b.u_mem = 100000; b.w_mem = 900000   # 24 MB per basis, 98 GB for 4,096: no garbage collection, no Reallocate
     stream = torch.cuda.Stream()
     b.set_stream(stream.cuda_stream)
 
