@@ -16,6 +16,9 @@
  */
 #ifndef BLU_FACTOR_BUMP_CUH
 #define BLU_FACTOR_BUMP_CUH
+#ifndef PF_DIST
+#define PF_DIST 2   /* how many of its own lines ahead a warp prefetches into L2 */
+#endif
 #ifndef SEARCH_MERGE
 #define SEARCH_MERGE 0   /* measured on B200: the every-thread merge costs 3 % more than three block-wide minima */
 #endif
@@ -721,8 +724,8 @@ template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
 
     /* column file update, pivot.rs:219-331 / 569-693: one warp per column of the pivot row */
     for (int k = 1 + wid; k <= rnz1; k += NW) {
-        if (k + NW <= rnz1) {      /* next line of this warp: start pulling it in now */
-            const int nb = S.chb[k + NW], nn = S.che[k + NW] - nb;
+        if (k + PF_DIST * NW <= rnz1) {      /* a later line of this warp: start pulling it in now */
+            const int nb = S.chb[k + PF_DIST * NW], nn = S.che[k + PF_DIST * NW] - nb;
             warp_prefetch_l2(M.w_idx + nb, nn * 4);
             warp_prefetch_l2(M.w_val + nb, nn * 8);
         }
@@ -860,7 +863,7 @@ template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
 
     /* row file update, pivot.rs:335-401 / 697-774: one warp per row of the pivot column */
     for (int p = 1 + wid; p <= cnz1; p += NW) {
-        if (p + NW <= cnz1) warp_prefetch_l2(M.w_idx + S.rhb[p + NW], (S.rhe[p + NW] - S.rhb[p + NW]) * 4);
+        if (p + PF_DIST * NW <= cnz1) warp_prefetch_l2(M.w_idx + S.rhb[p + PF_DIST * NW], (S.rhe[p + PF_DIST * NW] - S.rhb[p + PF_DIST * NW]) * 4);
         const int i = cidx[p];
         const int line = m + i;
         int beg = S.rhb[p], end = S.rhe[p], cap = S.rhc[p];

@@ -351,3 +351,68 @@ def test_batch_pipelined_upload(layout):
         _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
         assert np.array_equal(x[k], xo)
         assert b.info(k, "condest_u") == o.info("condest_u") and b.info(k, "residual_test") == o.info("residual_test")
+
+
+# ---- BASELINE.json's full sizes, through size-independent properties (no oracle run needed) ----
+
+def _residual(cp, ri, v, m, x, b, trans="N"):
+    A = sp.csc_matrix((v, ri, cp), shape=(m, m))
+    r = (A @ x if trans == "N" else A.T @ x) - b
+    return np.abs(r).max() / max(np.abs(b).max(), np.abs(x).max() * abs(A).sum(axis=0).max())
+
+
+def test_config2_full_batch_properties():
+    """configs[1] at full size: 4,096 bases of 2,000^2 through blu_batch_factorize (pipelined upload) +
+    blu_batch_solve_dense.  Every basis must come back OK with full rank and a small residual; a sample
+    is compared with the oracle bit for bit."""
+    nmat, m = 4096, 2000
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 700, 5.0, 2000, 3000)
+    b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()))
+    b.l_mem = 100000; b.u_mem = 100000; b.w_mem = 900000
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all()
+    st, x, sst = b.solve_dense(rhs, "N")
+    assert st == 0 and (sst == 0).all()
+    worst = 0.0
+    for k in range(0, nmat, 16):
+        lo, hi = bb[k * m], be[(k + 1) * m - 1]
+        cp = np.concatenate([bb[k * m:(k + 1) * m], [hi]]) - lo
+        worst = max(worst, _residual(cp, bi[lo:hi], bx[lo:hi], m, x[k], rhs[k * m:(k + 1) * m]))
+        assert b.info(k, "rank") == m and b.info(k, "residual_test") < 1e-10
+    assert worst < 1e-10, worst
+    for k in (0, 2047, 4095):
+        cp, ri, v = gen.basis(2000 + k, m, 700, 5.0)
+        o = oracle_for(m, len(v))
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        _, fo = o.get_factors()
+        _, fg = b.get_factors(k)
+        for key in fo:
+            assert np.array_equal(fo[key], fg[key]), (k, key)
+        _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
+        assert np.array_equal(x[k], xo)
+
+
+def test_config3_full_size_properties():
+    """configs[2] at full size (100,000 rows, 3,995-wide bump that fills to full density): rank, the
+    permutation outputs, B[rowperm,colperm] = L U and both solves, without running the oracle."""
+    m, bump = 100000, 4000
+    cp, ri, v = gen.config3(m, bump)
+    g = BLU(m, len(v))
+    g.threads_per_basis = 1024
+    dense = bump * bump
+    g.l_mem = int(2.2 * (dense // 2 + 10 * m)); g.u_mem = int(1.2 * (dense // 2 + 10 * m)); g.w_mem = int(3.0 * dense + 40 * m)
+    assert g.factorize(cp[:-1], cp[1:], ri, v) == 0
+    assert g.info("rank") == m and g.info("internal_error") == 0 and g.info("bump_size") > 3900
+    st, f = g.get_factors()
+    assert st == 0
+    assert np.array_equal(np.sort(f["rowperm"]), np.arange(m)) and np.array_equal(np.sort(f["colperm"]), np.arange(m))
+    assert_backward_error(cp, ri, v, f, m, m)
+    b = gen.rhs(4002, m)
+    for tr in "NT":
+        st, x = g.solve_dense(b, tr)
+        assert st == 0 and _residual(cp, ri, v, m, x, b, tr) < 1e-9
+    idx, val = gen.sparse_rhs_np(6000, m, 100)
+    assert g.solve_sparse(100, idx, val, "N") == 0
+    bs = np.zeros(m); bs[idx] = val
+    assert _residual(cp, ri, v, m, g.lhs, bs) < 1e-9
+    assert set(np.nonzero(g.lhs)[0]) <= set(g.ilhs[:g.nzlhs])
