@@ -109,6 +109,15 @@ def algorithmic_bytes(b, nmat, m):
     return tot_f, tot_s
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -136,7 +145,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -150,6 +159,13 @@ def main():
     ap.add_argument("--ref-per-core", type=int, default=16, help="bases per host core in one reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+
+    # stdout carries exactly ONE line, the JSON record: everything else that libraries print there
+    # (NCCL prints its version banner on stdout) is sent to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -311,7 +327,7 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     b.close()
     if world > 1:
         dist.destroy_process_group()
