@@ -3,14 +3,15 @@
  * solve_for_update,update}.rs and the argument checks of src/{solve_sparse,
  * solve_for_update,update}.rs.
  *
- * One warp per call.  What is sequential in the reference and decides the output
- * (the depth-first reach, whose finishing order IS the order of ilhs; the path search
- * and permutation of update()) runs on lane 0; everything that is a sweep over a line
- * (axpy down a column, scans for an index, gathers/scatters of a pattern, compaction)
- * is shared by the 32 lanes with ballot/prefix ordering so that in-line storage order --
- * which the next DFS depends on -- is exactly the reference's.  Floating point: one
- * rounding per multiply and per add/subtract (no FMA) and sums accumulated in the
- * reference's order, so values are bit-identical to the sequential code.
+ * One warp per call.  What is sequential in the reference and decides the output keeps its order:
+ * the depth-first reach (whose finishing order IS the order of ilhs) is walked with the reference's
+ * control flow, but the whole warp probes 32 edges at a time for "first neighbour not marked yet"
+ * (sp_dfs_warp); the breadth-first path search and the permutation of update() run on lane 0.
+ * Everything that is a sweep over a line (axpy down a column, scans for an index, gathers/scatters of a
+ * pattern, compaction) is shared by the 32 lanes with ballot/prefix ordering so that in-line storage
+ * order -- which the next DFS depends on -- is exactly the reference's.  Floating point: one rounding
+ * per multiply and per add/subtract (no FMA) and sums accumulated in the reference's order, so values
+ * are bit-identical to the sequential code.
  *
  * The row file of U lives in W as lines (lbeg,lend,lcap)[j], j < m, inside the live half
  * of W (info->w_half); "the line has no room" (w_end[j] == w_begin[next], update.rs:524)
