@@ -59,9 +59,25 @@ void launch(emu_dim3 grid, emu_dim3 block, size_t smem, std::function<void()> bo
             f.state = 0;
         }
         int done = 0;
+        /* EMU_SEED != 0: visit the runnable threads in a different pseudo-random order on every scheduler
+         * pass.  Between two barriers the real hardware promises no order among lanes either, so code
+         * that only works in lane order (a missing __syncwarp between a read and a write of the same
+         * word, say) shows up as a parity failure under some seed. */
+        unsigned long long rng = 0;
+        { const char *e = getenv("EMU_SEED"); rng = e ? strtoull(e, nullptr, 10) * 0x9E3779B97F4A7C15ULL + b : 0; }
+        std::vector<int> order((size_t)nthreads);
+        for (int t = 0; t < nthreads; t++) order[(size_t)t] = t;
         while (done < nthreads) {
             int progressed = 0;
-            for (int t = 0; t < nthreads; t++) {
+            if (rng) {
+                for (int t = nthreads - 1; t > 0; t--) {
+                    rng = rng * 6364136223846793005ULL + 1442695040888963407ULL;
+                    int u = (int)((rng >> 33) % (unsigned long long)(t + 1));
+                    int tmp = order[(size_t)t]; order[(size_t)t] = order[(size_t)u]; order[(size_t)u] = tmp;
+                }
+            }
+            for (int ti = 0; ti < nthreads; ti++) {
+                const int t = order[(size_t)ti];
                 Fiber &f = fibers[t];
                 if (f.state == 2) continue;
                 if (f.state == 1) { if (*f.gen == f.mygen) continue; f.state = 0; }

@@ -169,3 +169,23 @@ def test_emu_edge_shapes(emu, case, monkeypatch):
     import test_gpu_parity as tg
     monkeypatch.setattr(tg, "BLU", lambda m, nnz: BLU(m, nnz, lib=emu))
     tg.test_edge_shapes(case)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_emu_random_lane_order(emu, seed, monkeypatch):
+    """The emulator visits the runnable lanes in a pseudo-random order between barriers (EMU_SEED): code
+    that silently relies on lane order -- a missing __syncwarp between a read and a write of one word --
+    fails parity under some seed.  One compact scenario through every kernel."""
+    from parity import replay_updates, assert_sparse_solve_parity
+    monkeypatch.setenv("EMU_SEED", str(seed))
+    m = 90
+    cp, ri, v = gen.basis(200 + seed, m, 30, 4.0)
+    pool = gen.basis(300 + seed, m, 0, 3.0)
+    o = oracle_for(m, len(v), 400)
+    g = BLU(m, len(v), lib=emu)
+    g.threads_per_basis = 64
+    assert o.factorize(cp[:-1], cp[1:], ri, v) == g.factorize(cp[:-1], cp[1:], ri, v) == 0
+    assert_factor_parity(g, o)
+    assert_sparse_solve_parity(g, o, m, 900 + seed, sizes=(1, 4, 30))
+    replay_updates(g, o, m, pool, 12)
+    assert_sparse_solve_parity(g, o, m, 950 + seed, sizes=(2, 40))
