@@ -69,6 +69,7 @@ def load_library(path=None):
     L.blu_factorize.argtypes = [vp, i64p, i64p, i64p, f64p]
     L.blu_get_factors.argtypes = [vp, i64p, i64p, i64p, i64p, f64p, i64p, i64p, f64p]
     L.blu_solve_dense.argtypes = [vp, f64p, f64p, ctypes.c_char]
+    L.blu_solve_dense_multi.argtypes = [vp, ctypes.c_int64, f64p, f64p, ctypes.c_char]
     L.blu_solve_sparse.argtypes = [vp, ctypes.c_int64, i64p, f64p, i64p, i64p, f64p, ctypes.c_char]
     L.blu_solve_for_update.argtypes = [vp, ctypes.c_int64, i64p, f64p, i64p, i64p, f64p, ctypes.c_char]
     L.blu_update.argtypes = [vp, ctypes.c_double]
@@ -200,6 +201,13 @@ class BLU(_Base):
             else:
                 self.lhs[:] = 0.0
             self.nzlhs = 0
+
+    def solve_dense_multi(self, rhs, trans="N"):
+        """rhs[nrhs, m] -> (status, x[nrhs, m]): solve_dense for every row, all in flight together."""
+        r = _f64(rhs).reshape(-1, self.m)
+        x = np.zeros_like(r)
+        st = self._L.blu_solve_dense_multi(self._h, r.shape[0], _pf(r), _pf(x), _ch(trans))
+        return st, x
 
     # blu.rs:207: result in self.lhs / self.ilhs / self.nzlhs
     def solve_sparse(self, nzrhs, irhs, xrhs, trans="N"):

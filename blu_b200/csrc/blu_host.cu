@@ -42,6 +42,7 @@ struct blu_b200 {
     /* sparse-solve staging (object API) */
     int64_t *d_irhs; double *d_xrhs; int64_t *d_ilhs; double *d_xout; int *d_scal;
     int *h_scal; int64_t *h_ilhs; double *h_xout;   /* pinned */
+    double *dm_rhs, *dm_lhs, *dm_work; int *dm_status; int64_t multi_cap;   /* blu_solve_dense_multi staging */
     int info_dirty;             /* device info block is newer than hinfo */
     int norms;                  /* run condest/residual_test after every factorization (factorize.rs:121-147) */
     cudaStream_t copy_stream, chunk_stream[4]; cudaEvent_t ev_up[16], ev_ch[4]; int have_pipe;   /* pipelined upload (blu_batch_factorize) */
@@ -118,6 +119,7 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     o->launches = 0; o->nrealloc = 0; o->last_ms[0] = o->last_ms[1] = 0.0;
     o->have_b = 0; o->info_dirty = 0; o->norms = 1; o->last_norms_ms = 0.0;
     o->have_pipe = 0; o->d_chunk_end = nullptr; o->h_chunk_end = nullptr;
+    o->dm_rhs = o->dm_lhs = o->dm_work = nullptr; o->dm_status = nullptr; o->multi_cap = 0;
     o->h_scal = nullptr; o->h_ilhs = nullptr; o->h_xout = nullptr;
     o->time_factorize = o->time_solve = o->time_update = 0.0;
     BluDev &d = o->d;
@@ -360,7 +362,7 @@ extern "C" int blu_batch_factorize_resident(blu_batch_t *o) {
 static int solve_dense_resident(blu_b200 *o, char trans) {
     CK(cudaSetDevice(o->device));
     timer_start(o);
-    BLU_LAUNCH(k_solve_dense, o->d.nmat, 32, 0, o->stream, o->d, (const double *)o->d_rhs, o->d_lhs, trans, o->d_status);
+    BLU_LAUNCH(k_solve_dense, o->d.nmat, 32, 0, o->stream, o->d, (const double *)o->d_rhs, o->d_lhs, trans, o->d_status, (double *)nullptr, 0);
     o->launches++;
     CK(cudaGetLastError());
     timer_stop(o, 1);
@@ -907,3 +909,40 @@ extern "C" int blu_update(blu_t *o, double xtbl) {
     o->time_update += wall_now() - tic;
     return status;
 }
+
+/* many right-hand sides against one factorization -- solve_dense (solve_dense.rs:24)
+ * applied to every column of rhs[nrhs][m]; one warp per right-hand side, all of them in flight together
+ * (the factors are read-only).  Bit-identical to nrhs separate blu_solve_dense calls. */
+extern "C" int blu_solve_dense_multi(blu_t *o, int64_t nrhs, const double *rhs, double *lhs, char trans) {
+    if (!o || !o->single || nrhs < 0 || (nrhs > 0 && (!rhs || !lhs))) return BLU_ERROR_INVALID_ARGUMENT;
+    { int st0 = ensure_info(o); if (st0 != BLU_OK) return st0; }
+    if (o->hinfo[0].nupdate < 0) return BLU_ERROR_INVALID_CALL;   /* solve_dense.rs:25 */
+    if (nrhs == 0) return BLU_OK;
+    CK(cudaSetDevice(o->device));
+    const double tic = wall_now();
+    const size_t m = (size_t)o->d.m, n = (size_t)nrhs;
+    if ((int64_t)n > o->multi_cap) {
+        dfree(o, o->dm_rhs); dfree(o, o->dm_lhs); dfree(o, o->dm_work); dfree(o, o->dm_status);
+        o->dm_rhs = o->dm_lhs = o->dm_work = nullptr; o->dm_status = nullptr; o->multi_cap = 0;
+        int st = dalloc(o, &o->dm_rhs, n * m);
+        if (st == BLU_OK) st = dalloc(o, &o->dm_lhs, n * m);
+        if (st == BLU_OK) st = dalloc(o, &o->dm_work, n * m);
+        if (st == BLU_OK) st = dalloc(o, &o->dm_status, n);
+        if (st != BLU_OK) return st;
+        o->multi_cap = (int64_t)n;
+    }
+    CK(cudaMemcpyAsync(o->dm_rhs, rhs, n * m * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+    BLU_LAUNCH(k_garbage_perm, 1, 32, 0, o->stream, o->d);
+    timer_start(o);
+    BLU_LAUNCH(k_solve_dense, (int)std::min<size_t>(n, 1u << 20), 32, 0, o->stream, o->d, (const double *)o->dm_rhs, o->dm_lhs, trans,
+               o->dm_status, o->dm_work, (int)nrhs);
+    o->launches += 2;
+    CK(cudaGetLastError());
+    timer_stop(o, 1);
+    CK(cudaMemcpyAsync(lhs, o->dm_lhs, n * m * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+    CK(cudaStreamSynchronize(o->stream));
+    o->info_dirty = 1;
+    o->time_solve += wall_now() - tic;
+    return BLU_OK;
+}
+

@@ -128,20 +128,29 @@ __device__ __forceinline__ void dev_dot_sweep(int m, bool asc, const int *dep, c
  * reference); the lanes share the dot product / axpy of each step and the pointer
  * loads are batched 32 pivots at a time.  Every multiply, add, subtract and divide is
  * rounded once and sums run in the reference's order, so the result is bit-identical. */
-__global__ void __launch_bounds__(32) k_solve_dense(BluDev D, const double *rhs_all, double *lhs_all, char trans, int *status) {
+/* Two shapes: (a) multi_work == nullptr: unit u = basis D.slot0 + u of a batch, one right-hand side each;
+ * (b) multi_work != nullptr: nrhs right-hand sides against the ONE basis in slot D.slot0 (the factors are
+ * only read; every unit has its own work vector multi_work + u*m; the pivot sequence must have been
+ * compacted by k_garbage_perm before). */
+__global__ void __launch_bounds__(32) k_solve_dense(BluDev D, const double *rhs_all, double *lhs_all, char trans, int *status,
+                                                     double *multi_work, int nrhs) {
     __shared__ Mat M;
     const int lane = threadIdx.x & 31;
-    for (int s = D.slot0 + blockIdx.x; s < D.slot0 + D.nslot; s += gridDim.x) {
-        if (lane == 0) mat_view(M, D, s);
+    const bool multi = multi_work != nullptr;
+    const int nunits = multi ? nrhs : D.nslot;
+    for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const int s = multi ? unit : D.slot0 + unit;       /* index of rhs / lhs / status */
+        __syncwarp();
+        if (lane == 0) mat_view(M, D, multi ? D.slot0 : s);
         __syncwarp();
         const int m = M.m;
         BluInfo *I = M.info;
         if (I->nupdate < 0) { if (lane == 0 && status) status[s] = BLU_ERROR_INVALID_CALL; __syncwarp(); continue; }
-        if (lane == 0) dev_garbage_perm(M);
+        if (!multi && lane == 0) dev_garbage_perm(M);
         __syncwarp();
         const double *rhs = rhs_all + (size_t)s * m;
         double *lhs = lhs_all + (size_t)s * m;
-        double *work = M.work1;
+        double *work = multi ? multi_work + (size_t)unit * m : M.work1;
         const int nforrest = I->nforrest;
         const bool fresh = I->nupdate == 0;   /* the wavefront sweeps need the dependency reach computed by build_factors */
         for (int i = lane; i < m; i += 32) work[i] = rhs[i];
@@ -292,6 +301,11 @@ __global__ void __launch_bounds__(32) k_solve_dense(BluDev D, const double *rhs_
         if (lane == 0 && status) status[s] = BLU_OK;
         __syncwarp();
     }
+}
+
+__global__ void k_garbage_perm(BluDev D) {
+    __shared__ Mat M;
+    if (threadIdx.x == 0) { mat_view(M, D, D.slot0); if (M.info->nupdate >= 0) dev_garbage_perm(M); }
 }
 
 /* get_factors.rs:48-180.  Output in 64-bit indices straight into device staging buffers:

@@ -86,6 +86,10 @@ int blu_get_factors(blu_t *o, int64_t *rowperm, int64_t *colperm,
 /* BLU::solve_dense, blu.rs:182-184 -> solve_dense.rs:24.  trans 't'/'T' = transposed. */
 int blu_solve_dense(blu_t *o, const double *rhs, double *lhs, char trans);
 
+/* Many right-hand sides against one factorization: rhs and lhs hold nrhs vectors of
+ * length m back to back; the result is bit-identical to nrhs calls of blu_solve_dense. */
+int blu_solve_dense_multi(blu_t *o, int64_t nrhs, const double *rhs, double *lhs, char trans);
+
 /* BLU::solve_sparse, blu.rs:207-230 -> solve_sparse.rs:35.  The result is returned like
  * BLU.lhs / ilhs / nzlhs: lhs[m] scattered (zero elsewhere), ilhs[0..*nzlhs) its pattern. */
 int blu_solve_sparse(blu_t *o, int64_t nzrhs, const int64_t *irhs, const double *xrhs,

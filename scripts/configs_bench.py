@@ -104,7 +104,7 @@ def c4(args):
     rec, g, o = run_factorize(f"configs[3] scaled: circuit-like {n}x{n} grid (m={m}); full size is 1000x1000", cp, ri, v, m, 1024, mem, 5002,
                               file_diff=False, note="scaled down: the Markowitz search of the device path scans the active columns (O(bump) per pivot), which does not scale to a 10^6 bump yet")
     # Gilbert-Peierls solves: 0.1 % dense right-hand sides, both systems
-    nrhs = 1000 if not args.quick else 100
+    nrhs = args.nrhs or (1000 if not args.quick else 100)
     nz = max(1, m // 1000)
     tg = to = 0.0
     same = True
@@ -117,6 +117,22 @@ def c4(args):
         n_ = o.nzlhs
         nzl += n_
         same = same and g.nzlhs == n_ and np.array_equal(g.ilhs[:n_], o.ilhs[:n_]) and np.array_equal(g.lhs, o.lhs)
+    # the same right-hand sides, all at once, through the multi-RHS dense solve
+    R = np.zeros((nrhs, m))
+    for r in range(nrhs):
+        idx, val = gen.sparse_rhs_np(6000 + r, m, nz)
+        R[r, idx] = val
+    g.solve_dense_multi(R[:8], "N")                              # warm-up / staging allocation
+    (sm, X), tm = wall(lambda: g.solve_dense_multi(R, "N"))
+    ns = min(nrhs, 50)
+    tcs = 0.0
+    same_multi = sm == 0
+    for r in range(ns):
+        (_, xo), dt = wall(lambda: o.solve_dense(R[r], "N")); tcs += dt
+        same_multi = same_multi and np.array_equal(X[r], xo)
+    rec["solve_dense_multi"] = {"nrhs": nrhs, "gpu_ms_total": 1e3 * tm, "gpu_ms_per_rhs": 1e3 * tm / nrhs,
+                                "cpu_oracle_ms_per_rhs": 1e3 * tcs / ns, "bit_identical_to_oracle_solve_dense": bool(same_multi),
+                                "note": "one warp per right-hand side, all in flight; includes H2D of rhs and D2H of the solutions"}
     rec["solve_sparse"] = {"calls": nrhs, "nzrhs": nz, "avg_nzlhs": nzl / nrhs, "gpu_ms_per_call": 1e3 * tg / nrhs,
                            "cpu_oracle_ms_per_call": 1e3 * to / nrhs, "bit_identical_pattern_order_and_values": bool(same),
                            "bound": "latency (one warp; DFS on one lane)"}
@@ -189,6 +205,7 @@ def c5(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--nrhs", type=int, default=0, help="right-hand sides of the configs[3] solve series")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.jsonl"))
     ap.add_argument("which", nargs="*", default=["c1", "c3", "c4", "c5"])
     args = ap.parse_args()

@@ -1,0 +1,3 @@
+cd /root/repo
+rm -f gpurun_out/configs_q6.jsonl
+timeout 900 python scripts/configs_bench.py --quick --nrhs 1000 --out gpurun_out/configs_q6.jsonl c4 > gpurun_out/cfgq6_c4.log 2>&1; echo "rc $?"; tail -3 gpurun_out/cfgq6_c4.log | cut -c1-300

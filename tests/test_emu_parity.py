@@ -189,3 +189,20 @@ def test_emu_random_lane_order(emu, seed, monkeypatch):
     assert_sparse_solve_parity(g, o, m, 900 + seed, sizes=(1, 4, 30))
     replay_updates(g, o, m, pool, 12)
     assert_sparse_solve_parity(g, o, m, 950 + seed, sizes=(2, 40))
+
+
+def test_emu_solve_dense_multi(emu):
+    """many right-hand sides against one factorization == that many solve_dense calls."""
+    m = 120
+    cp, ri, v = gen.basis(77, m, 30, 4.0)
+    g, o, st = pair(emu, cp, ri, v, m, 64)
+    assert st == 0
+    R = np.stack([gen.rhs(800 + k, m) for k in range(5)])
+    for tr in "NT":
+        sg, X = g.solve_dense_multi(R, tr)
+        assert sg == 0
+        for k in range(5):
+            _, xo = o.solve_dense(R[k], tr)
+            assert np.array_equal(X[k], xo), (tr, k)
+    g2 = BLU(m, len(v), lib=emu)
+    assert g2.solve_dense_multi(R, "N")[0] == -2          # never factorized

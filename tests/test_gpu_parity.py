@@ -416,3 +416,19 @@ def test_config3_full_size_properties():
     bs = np.zeros(m); bs[idx] = val
     assert _residual(cp, ri, v, m, g.lhs, bs) < 1e-9
     assert set(np.nonzero(g.lhs)[0]) <= set(g.ilhs[:g.nzlhs])
+
+
+def test_solve_dense_multi():
+    """many right-hand sides against one factorization, bit-identical to separate calls."""
+    m = 2000
+    (cp, ri, v), _ = gen.config2_matrix(5)
+    g, o, st = run_pair(cp, ri, v, m)
+    assert st == 0
+    R = np.stack([gen.rhs(800 + k, m) for k in range(64)])
+    for tr in "NT":
+        sg, X = g.solve_dense_multi(R, tr)
+        assert sg == 0
+        for k in (0, 17, 63):
+            _, xo = o.solve_dense(R[k], tr)
+            assert np.array_equal(X[k], xo), (tr, k)
+    assert BLU(m, 10).solve_dense_multi(R[:2], "N")[0] == -2
