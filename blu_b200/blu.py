@@ -70,6 +70,7 @@ def load_library(path=None):
     L.blu_get_factors.argtypes = [vp, i64p, i64p, i64p, i64p, f64p, i64p, i64p, f64p]
     L.blu_solve_dense.argtypes = [vp, f64p, f64p, ctypes.c_char]
     L.blu_solve_dense_multi.argtypes = [vp, ctypes.c_int64, f64p, f64p, ctypes.c_char]
+    L.blu_solve_sparse_multi.argtypes = [vp, ctypes.c_int64, i64p, i64p, f64p, i64p, i64p, f64p, i32p, ctypes.c_char]
     L.blu_solve_sparse.argtypes = [vp, ctypes.c_int64, i64p, f64p, i64p, i64p, f64p, ctypes.c_char]
     L.blu_solve_for_update.argtypes = [vp, ctypes.c_int64, i64p, f64p, i64p, i64p, f64p, ctypes.c_char]
     L.blu_update.argtypes = [vp, ctypes.c_double]
@@ -208,6 +209,27 @@ class BLU(_Base):
         x = np.zeros_like(r)
         st = self._L.blu_solve_dense_multi(self._h, r.shape[0], _pf(r), _pf(x), _ch(trans))
         return st, x
+
+    def solve_sparse_multi(self, rhs_list, trans="N"):
+        """rhs_list = [(irhs, xrhs), ...] -> (status, [(ilhs, values), ...]): solve_sparse for each, all in
+        flight together; entry n of a result is lhs[ilhs[n]] = values[n], in solve_sparse's order."""
+        n = len(rhs_list)
+        begin = np.zeros(n + 1, dtype=np.int64)
+        for r, (ii, _) in enumerate(rhs_list):
+            begin[r + 1] = begin[r] + len(ii)
+        irhs = _i64(np.concatenate([np.asarray(ii, dtype=np.int64) for ii, _ in rhs_list])) if n else np.zeros(0, np.int64)
+        xrhs = _f64(np.concatenate([np.asarray(xx, dtype=np.float64) for _, xx in rhs_list])) if n else np.zeros(0)
+        nz = np.zeros(n, dtype=np.int64)
+        il = np.zeros(n * self.m, dtype=np.int64)
+        xl = np.zeros(n * self.m)
+        stat = np.zeros(n, dtype=np.int32)
+        st = self._L.blu_solve_sparse_multi(self._h, n, _pi(begin), _pi(irhs), _pf(xrhs), _pi(nz), _pi(il), _pf(xl),
+                                            stat.ctypes.data_as(i32p), _ch(trans))
+        out = []
+        for r in range(n):
+            k = max(int(nz[r]), 0)
+            out.append((il[r * self.m:r * self.m + k].copy(), xl[r * self.m:r * self.m + k].copy()))
+        return st, out, stat
 
     # blu.rs:207: result in self.lhs / self.ilhs / self.nzlhs
     def solve_sparse(self, nzrhs, irhs, xrhs, trans="N"):

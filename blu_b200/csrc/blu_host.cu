@@ -43,6 +43,8 @@ struct blu_b200 {
     int64_t *d_irhs; double *d_xrhs; int64_t *d_ilhs; double *d_xout; int *d_scal;
     int *h_scal; int64_t *h_ilhs; double *h_xout;   /* pinned */
     double *dm_rhs, *dm_lhs, *dm_work; int *dm_status; int64_t multi_cap;   /* blu_solve_dense_multi staging */
+    int *sm_ints, *sm_markers, *sm_scal; double *sm_dbls, *sm_xout; int64_t *sm_ilhs, *sm_begin; int64_t smulti_cap;   /* blu_solve_sparse_multi */
+    int64_t *sm_irhs; double *sm_xrhs; int64_t smulti_rhs_cap;
     int info_dirty;             /* device info block is newer than hinfo */
     int norms;                  /* run condest/residual_test after every factorization (factorize.rs:121-147) */
     cudaStream_t copy_stream, chunk_stream[4]; cudaEvent_t ev_up[16], ev_ch[4]; int have_pipe;   /* pipelined upload (blu_batch_factorize) */
@@ -120,6 +122,8 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     o->have_b = 0; o->info_dirty = 0; o->norms = 1; o->last_norms_ms = 0.0;
     o->have_pipe = 0; o->d_chunk_end = nullptr; o->h_chunk_end = nullptr;
     o->dm_rhs = o->dm_lhs = o->dm_work = nullptr; o->dm_status = nullptr; o->multi_cap = 0;
+    o->sm_ints = o->sm_markers = o->sm_scal = nullptr; o->sm_dbls = o->sm_xout = nullptr; o->sm_ilhs = o->sm_begin = nullptr; o->smulti_cap = 0;
+    o->sm_irhs = nullptr; o->sm_xrhs = nullptr; o->smulti_rhs_cap = 0;
     o->h_scal = nullptr; o->h_ilhs = nullptr; o->h_xout = nullptr;
     o->time_factorize = o->time_solve = o->time_update = 0.0;
     BluDev &d = o->d;
@@ -841,7 +845,7 @@ static int sparse_call(blu_b200 *o, int64_t nzrhs, const int64_t *irhs, const do
     int status = BLU_ERROR_INTERNAL, nz = 0;
     for (int attempt = 0; attempt < 40; attempt++) {
         BLU_LAUNCH(k_solve_sparse, 1, 32, 0, o->stream, o->d, nrhs, (const i64 *)o->d_irhs, dx, trans, for_update, want,
-                   o->d_scal, (i64 *)o->d_ilhs, o->d_xout);
+                   o->d_scal, (i64 *)o->d_ilhs, o->d_xout, SpMulti{0, nullptr, nullptr, nullptr, nullptr});
         o->launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(o->h_scal, o->d_scal, 2 * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
@@ -924,6 +928,8 @@ extern "C" int blu_solve_dense_multi(blu_t *o, int64_t nrhs, const double *rhs, 
     if ((int64_t)n > o->multi_cap) {
         dfree(o, o->dm_rhs); dfree(o, o->dm_lhs); dfree(o, o->dm_work); dfree(o, o->dm_status);
         o->dm_rhs = o->dm_lhs = o->dm_work = nullptr; o->dm_status = nullptr; o->multi_cap = 0;
+    o->sm_ints = o->sm_markers = o->sm_scal = nullptr; o->sm_dbls = o->sm_xout = nullptr; o->sm_ilhs = o->sm_begin = nullptr; o->smulti_cap = 0;
+    o->sm_irhs = nullptr; o->sm_xrhs = nullptr; o->smulti_rhs_cap = 0;
         int st = dalloc(o, &o->dm_rhs, n * m);
         if (st == BLU_OK) st = dalloc(o, &o->dm_lhs, n * m);
         if (st == BLU_OK) st = dalloc(o, &o->dm_work, n * m);
@@ -946,3 +952,68 @@ extern "C" int blu_solve_dense_multi(blu_t *o, int64_t nrhs, const double *rhs, 
     return BLU_OK;
 }
 
+/* Many sparse right-hand sides against one factorization: solve_sparse (solve_sparse.rs:35) for each of
+ * them, one warp per right-hand side, all in flight together; every unit has its own marks, stacks and
+ * vectors, the factors are only read.  Right-hand side r is irhs/xrhs[rhs_begin[r] .. rhs_begin[r+1]).
+ * Results: nzlhs[r] entries (-1 if that right-hand side was rejected, status[r] says why), indices in
+ * ilhs[r*m ..] in the same order as blu_solve_sparse returns them, and their VALUES compacted in
+ * xlhs[r*m + n] (value of entry ilhs[r*m + n]).  Bit-identical to nrhs separate blu_solve_sparse calls. */
+extern "C" int blu_solve_sparse_multi(blu_t *o, int64_t nrhs, const int64_t *rhs_begin, const int64_t *irhs, const double *xrhs,
+                                      int64_t *nzlhs, int64_t *ilhs, double *xlhs, int *status, char trans) {
+    if (!o || !o->single || nrhs < 0 || (nrhs > 0 && (!rhs_begin || !nzlhs || !ilhs || !xlhs))) return BLU_ERROR_INVALID_ARGUMENT;
+    { int st0 = ensure_info(o); if (st0 != BLU_OK) return st0; }
+    if (o->hinfo[0].nupdate < 0) return BLU_ERROR_INVALID_CALL;   /* solve_sparse.rs:42 */
+    if (nrhs == 0) return BLU_OK;
+    CK(cudaSetDevice(o->device));
+    const double tic = wall_now();
+    const size_t m = (size_t)o->d.m, n = (size_t)nrhs;
+    const int64_t tot = rhs_begin[nrhs];
+    if (tot < 0 || (tot > 0 && (!irhs || !xrhs))) return BLU_ERROR_INVALID_ARGUMENT;
+    int st = BLU_OK;
+    if ((int64_t)n > o->smulti_cap) {
+        dfree(o, o->sm_ints); dfree(o, o->sm_dbls); dfree(o, o->sm_markers); dfree(o, o->sm_scal); dfree(o, o->sm_xout); dfree(o, o->sm_ilhs); dfree(o, o->sm_begin);
+        o->sm_ints = o->sm_markers = o->sm_scal = nullptr; o->sm_dbls = o->sm_xout = nullptr; o->sm_ilhs = o->sm_begin = nullptr; o->smulti_cap = 0;
+        st = dalloc(o, &o->sm_ints, n * 7 * m);
+        if (st == BLU_OK) st = dalloc(o, &o->sm_dbls, n * 2 * m);
+        if (st == BLU_OK) st = dalloc(o, &o->sm_markers, n);
+        if (st == BLU_OK) st = dalloc(o, &o->sm_scal, 2 * n);
+        if (st == BLU_OK) st = dalloc(o, &o->sm_xout, n * m);
+        if (st == BLU_OK) st = dalloc(o, &o->sm_ilhs, n * m);
+        if (st == BLU_OK) st = dalloc(o, &o->sm_begin, n + 1);
+        if (st != BLU_OK) return st;
+        o->smulti_cap = (int64_t)n;
+    }
+    if (tot > o->smulti_rhs_cap) {
+        dfree(o, o->sm_irhs); dfree(o, o->sm_xrhs); o->sm_irhs = nullptr; o->sm_xrhs = nullptr; o->smulti_rhs_cap = 0;
+        st = dalloc(o, &o->sm_irhs, (size_t)tot);
+        if (st == BLU_OK) st = dalloc(o, &o->sm_xrhs, (size_t)tot);
+        if (st != BLU_OK) return st;
+        o->smulti_rhs_cap = tot;
+    }
+    CK(cudaMemcpyAsync(o->sm_begin, rhs_begin, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
+    if (tot > 0) {
+        CK(cudaMemcpyAsync(o->sm_irhs, irhs, (size_t)tot * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
+        CK(cudaMemcpyAsync(o->sm_xrhs, xrhs, (size_t)tot * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+    }
+    BLU_LAUNCH(k_garbage_perm, 1, 32, 0, o->stream, o->d);
+    SpMulti W{(int)nrhs, o->sm_ints, o->sm_dbls, o->sm_markers, (const i64 *)o->sm_begin};
+    BLU_LAUNCH(k_solve_sparse, (int)nrhs, 32, 0, o->stream, o->d, 0, (const i64 *)o->sm_irhs, (const double *)o->sm_xrhs, trans, 0, 1,
+               o->sm_scal, (i64 *)o->sm_ilhs, o->sm_xout, W);
+    o->launches += 2;
+    CK(cudaGetLastError());
+    std::vector<int> hs(2 * n);
+    CK(cudaMemcpyAsync(hs.data(), o->sm_scal, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+    CK(cudaMemcpyAsync(ilhs, o->sm_ilhs, n * m * sizeof(int64_t), cudaMemcpyDeviceToHost, o->stream));
+    CK(cudaMemcpyAsync(xlhs, o->sm_xout, n * m * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+    CK(cudaStreamSynchronize(o->stream));
+    int worst = BLU_OK;
+    for (size_t r = 0; r < n; r++) {
+        const int s = hs[2 * r];
+        if (status) status[r] = s;
+        nzlhs[r] = s == BLU_OK ? hs[2 * r + 1] : -1;
+        if (s != BLU_OK && worst == BLU_OK) worst = s;
+    }
+    o->info_dirty = 1;
+    o->time_solve += wall_now() - tic;
+    return worst;
+}

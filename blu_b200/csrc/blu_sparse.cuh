@@ -35,6 +35,7 @@ struct SpCtx {
     Mat M;
     int m, status;
     int *pattern_symb, *pattern, *marked, *pstack, *pend, *irhs, *ilhs;
+    int *marker_ptr;          /* the marker counter that goes with `marked` (the object's, or this unit's in a multi-RHS call) */
     double *work, *xlhs;
     i64 l_flops, u_flops, r_flops;
 };
@@ -249,7 +250,7 @@ __device__ int sp_solve_triangular(int nz_symb, const int *pattern_symb, const i
 __device__ __forceinline__ int sp_next_marker(SpCtx &C) {
     int mk = 0;
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mk = ++C.M.info->marker;
+    if ((threadIdx.x & 31) == 0) mk = ++*C.marker_ptr;
     mk = sp_bcast(mk);
     return mk;
 }
@@ -445,10 +446,38 @@ __device__ __forceinline__ void sp_ctx_init(SpCtx &C, const BluDev &D) {
     C.pattern_symb = M.iwork1; C.pattern = M.iwork1 + M.m;
     C.marked = M.marked; C.pstack = M.pstack; C.pend = M.tmpi + M.m; C.irhs = M.acols; C.ilhs = M.tmpi;
     C.work = M.work0; C.xlhs = M.gwork;
+    C.marker_ptr = &M.info->marker;
     C.l_flops = C.u_flops = C.r_flops = 0;
 }
 
 /* lu/solve_sparse.rs:356-358 and the update-cost model (lu.rs:321-326) */
+/* Workspace of blu_solve_sparse_multi: every right-hand side (unit) has its own marks, stacks, patterns
+ * and the two scattered vectors, so that all units run at once against the same (read-only) factors. */
+struct SpMulti {
+    int nunits;               /* 0: single call */
+    int *ints;                /* nunits * 7m : marked | pattern_symb | pattern | pstack | ilhs | pend | irhs */
+    double *dbls;             /* nunits * 2m : work | xlhs  (all-zero between calls) */
+    int *markers;             /* nunits */
+    const i64 *rhs_begin;     /* nunits + 1 offsets into irhs64 / xrhs */
+};
+__device__ __forceinline__ void sp_ctx_init_unit(SpCtx &C, const BluDev &D, const SpMulti &W, int u) {
+    mat_view(C.M, D, 0);
+    const size_t m = (size_t)C.M.m;
+    C.m = C.M.m; C.status = BLU_OK;
+    int *ib = W.ints + (size_t)u * 7 * m;
+    C.marked = ib; C.pattern_symb = ib + m; C.pattern = ib + 2 * m; C.pstack = ib + 3 * m;
+    C.ilhs = ib + 4 * m; C.pend = ib + 5 * m; C.irhs = ib + 6 * m;
+    C.work = W.dbls + (size_t)u * 2 * m; C.xlhs = C.work + m;
+    C.marker_ptr = W.markers + u;
+    C.l_flops = C.u_flops = C.r_flops = 0;
+}
+__device__ __forceinline__ void sp_solve_done_atomic(SpCtx &C) {
+    BluInfo *I = C.M.info;
+    atomicAdd((unsigned long long *)&I->l_flops, (unsigned long long)C.l_flops);
+    atomicAdd((unsigned long long *)&I->u_flops, (unsigned long long)C.u_flops);
+    atomicAdd((unsigned long long *)&I->r_flops, (unsigned long long)C.r_flops);
+    atomicAdd(&I->update_cost_numer, (double)C.r_flops);
+}
 __device__ __forceinline__ void sp_solve_done(SpCtx &C) {
     BluInfo *I = C.M.info;
     I->l_flops += C.l_flops; I->u_flops += C.u_flops; I->r_flops += C.r_flops;
@@ -459,10 +488,20 @@ __device__ __forceinline__ void sp_solve_done(SpCtx &C) {
  * (solve_for_update.rs:72-119 + lu/solve_for_update.rs:12-455).
  * scal[0] = status, scal[1] = nzlhs.  The solution leaves compacted: ilhs_out[n], xout[n]. */
 __global__ void __launch_bounds__(32) k_solve_sparse(BluDev D, int nrhs, const i64 *irhs64, const double *xrhs, char trans,
-                                                      int for_update, int want_solution, int *scal, i64 *ilhs_out, double *xout) {
+                                                      int for_update, int want_solution, int *scal, i64 *ilhs_out, double *xout,
+                                                      SpMulti W) {
     __shared__ SpCtx C;
     const int lane = threadIdx.x & 31;
-    if (lane == 0) sp_ctx_init(C, D);
+    const bool multi = W.nunits > 0;
+    if (multi) {
+        /* unit = blockIdx.x: its slice of the right-hand sides and of the outputs */
+        const int u = blockIdx.x;
+        const i64 b = W.rhs_begin[u], e = W.rhs_begin[u + 1];
+        irhs64 += b; xrhs += b;
+        nrhs = (e - b < 0 || e - b > 0x7fffffff) ? -1 : (int)(e - b);
+        scal += 2 * u; ilhs_out += (size_t)u * D.m; xout += (size_t)u * D.m;
+        if (lane == 0) sp_ctx_init_unit(C, D, W, u);
+    } else if (lane == 0) sp_ctx_init(C, D);
     __syncwarp();
     Mat &M = C.M;
     BluInfo *I = M.info;
@@ -482,7 +521,7 @@ __global__ void __launch_bounds__(32) k_solve_sparse(BluDev D, int nrhs, const i
     }
     if (st != BLU_OK) { if (lane == 0) { scal[0] = st; scal[1] = 0; } return; }
     for (int n = lane; n < nrhs; n += 32) C.irhs[n] = (int)irhs64[n];
-    if (lane == 0) I->addmem_l = I->addmem_u = I->addmem_w = 0;
+    if (lane == 0 && !multi) I->addmem_l = I->addmem_u = I->addmem_w = 0;
     __syncwarp();
 
     int nz = 0;
@@ -597,7 +636,7 @@ __global__ void __launch_bounds__(32) k_solve_sparse(BluDev D, int nrhs, const i
         xout[n] = C.xlhs[j];
         C.xlhs[j] = 0.0;
     }
-    if (lane == 0) { sp_solve_done(C); scal[0] = C.status; scal[1] = nz; }
+    if (lane == 0) { if (multi) sp_solve_done_atomic(C); else sp_solve_done(C); scal[0] = C.status; scal[1] = nz; }
 }
 
 /* ------------------------------------------------------------------ */

@@ -90,6 +90,14 @@ int blu_solve_dense(blu_t *o, const double *rhs, double *lhs, char trans);
  * length m back to back; the result is bit-identical to nrhs calls of blu_solve_dense. */
 int blu_solve_dense_multi(blu_t *o, int64_t nrhs, const double *rhs, double *lhs, char trans);
 
+/* Many sparse right-hand sides against one factorization: right-hand side r is
+ * irhs/xrhs[rhs_begin[r] .. rhs_begin[r+1]).  For every r: nzlhs[r] (or -1 and status[r], which may be NULL),
+ * the pattern ilhs[r*m .. r*m+nzlhs[r]) in the order blu_solve_sparse returns it, and the VALUES of those
+ * entries compacted in xlhs[r*m + n].  Bit-identical to nrhs calls of blu_solve_sparse; returns the first
+ * non-OK status. */
+int blu_solve_sparse_multi(blu_t *o, int64_t nrhs, const int64_t *rhs_begin, const int64_t *irhs, const double *xrhs,
+                           int64_t *nzlhs, int64_t *ilhs, double *xlhs, int *status, char trans);
+
 /* BLU::solve_sparse, blu.rs:207-230 -> solve_sparse.rs:35.  The result is returned like
  * BLU.lhs / ilhs / nzlhs: lhs[m] scattered (zero elsewhere), ilhs[0..*nzlhs) its pattern. */
 int blu_solve_sparse(blu_t *o, int64_t nzrhs, const int64_t *irhs, const double *xrhs,

@@ -133,6 +133,19 @@ def c4(args):
     rec["solve_dense_multi"] = {"nrhs": nrhs, "gpu_ms_total": 1e3 * tm, "gpu_ms_per_rhs": 1e3 * tm / nrhs,
                                 "cpu_oracle_ms_per_rhs": 1e3 * tcs / ns, "bit_identical_to_oracle_solve_dense": bool(same_multi),
                                 "note": "one warp per right-hand side, all in flight; includes H2D of rhs and D2H of the solutions"}
+    # and through the multi-RHS SPARSE solve: the Gilbert-Peierls solve of every right-hand side, one warp each
+    rl = [gen.sparse_rhs_np(6000 + r, m, nz) for r in range(nrhs)]
+    g.solve_sparse_multi(rl[:8], "N")
+    (ssm, outm, statm), tsm = wall(lambda: g.solve_sparse_multi(rl, "N"))
+    same_sm = ssm == 0
+    tco = 0.0
+    for r in range(ns):
+        _, dt = wall(lambda: o.solve_sparse(nz, rl[r][0], rl[r][1], "N")); tco += dt
+        n_ = o.nzlhs
+        same_sm = same_sm and len(outm[r][0]) == n_ and np.array_equal(outm[r][0], o.ilhs[:n_]) and np.array_equal(outm[r][1], o.lhs[o.ilhs[:n_]])
+    rec["solve_sparse_multi"] = {"nrhs": nrhs, "gpu_ms_total": 1e3 * tsm, "gpu_ms_per_rhs": 1e3 * tsm / nrhs,
+                                 "cpu_oracle_ms_per_rhs": 1e3 * tco / ns, "bit_identical_pattern_order_and_values": bool(same_sm),
+                                 "note": "blu_solve_sparse_multi: one warp per right-hand side, all in flight; H2D/D2H included"}
     rec["solve_sparse"] = {"calls": nrhs, "nzrhs": nz, "avg_nzlhs": nzl / nrhs, "gpu_ms_per_call": 1e3 * tg / nrhs,
                            "cpu_oracle_ms_per_call": 1e3 * to / nrhs, "bit_identical_pattern_order_and_values": bool(same),
                            "bound": "latency (one warp; DFS on one lane)"}

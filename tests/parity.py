@@ -157,3 +157,24 @@ def assert_maxvolume_parity(g, o, m, ncol, seed, volumetol=1.0):
         _, xg = g.solve_dense(b, tr)
         assert np.array_equal(xg, xo), tr
     return no
+
+
+def assert_sparse_multi_parity(g, o, m, seed, sizes=(1, 3, 17, 60), reps=3):
+    """blu_solve_sparse_multi == that many solve_sparse calls (pattern order and values bit-exact)."""
+    from blu_b200 import gen
+    for tr in "NT":
+        rhs = []
+        for rep in range(reps):
+            for k, nz in enumerate(sizes):
+                rhs.append(gen.sparse_rhs(seed + 10 * rep + k, m, min(nz, m)))
+        st, out, stat = g.solve_sparse_multi(rhs, tr)
+        assert st == 0 and (stat == 0).all()
+        for (idx, val), (il, xl) in zip(rhs, out):
+            assert o.solve_sparse(len(idx), idx, val, tr) == 0
+            n = o.nzlhs
+            assert len(il) == n and np.array_equal(il, o.ilhs[:n]), "pattern order"
+            assert np.array_equal(xl, o.lhs[o.ilhs[:n]]), "values"
+    # a bad right-hand side is reported for that unit only
+    st, out, stat = g.solve_sparse_multi([(np.array([0]), np.array([1.0])), (np.array([m]), np.array([1.0]))], "N")
+    assert st == -4 and list(stat) == [0, -4] and len(out[1][0]) == 0
+    assert o.solve_sparse(1, np.array([0]), np.array([1.0]), "N") == 0      # keep the flop counters of both sides in step

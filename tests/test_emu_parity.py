@@ -206,3 +206,15 @@ def test_emu_solve_dense_multi(emu):
             assert np.array_equal(X[k], xo), (tr, k)
     g2 = BLU(m, len(v), lib=emu)
     assert g2.solve_dense_multi(R, "N")[0] == -2          # never factorized
+
+
+def test_emu_solve_sparse_multi(emu):
+    from parity import assert_sparse_multi_parity, replay_updates
+    m = 140
+    cp, ri, v = gen.basis(88, m, 40, 4.0)
+    g, o, st = pair(emu, cp, ri, v, m, 64)
+    assert st == 0
+    assert_sparse_multi_parity(g, o, m, 1500)
+    # also after updates (etas, permuted pivots): the factors are still only read
+    replay_updates(g, o, m, gen.basis(89, m, 0, 3.0), 8)
+    assert_sparse_multi_parity(g, o, m, 1600, sizes=(2, 25), reps=2)

@@ -432,3 +432,16 @@ def test_solve_dense_multi():
             _, xo = o.solve_dense(R[k], tr)
             assert np.array_equal(X[k], xo), (tr, k)
     assert BLU(m, 10).solve_dense_multi(R[:2], "N")[0] == -2
+
+
+def test_solve_sparse_multi():
+    """Many sparse right-hand sides against one factorization (one warp each): pattern order and values
+    bit-identical to separate solve_sparse calls, before and after updates."""
+    from parity import assert_sparse_multi_parity, replay_updates
+    m = 1000
+    (cp, ri, v), _ = gen.config1()
+    g, o, st = run_pair(cp, ri, v, m)
+    assert st == 0
+    assert_sparse_multi_parity(g, o, m, 1500, sizes=(1, 5, 40, 300), reps=8)
+    replay_updates(g, o, m, gen.basis(89, m, 0, 3.0), 10, check_dense=False)
+    assert_sparse_multi_parity(g, o, m, 1600, sizes=(2, 60), reps=4)
