@@ -78,6 +78,8 @@ def load_library(path=None):
     L.blu_batch_destroy.argtypes = [vp]
     L.blu_batch_factorize.argtypes = [vp, i64p, i64p, i64p, f64p, ctypes.c_int64, i32p]
     L.blu_batch_solve_dense.argtypes = [vp, f64p, f64p, ctypes.c_char, i32p]
+    L.blu_batch_solve_for_update.argtypes = [vp, i64p, i64p, f64p, ctypes.c_int, i64p, i64p, f64p, i32p, ctypes.c_char]
+    L.blu_batch_update.argtypes = [vp, f64p, i32p]
     L.blu_batch_get_info.argtypes = [vp, ctypes.c_int64, ctypes.c_int]; L.blu_batch_get_info.restype = ctypes.c_double
     L.blu_batch_get_factors.argtypes = [vp, ctypes.c_int64, i64p, i64p, i64p, i64p, f64p, i64p, i64p, f64p]
     L.blu_batch_upload.argtypes = [vp, i64p, i64p, i64p, f64p, ctypes.c_int64, f64p]
@@ -298,6 +300,32 @@ class BLUBatch(_Base):
         status = np.zeros(self.nmat, dtype=np.int32)
         st = self._L.blu_batch_solve_dense(self._h, _pf(r), _pf(x), _ch(trans), status.ctypes.data_as(i32p))
         return st, x.reshape(self.nmat, self.m), status
+
+    def solve_for_update(self, rhs_list, trans="N", want_solution=0):
+        """rhs_list[k] = (irhs, xrhs or None) for basis k -> (status, per-basis status, [(ilhs, values)] or None)"""
+        n = self.nmat
+        begin = np.zeros(n + 1, dtype=np.int64)
+        for k, (ii, _) in enumerate(rhs_list):
+            begin[k + 1] = begin[k] + len(ii)
+        irhs = _i64(np.concatenate([np.asarray(ii, dtype=np.int64).reshape(-1) for ii, _ in rhs_list]))
+        have_x = rhs_list[0][1] is not None
+        xrhs = _f64(np.concatenate([np.asarray(xx, dtype=np.float64) for _, xx in rhs_list])) if have_x else None
+        stat = np.zeros(n, dtype=np.int32)
+        if want_solution:
+            nz = np.zeros(n, dtype=np.int64); il = np.zeros(n * self.m, dtype=np.int64); xl = np.zeros(n * self.m)
+            st = self._L.blu_batch_solve_for_update(self._h, _pi(begin), _pi(irhs), _pf(xrhs), 1, _pi(nz), _pi(il), _pf(xl),
+                                                    stat.ctypes.data_as(i32p), _ch(trans))
+            out = [(il[k * self.m:k * self.m + max(int(nz[k]), 0)].copy(), xl[k * self.m:k * self.m + max(int(nz[k]), 0)].copy()) for k in range(n)]
+            return st, stat, out
+        st = self._L.blu_batch_solve_for_update(self._h, _pi(begin), _pi(irhs), _pf(xrhs), 0, None, None, None,
+                                                stat.ctypes.data_as(i32p), _ch(trans))
+        return st, stat, None
+
+    def update(self, xtbl):
+        x = _f64(xtbl)
+        stat = np.zeros(self.nmat, dtype=np.int32)
+        st = self._L.blu_batch_update(self._h, _pf(x), stat.ctypes.data_as(i32p))
+        return st, stat
 
     def get_factors(self, k):
         m = self.m

@@ -845,7 +845,7 @@ static int sparse_call(blu_b200 *o, int64_t nzrhs, const int64_t *irhs, const do
     int status = BLU_ERROR_INTERNAL, nz = 0;
     for (int attempt = 0; attempt < 40; attempt++) {
         BLU_LAUNCH(k_solve_sparse, 1, 32, 0, o->stream, o->d, nrhs, (const i64 *)o->d_irhs, dx, trans, for_update, want,
-                   o->d_scal, (i64 *)o->d_ilhs, o->d_xout, SpMulti{0, nullptr, nullptr, nullptr, nullptr});
+                   o->d_scal, (i64 *)o->d_ilhs, o->d_xout, SpMulti{0, 0, nullptr, nullptr, nullptr, nullptr});
         o->launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(o->h_scal, o->d_scal, 2 * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
@@ -892,7 +892,7 @@ extern "C" int blu_update(blu_t *o, double xtbl) {
     const double tic = wall_now();
     int status = BLU_ERROR_INTERNAL;
     for (int attempt = 0; attempt < 40; attempt++) {
-        BLU_LAUNCH(k_update, 1, 32, 0, o->stream, o->d, xtbl, o->d_scal);
+        BLU_LAUNCH(k_update, 1, 32, 0, o->stream, o->d, xtbl, o->d_scal, (const double *)nullptr);
         o->launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(o->h_scal, o->d_scal, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
@@ -996,7 +996,7 @@ extern "C" int blu_solve_sparse_multi(blu_t *o, int64_t nrhs, const int64_t *rhs
         CK(cudaMemcpyAsync(o->sm_xrhs, xrhs, (size_t)tot * sizeof(double), cudaMemcpyHostToDevice, o->stream));
     }
     BLU_LAUNCH(k_garbage_perm, 1, 32, 0, o->stream, o->d);
-    SpMulti W{(int)nrhs, o->sm_ints, o->sm_dbls, o->sm_markers, (const i64 *)o->sm_begin};
+    SpMulti W{(int)nrhs, 0, o->sm_ints, o->sm_dbls, o->sm_markers, (const i64 *)o->sm_begin};
     BLU_LAUNCH(k_solve_sparse, (int)nrhs, 32, 0, o->stream, o->d, 0, (const i64 *)o->sm_irhs, (const double *)o->sm_xrhs, trans, 0, 1,
                o->sm_scal, (i64 *)o->sm_ilhs, o->sm_xout, W);
     o->launches += 2;
@@ -1015,5 +1015,96 @@ extern "C" int blu_solve_sparse_multi(blu_t *o, int64_t nrhs, const int64_t *rhs
     }
     o->info_dirty = 1;
     o->time_solve += wall_now() - tic;
+    return worst;
+}
+
+/* ------------------------------------------------------------------ */
+/* batch: one basis change on every basis at once (multi-LP sweeps)    */
+/* ------------------------------------------------------------------ */
+static int ensure_batch_sparse(blu_b200 *o, int64_t tot) {
+    const size_t n = (size_t)o->d.nmat, m = (size_t)o->d.m;
+    int st = BLU_OK;
+    if (!o->sm_scal) {
+        st = dalloc(o, &o->sm_scal, 2 * n);
+        if (st == BLU_OK) st = dalloc(o, &o->sm_xout, n * m);
+        if (st == BLU_OK) st = dalloc(o, &o->sm_ilhs, n * m);
+        if (st == BLU_OK) st = dalloc(o, &o->sm_begin, n + 1);
+        if (st == BLU_OK) st = dalloc(o, &o->sm_dbls, n);          /* xtbl per basis */
+        if (st != BLU_OK) return st;
+    }
+    if (tot > o->smulti_rhs_cap) {
+        dfree(o, o->sm_irhs); dfree(o, o->sm_xrhs); o->sm_irhs = nullptr; o->sm_xrhs = nullptr; o->smulti_rhs_cap = 0;
+        st = dalloc(o, &o->sm_irhs, (size_t)tot);
+        if (st == BLU_OK) st = dalloc(o, &o->sm_xrhs, (size_t)tot);
+        if (st != BLU_OK) return st;
+        o->smulti_rhs_cap = tot;
+    }
+    return BLU_OK;
+}
+
+/* solve_for_update (blu.rs:257) on every basis of the batch, basis k with its own right-hand side
+ * irhs/xrhs[rhs_begin[k] .. rhs_begin[k+1]) (for trans 't'/'T': one index, the column to leave; xrhs may be
+ * NULL).  want_solution != 0: nzlhs[k], ilhs[k*m ..] and the values xlhs[k*m + n] as in
+ * blu_solve_sparse_multi.  The L/U/W stores are NOT grown in a batch: a basis that runs out of room gets
+ * status[k] = BLU_ERROR_OUT_OF_MEMORY and is left unchanged (size the stores with BLU_P_*_MEM). */
+extern "C" int blu_batch_solve_for_update(blu_batch_t *o, const int64_t *rhs_begin, const int64_t *irhs, const double *xrhs,
+                                          int want_solution, int64_t *nzlhs, int64_t *ilhs, double *xlhs, int *status, char trans) {
+    if (!o || !rhs_begin || !irhs) return BLU_ERROR_INVALID_ARGUMENT;
+    if (want_solution && (!nzlhs || !ilhs || !xlhs)) return BLU_ERROR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(o->device));
+    const size_t n = (size_t)o->d.nmat, m = (size_t)o->d.m;
+    const int64_t tot = rhs_begin[n];
+    if (tot < 0) return BLU_ERROR_INVALID_ARGUMENT;
+    int st = ensure_batch_sparse(o, tot);
+    if (st != BLU_OK) return st;
+    CK(cudaMemcpyAsync(o->sm_begin, rhs_begin, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
+    CK(cudaMemcpyAsync(o->sm_irhs, irhs, (size_t)tot * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
+    if (xrhs) CK(cudaMemcpyAsync(o->sm_xrhs, xrhs, (size_t)tot * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+    SpMulti W{(int)n, 1, nullptr, nullptr, nullptr, (const i64 *)o->sm_begin};
+    BLU_LAUNCH(k_solve_sparse, (int)n, 32, 0, o->stream, o->d, 0, (const i64 *)o->sm_irhs, xrhs ? (const double *)o->sm_xrhs : (const double *)nullptr,
+               trans, 1, want_solution ? 1 : 0, o->sm_scal, (i64 *)o->sm_ilhs, o->sm_xout, W);
+    o->launches++;
+    CK(cudaGetLastError());
+    std::vector<int> hs(2 * n);
+    CK(cudaMemcpyAsync(hs.data(), o->sm_scal, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+    if (want_solution) {
+        CK(cudaMemcpyAsync(ilhs, o->sm_ilhs, n * m * sizeof(int64_t), cudaMemcpyDeviceToHost, o->stream));
+        CK(cudaMemcpyAsync(xlhs, o->sm_xout, n * m * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+    }
+    CK(cudaStreamSynchronize(o->stream));
+    int worst = BLU_OK;
+    for (size_t k = 0; k < n; k++) {
+        int s = hs[2 * k];
+        if (s == BLU_REALLOCATE) s = BLU_ERROR_OUT_OF_MEMORY;
+        if (status) status[k] = s;
+        if (want_solution) nzlhs[k] = s == BLU_OK ? hs[2 * k + 1] : -1;
+        if (s != BLU_OK && worst == BLU_OK) worst = s;
+    }
+    o->info_dirty = 1;
+    return worst;
+}
+
+/* update (blu.rs:319) on every basis of the batch, basis k with xtbl[k] */
+extern "C" int blu_batch_update(blu_batch_t *o, const double *xtbl, int *status) {
+    if (!o || !xtbl) return BLU_ERROR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(o->device));
+    const size_t n = (size_t)o->d.nmat;
+    int st = ensure_batch_sparse(o, 0);
+    if (st != BLU_OK) return st;
+    CK(cudaMemcpyAsync(o->sm_dbls, xtbl, n * sizeof(double), cudaMemcpyHostToDevice, o->stream));
+    BLU_LAUNCH(k_update, (int)n, 32, 0, o->stream, o->d, 0.0, o->sm_scal, (const double *)o->sm_dbls);
+    o->launches++;
+    CK(cudaGetLastError());
+    std::vector<int> hs(n);
+    CK(cudaMemcpyAsync(hs.data(), o->sm_scal, n * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+    CK(cudaStreamSynchronize(o->stream));
+    int worst = BLU_OK;
+    for (size_t k = 0; k < n; k++) {
+        int s = hs[k];
+        if (s == BLU_REALLOCATE) s = BLU_ERROR_OUT_OF_MEMORY;
+        if (status) status[k] = s;
+        if (s != BLU_OK && worst == BLU_OK) worst = s;
+    }
+    o->info_dirty = 1;
     return worst;
 }

@@ -439,8 +439,8 @@ __device__ int sp_btran_tail(SpCtx &C, int nz, int marker) {
     return nz;
 }
 
-__device__ __forceinline__ void sp_ctx_init(SpCtx &C, const BluDev &D) {
-    mat_view(C.M, D, 0);
+__device__ __forceinline__ void sp_ctx_init(SpCtx &C, const BluDev &D, int slot = 0) {
+    mat_view(C.M, D, slot);
     Mat &M = C.M;
     C.m = M.m; C.status = BLU_OK;
     C.pattern_symb = M.iwork1; C.pattern = M.iwork1 + M.m;
@@ -455,6 +455,7 @@ __device__ __forceinline__ void sp_ctx_init(SpCtx &C, const BluDev &D) {
  * and the two scattered vectors, so that all units run at once against the same (read-only) factors. */
 struct SpMulti {
     int nunits;               /* 0: single call */
+    int per_slot;             /* 1: unit u works on basis (slot) u of a batch with that slot's own scratch; ints/dbls/markers unused */
     int *ints;                /* nunits * 7m : marked | pattern_symb | pattern | pstack | ilhs | pend | irhs */
     double *dbls;             /* nunits * 2m : work | xlhs  (all-zero between calls) */
     int *markers;             /* nunits */
@@ -492,15 +493,16 @@ __global__ void __launch_bounds__(32) k_solve_sparse(BluDev D, int nrhs, const i
                                                       SpMulti W) {
     __shared__ SpCtx C;
     const int lane = threadIdx.x & 31;
-    const bool multi = W.nunits > 0;
-    if (multi) {
+    const bool units = W.nunits > 0;
+    const bool multi = units && !W.per_slot;     /* several units share ONE basis: its state is read-only */
+    if (units) {
         /* unit = blockIdx.x: its slice of the right-hand sides and of the outputs */
         const int u = blockIdx.x;
         const i64 b = W.rhs_begin[u], e = W.rhs_begin[u + 1];
-        irhs64 += b; xrhs += b;
+        irhs64 += b; if (xrhs) xrhs += b;
         nrhs = (e - b < 0 || e - b > 0x7fffffff) ? -1 : (int)(e - b);
         scal += 2 * u; ilhs_out += (size_t)u * D.m; xout += (size_t)u * D.m;
-        if (lane == 0) sp_ctx_init_unit(C, D, W, u);
+        if (lane == 0) { if (W.per_slot) sp_ctx_init(C, D, u); else sp_ctx_init_unit(C, D, W, u); }
     } else if (lane == 0) sp_ctx_init(C, D);
     __syncwarp();
     Mat &M = C.M;
@@ -821,10 +823,13 @@ __device__ int sp_compress_packed(SpCtx &C) {
 }
 
 /* update.rs:49-55 + lu/update.rs:388-959.  scal[0] = status. */
-__global__ void __launch_bounds__(32) k_update(BluDev D, double xtbl, int *scal) {
+__global__ void __launch_bounds__(32) k_update(BluDev D, double xtbl, int *scal, const double *xtbl_per_slot) {
     __shared__ SpCtx C;
     const int lane = threadIdx.x & 31;
-    if (lane == 0) sp_ctx_init(C, D);
+    /* object API: one block, slot 0.  Batch: block u updates basis u with its own xtbl and status word. */
+    const int slot = xtbl_per_slot ? (int)blockIdx.x : 0;
+    if (xtbl_per_slot) { xtbl = xtbl_per_slot[slot]; scal += slot; }
+    if (lane == 0) sp_ctx_init(C, D, slot);
     __syncwarp();
     Mat &M = C.M;
     BluInfo *I = M.info;

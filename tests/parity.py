@@ -178,3 +178,28 @@ def assert_sparse_multi_parity(g, o, m, seed, sizes=(1, 3, 17, 60), reps=3):
     st, out, stat = g.solve_sparse_multi([(np.array([0]), np.array([1.0])), (np.array([m]), np.array([1.0]))], "N")
     assert st == -4 and list(stat) == [0, -4] and len(out[1][0]) == 0
     assert o.solve_sparse(1, np.array([0]), np.array([1.0]), "N") == 0      # keep the flop counters of both sides in step
+
+
+def batch_replay_parity(b, oracles, m, pools, niter):
+    """blu_batch_solve_for_update + blu_batch_update: every basis of the batch advances one column
+    replacement per round, in lockstep with one oracle per basis; everything observable must be identical."""
+    nmat = len(oracles)
+    for it in range(niter):
+        cols = [(pools[k][1][pools[k][0][it]:pools[k][0][it + 1]], pools[k][2][pools[k][0][it]:pools[k][0][it + 1]]) for k in range(nmat)]
+        st, stat, out = b.solve_for_update(cols, "N", want_solution=1)
+        assert st == 0 and (stat == 0).all(), (it, st, stat)
+        leave, xt = [], []
+        for k, o in enumerate(oracles):
+            assert o.solve_for_update(len(cols[k][0]), cols[k][0], cols[k][1], "N", want_solution=1) == 0
+            n = o.nzlhs
+            assert np.array_equal(out[k][0], o.ilhs[:n]) and np.array_equal(out[k][1], o.lhs[o.ilhs[:n]]), (it, k)
+            j = int(np.argmax(np.abs(o.lhs)))
+            leave.append((np.array([j]), None)); xt.append(o.lhs[j])
+        st, stat, _ = b.solve_for_update(leave, "T", want_solution=0)
+        assert st == 0 and (stat == 0).all()
+        st, stat = b.update(np.array(xt))
+        for k, o in enumerate(oracles):
+            assert o.solve_for_update(1, leave[k][0], None, "T", want_solution=0) == 0
+            assert o.update(xt[k]) == stat[k], (it, k, stat[k])
+            for name in ("nupdate", "nforrest", "u_nz", "r_nz", "pivot_error", "max_eta", "l_flops", "u_flops", "r_flops"):
+                assert b.info(k, name) == o.info(name), (it, k, name)

@@ -218,3 +218,26 @@ def test_emu_solve_sparse_multi(emu):
     # also after updates (etas, permuted pivots): the factors are still only read
     replay_updates(g, o, m, gen.basis(89, m, 0, 3.0), 8)
     assert_sparse_multi_parity(g, o, m, 1600, sizes=(2, 25), reps=2)
+
+
+def test_emu_batch_replay(emu):
+    """Many LPs advancing together: batch solve_for_update + update, one warp per basis."""
+    from parity import batch_replay_parity
+    nmat, m = 3, 70
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 25, 4.0, 9100, 9600)
+    b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()), lib=emu)
+    b.l_mem = 40000; b.u_mem = 40000; b.w_mem = 60000
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all()
+    oracles, pools = [], []
+    for k in range(nmat):
+        cp, ri, v = gen.basis(9100 + k, m, 25, 4.0)
+        o = oracle_for(m, len(v), 400)
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        oracles.append(o); pools.append(gen.basis(9700 + k, m, 0, 3.0))
+    batch_replay_parity(b, oracles, m, pools, 8)
+    st, x, sst = b.solve_dense(rhs, "N")
+    assert st == 0
+    for k, o in enumerate(oracles):
+        _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
+        assert np.array_equal(x[k], xo)

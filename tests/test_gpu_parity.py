@@ -445,3 +445,27 @@ def test_solve_sparse_multi():
     assert_sparse_multi_parity(g, o, m, 1500, sizes=(1, 5, 40, 300), reps=8)
     replay_updates(g, o, m, gen.basis(89, m, 0, 3.0), 10, check_dense=False)
     assert_sparse_multi_parity(g, o, m, 1600, sizes=(2, 60), reps=4)
+
+
+def test_batch_update_replay():
+    """Many LPs advancing together: blu_batch_solve_for_update + blu_batch_update (one warp per basis),
+    every basis in lockstep with its own oracle."""
+    from parity import batch_replay_parity
+    nmat, m = 48, 300
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 90, 4.0, 9100, 9600)
+    b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()))
+    b.l_mem = 200000; b.u_mem = 200000; b.w_mem = 300000
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all()
+    oracles, pools = [], []
+    for k in range(nmat):
+        cp, ri, v = gen.basis(9100 + k, m, 90, 4.0)
+        o = oracle_for(m, len(v), 400)
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        oracles.append(o); pools.append(gen.basis(9700 + k, m, 0, 3.0))
+    batch_replay_parity(b, oracles, m, pools, 12)
+    st, x, sst = b.solve_dense(rhs, "T")
+    assert st == 0
+    for k, o in enumerate(oracles):
+        _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "T")
+        assert np.array_equal(x[k], xo)
