@@ -845,7 +845,7 @@ static int sparse_call(blu_b200 *o, int64_t nzrhs, const int64_t *irhs, const do
     int status = BLU_ERROR_INTERNAL, nz = 0;
     for (int attempt = 0; attempt < 40; attempt++) {
         BLU_LAUNCH(k_solve_sparse, 1, 32, 0, o->stream, o->d, nrhs, (const i64 *)o->d_irhs, dx, trans, for_update, want,
-                   o->d_scal, (i64 *)o->d_ilhs, o->d_xout, SpMulti{0, 0, nullptr, nullptr, nullptr, nullptr});
+                   o->d_scal, (i64 *)o->d_ilhs, o->d_xout, SpMulti{0, 0, 0, nullptr, nullptr, nullptr, nullptr});
         o->launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(o->h_scal, o->d_scal, 2 * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
@@ -892,7 +892,7 @@ extern "C" int blu_update(blu_t *o, double xtbl) {
     const double tic = wall_now();
     int status = BLU_ERROR_INTERNAL;
     for (int attempt = 0; attempt < 40; attempt++) {
-        BLU_LAUNCH(k_update, 1, 32, 0, o->stream, o->d, xtbl, o->d_scal, (const double *)nullptr);
+        BLU_LAUNCH(k_update, 1, 32, 0, o->stream, o->d, xtbl, o->d_scal, (const double *)nullptr, 0);
         o->launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(o->h_scal, o->d_scal, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
@@ -996,7 +996,7 @@ extern "C" int blu_solve_sparse_multi(blu_t *o, int64_t nrhs, const int64_t *rhs
         CK(cudaMemcpyAsync(o->sm_xrhs, xrhs, (size_t)tot * sizeof(double), cudaMemcpyHostToDevice, o->stream));
     }
     BLU_LAUNCH(k_garbage_perm, 1, 32, 0, o->stream, o->d);
-    SpMulti W{(int)nrhs, 0, o->sm_ints, o->sm_dbls, o->sm_markers, (const i64 *)o->sm_begin};
+    SpMulti W{(int)nrhs, 0, 0, o->sm_ints, o->sm_dbls, o->sm_markers, (const i64 *)o->sm_begin};
     BLU_LAUNCH(k_solve_sparse, (int)nrhs, 32, 0, o->stream, o->d, 0, (const i64 *)o->sm_irhs, (const double *)o->sm_xrhs, trans, 0, 1,
                o->sm_scal, (i64 *)o->sm_ilhs, o->sm_xout, W);
     o->launches += 2;
@@ -1021,6 +1021,52 @@ extern "C" int blu_solve_sparse_multi(blu_t *o, int64_t nrhs, const int64_t *rhs
 /* ------------------------------------------------------------------ */
 /* batch: one basis change on every basis at once (multi-LP sweeps)    */
 /* ------------------------------------------------------------------ */
+
+/* lu_realloc_obj (blu.rs:345-377) for a batch: every basis gets the larger store, content kept */
+static int grow_batch_stores(blu_b200 *o) {
+    BluDev &d = o->d;
+    int st = fetch_info(o);
+    if (st != BLU_OK) return st;
+    int64_t al = 0, au = 0, aw = 0;
+    /* the kernels zero addmem_* on entry: only the bases that returned Reallocate carry a request */
+    for (auto &I : o->hinfo) { al = std::max<int64_t>(al, I.addmem_l); au = std::max<int64_t>(au, I.addmem_u); aw = std::max<int64_t>(aw, I.addmem_w); }
+    const double f = o->realloc_factor < 1.0 ? 1.0 : o->realloc_factor;
+    const size_t n = (size_t)d.nmat;
+    CK(cudaStreamSynchronize(o->stream));
+    for (int which = 0; which < 2; which++) {
+        const int64_t add = which == 0 ? al : au;
+        if (add <= 0) continue;
+        blu_i64 &mem = which == 0 ? d.l_mem : d.u_mem;
+        const int64_t newmem = (int64_t)(f * (double)(mem + add)) + 1;
+        if (newmem > 0x3fffffff) return BLU_ERROR_OUT_OF_MEMORY;
+        int *ni = nullptr; double *nv = nullptr;
+        st = dalloc(o, &ni, n * (size_t)newmem + PADDING);
+        if (st == BLU_OK) st = dalloc(o, &nv, n * (size_t)newmem + PADDING);
+        if (st != BLU_OK) return st;
+        int *&oi = which == 0 ? d.l_idx : d.u_idx; double *&ov = which == 0 ? d.l_val : d.u_val;
+        CK(cudaMemcpy2DAsync(ni, (size_t)newmem * sizeof(int), oi, (size_t)mem * sizeof(int), (size_t)mem * sizeof(int), n, cudaMemcpyDeviceToDevice, o->stream));
+        CK(cudaMemcpy2DAsync(nv, (size_t)newmem * sizeof(double), ov, (size_t)mem * sizeof(double), (size_t)mem * sizeof(double), n, cudaMemcpyDeviceToDevice, o->stream));
+        CK(cudaStreamSynchronize(o->stream));
+        dfree(o, oi); dfree(o, ov); oi = ni; ov = nv; mem = newmem;
+    }
+    if (aw > 0) {
+        const int64_t newmem = (int64_t)(f * (double)(d.w_mem + aw)) + 1;
+        if (newmem > 0x1fffffff) return BLU_ERROR_OUT_OF_MEMORY;
+        int *ni = nullptr; double *nv = nullptr;
+        st = dalloc(o, &ni, n * 2 * (size_t)newmem + PADDING);
+        if (st == BLU_OK) st = dalloc(o, &nv, n * 2 * (size_t)newmem + PADDING);
+        if (st != BLU_OK) return st;
+        BLU_LAUNCH(k_w_regrow_batch, d.nmat, 256, 0, o->stream, d, (const int *)d.w_idx, (const double *)d.w_val, d.w_mem, ni, nv, (blu_i64)newmem);
+        o->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(o->stream));
+        dfree(o, d.w_idx); dfree(o, d.w_val); d.w_idx = ni; d.w_val = nv; d.w_mem = newmem;
+    }
+    o->nrealloc++;
+    o->info_dirty = 1;
+    return (al > 0 || au > 0 || aw > 0) ? BLU_OK : BLU_ERROR_INTERNAL;
+}
+
 static int ensure_batch_sparse(blu_b200 *o, int64_t tot) {
     const size_t n = (size_t)o->d.nmat, m = (size_t)o->d.m;
     int st = BLU_OK;
@@ -1045,8 +1091,8 @@ static int ensure_batch_sparse(blu_b200 *o, int64_t tot) {
 /* solve_for_update (blu.rs:257) on every basis of the batch, basis k with its own right-hand side
  * irhs/xrhs[rhs_begin[k] .. rhs_begin[k+1]) (for trans 't'/'T': one index, the column to leave; xrhs may be
  * NULL).  want_solution != 0: nzlhs[k], ilhs[k*m ..] and the values xlhs[k*m + n] as in
- * blu_solve_sparse_multi.  The L/U/W stores are NOT grown in a batch: a basis that runs out of room gets
- * status[k] = BLU_ERROR_OUT_OF_MEMORY and is left unchanged (size the stores with BLU_P_*_MEM). */
+ * blu_solve_sparse_multi.  Reallocate is handled as in blu.rs:268-291: the stores of the whole batch are
+ * grown (content kept) and the bases that asked run again; BLU_ERROR_OUT_OF_MEMORY only if that fails. */
 extern "C" int blu_batch_solve_for_update(blu_batch_t *o, const int64_t *rhs_begin, const int64_t *irhs, const double *xrhs,
                                           int want_solution, int64_t *nzlhs, int64_t *ilhs, double *xlhs, int *status, char trans) {
     if (!o || !rhs_begin || !irhs) return BLU_ERROR_INVALID_ARGUMENT;
@@ -1060,13 +1106,21 @@ extern "C" int blu_batch_solve_for_update(blu_batch_t *o, const int64_t *rhs_beg
     CK(cudaMemcpyAsync(o->sm_begin, rhs_begin, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
     CK(cudaMemcpyAsync(o->sm_irhs, irhs, (size_t)tot * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
     if (xrhs) CK(cudaMemcpyAsync(o->sm_xrhs, xrhs, (size_t)tot * sizeof(double), cudaMemcpyHostToDevice, o->stream));
-    SpMulti W{(int)n, 1, nullptr, nullptr, nullptr, (const i64 *)o->sm_begin};
-    BLU_LAUNCH(k_solve_sparse, (int)n, 32, 0, o->stream, o->d, 0, (const i64 *)o->sm_irhs, xrhs ? (const double *)o->sm_xrhs : (const double *)nullptr,
-               trans, 1, want_solution ? 1 : 0, o->sm_scal, (i64 *)o->sm_ilhs, o->sm_xout, W);
-    o->launches++;
-    CK(cudaGetLastError());
     std::vector<int> hs(2 * n);
-    CK(cudaMemcpyAsync(hs.data(), o->sm_scal, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+    for (int attempt = 0; attempt < 40; attempt++) {
+        SpMulti W{(int)n, attempt > 0, 1, nullptr, nullptr, nullptr, (const i64 *)o->sm_begin};
+        BLU_LAUNCH(k_solve_sparse, (int)n, 32, 0, o->stream, o->d, 0, (const i64 *)o->sm_irhs, xrhs ? (const double *)o->sm_xrhs : (const double *)nullptr,
+                   trans, 1, want_solution ? 1 : 0, o->sm_scal, (i64 *)o->sm_ilhs, o->sm_xout, W);
+        o->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(hs.data(), o->sm_scal, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+        CK(cudaStreamSynchronize(o->stream));
+        bool again = false;
+        for (size_t k = 0; k < n; k++) again = again || hs[2 * k] == BLU_REALLOCATE;
+        if (!again) break;
+        /* blu.rs:268-291: grow and run those bases again (the others keep their results) */
+        if (grow_batch_stores(o) != BLU_OK) break;      /* what still says Reallocate is reported as out of memory below */
+    }
     if (want_solution) {
         CK(cudaMemcpyAsync(ilhs, o->sm_ilhs, n * m * sizeof(int64_t), cudaMemcpyDeviceToHost, o->stream));
         CK(cudaMemcpyAsync(xlhs, o->sm_xout, n * m * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
@@ -1092,12 +1146,18 @@ extern "C" int blu_batch_update(blu_batch_t *o, const double *xtbl, int *status)
     int st = ensure_batch_sparse(o, 0);
     if (st != BLU_OK) return st;
     CK(cudaMemcpyAsync(o->sm_dbls, xtbl, n * sizeof(double), cudaMemcpyHostToDevice, o->stream));
-    BLU_LAUNCH(k_update, (int)n, 32, 0, o->stream, o->d, 0.0, o->sm_scal, (const double *)o->sm_dbls);
-    o->launches++;
-    CK(cudaGetLastError());
     std::vector<int> hs(n);
-    CK(cudaMemcpyAsync(hs.data(), o->sm_scal, n * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
-    CK(cudaStreamSynchronize(o->stream));
+    for (int attempt = 0; attempt < 40; attempt++) {
+        BLU_LAUNCH(k_update, (int)n, 32, 0, o->stream, o->d, 0.0, o->sm_scal, (const double *)o->sm_dbls, attempt > 0 ? 1 : 0);
+        o->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(hs.data(), o->sm_scal, n * sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+        CK(cudaStreamSynchronize(o->stream));
+        bool again = false;
+        for (size_t k = 0; k < n; k++) again = again || hs[k] == BLU_REALLOCATE;
+        if (!again) break;
+        if (grow_batch_stores(o) != BLU_OK) break;      /* blu.rs:319-334 */
+    }
     int worst = BLU_OK;
     for (size_t k = 0; k < n; k++) {
         int s = hs[k];

@@ -455,6 +455,7 @@ __device__ __forceinline__ void sp_ctx_init(SpCtx &C, const BluDev &D, int slot 
  * and the two scattered vectors, so that all units run at once against the same (read-only) factors. */
 struct SpMulti {
     int nunits;               /* 0: single call */
+    int rerun;                /* 1: only the units whose previous status was Reallocate run again */
     int per_slot;             /* 1: unit u works on basis (slot) u of a batch with that slot's own scratch; ints/dbls/markers unused */
     int *ints;                /* nunits * 7m : marked | pattern_symb | pattern | pstack | ilhs | pend | irhs */
     double *dbls;             /* nunits * 2m : work | xlhs  (all-zero between calls) */
@@ -502,6 +503,7 @@ __global__ void __launch_bounds__(32) k_solve_sparse(BluDev D, int nrhs, const i
         irhs64 += b; if (xrhs) xrhs += b;
         nrhs = (e - b < 0 || e - b > 0x7fffffff) ? -1 : (int)(e - b);
         scal += 2 * u; ilhs_out += (size_t)u * D.m; xout += (size_t)u * D.m;
+        if (W.rerun && scal[0] != BLU_REALLOCATE) return;
         if (lane == 0) { if (W.per_slot) sp_ctx_init(C, D, u); else sp_ctx_init_unit(C, D, W, u); }
     } else if (lane == 0) sp_ctx_init(C, D);
     __syncwarp();
@@ -823,12 +825,13 @@ __device__ int sp_compress_packed(SpCtx &C) {
 }
 
 /* update.rs:49-55 + lu/update.rs:388-959.  scal[0] = status. */
-__global__ void __launch_bounds__(32) k_update(BluDev D, double xtbl, int *scal, const double *xtbl_per_slot) {
+__global__ void __launch_bounds__(32) k_update(BluDev D, double xtbl, int *scal, const double *xtbl_per_slot, int rerun) {
     __shared__ SpCtx C;
     const int lane = threadIdx.x & 31;
     /* object API: one block, slot 0.  Batch: block u updates basis u with its own xtbl and status word. */
     const int slot = xtbl_per_slot ? (int)blockIdx.x : 0;
     if (xtbl_per_slot) { xtbl = xtbl_per_slot[slot]; scal += slot; }
+    if (rerun && scal[0] != BLU_REALLOCATE) return;      /* batch re-run after a store was grown: only the bases that asked */
     if (lane == 0) sp_ctx_init(C, D, slot);
     __syncwarp();
     Mat &M = C.M;
@@ -1164,6 +1167,22 @@ __global__ void __launch_bounds__(32) k_update(BluDev D, double xtbl, int *scal,
         I->nupdate++; I->nupdate_total++;
         scal[0] = C.status;
     }
+}
+
+/* batch: move every basis' live half of W into a store with a larger per-basis size and rebase its line table */
+__global__ void k_w_regrow_batch(BluDev D, const int *old_idx, const double *old_val, blu_i64 old_w_mem, int *new_idx, double *new_val, blu_i64 new_w_mem) {
+    __shared__ Mat M;
+    const int s = blockIdx.x;
+    if (threadIdx.x == 0) mat_view(M, D, s);
+    __syncthreads();
+    const int half = M.info->w_half;
+    const size_t src = (size_t)s * 2 * (size_t)old_w_mem + (size_t)half * (size_t)old_w_mem, dst = (size_t)s * 2 * (size_t)new_w_mem;
+    const int used = (int)(M.info->w_used - (blu_i64)half * old_w_mem);
+    for (int q = threadIdx.x; q < used; q += blockDim.x) { new_idx[dst + q] = old_idx[src + q]; new_val[dst + q] = old_val[src + q]; }
+    const int delta = half * (int)old_w_mem;
+    for (int l = threadIdx.x; l < 2 * M.m; l += blockDim.x) { M.lbeg[l] -= delta; M.lend[l] -= delta; M.lcap[l] -= delta; }
+    __syncthreads();
+    if (threadIdx.x == 0) { M.info->w_used -= delta; M.info->w_half = 0; }
 }
 
 /* after the host moved the live half of W into a larger store: shift the line table */

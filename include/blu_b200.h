@@ -138,8 +138,8 @@ int blu_batch_get_factors(blu_batch_t *b, int64_t k, int64_t *rowperm, int64_t *
  * irhs/xrhs[rhs_begin[k] .. rhs_begin[k+1]); for trans 't'/'T' one index (the leaving column), xrhs may be
  * NULL.  With want_solution: nzlhs[k], the pattern ilhs[k*m ..] and the values of those entries compacted
  * in xlhs[k*m + n].  status[k] carries the per-basis code (may be NULL); the return value is the first
- * non-OK one.  The L/U/W stores are not grown in a batch: a basis that runs out of room reports
- * BLU_ERROR_OUT_OF_MEMORY and is left unchanged -- size the stores with BLU_P_L_MEM / U_MEM / W_MEM. */
+ * non-OK one.  Reallocate never escapes (blu.rs:268-291, 319-334): the stores of the whole batch are grown,
+ * content kept, and the bases that asked run again. */
 int blu_batch_solve_for_update(blu_batch_t *b, const int64_t *rhs_begin, const int64_t *irhs, const double *xrhs,
                                int want_solution, int64_t *nzlhs, int64_t *ilhs, double *xlhs, int *status, char trans);
 int blu_batch_update(blu_batch_t *b, const double *xtbl, int *status);

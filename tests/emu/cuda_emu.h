@@ -156,6 +156,10 @@ inline cudaError_t cudaMallocHost(void **p, size_t n) { *p = calloc(n ? n : 1, 1
 inline cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, int, cudaStream_t) {
+    for (size_t r = 0; r < h; r++) memcpy((char *)d + r * dp, (const char *)s + r * sp, w);
+    return 0;
+}
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return 0; }
 inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }

@@ -220,13 +220,19 @@ def test_emu_solve_sparse_multi(emu):
     assert_sparse_multi_parity(g, o, m, 1600, sizes=(2, 25), reps=2)
 
 
-def test_emu_batch_replay(emu):
-    """Many LPs advancing together: batch solve_for_update + update, one warp per basis."""
+@pytest.mark.parametrize("tight", [False, True])
+def test_emu_batch_replay(emu, tight):
+    """Many LPs advancing together: batch solve_for_update + update, one warp per basis.  tight: the stores
+    start at nnz(B), so the batch Reallocate protocol (grow every basis' store, content kept, re-run only
+    the bases that asked) is exercised."""
     from parity import batch_replay_parity
     nmat, m = 3, 70
     bb, be, bi, bx, rhs = gen.batch(nmat, m, 25, 4.0, 9100, 9600)
     b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()), lib=emu)
-    b.l_mem = 40000; b.u_mem = 40000; b.w_mem = 60000
+    if tight:
+        b.l_mem = 300; b.u_mem = 300; b.w_mem = 300
+    else:
+        b.l_mem = 40000; b.u_mem = 40000; b.w_mem = 60000
     st, status = b.factorize(bb, be, bi, bx)
     assert st == 0 and (status == 0).all()
     oracles, pools = [], []
@@ -235,7 +241,10 @@ def test_emu_batch_replay(emu):
         o = oracle_for(m, len(v), 400)
         assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
         oracles.append(o); pools.append(gen.basis(9700 + k, m, 0, 3.0))
-    batch_replay_parity(b, oracles, m, pools, 8)
+    nr0 = b.info(0, "nrealloc")
+    batch_replay_parity(b, oracles, m, pools, 8 if not tight else 20)
+    if tight:
+        assert b.info(0, "nrealloc") > nr0
     st, x, sst = b.solve_dense(rhs, "N")
     assert st == 0
     for k, o in enumerate(oracles):
