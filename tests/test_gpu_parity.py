@@ -447,14 +447,19 @@ def test_solve_sparse_multi():
     assert_sparse_multi_parity(g, o, m, 1600, sizes=(2, 60), reps=4)
 
 
-def test_batch_update_replay():
+@pytest.mark.parametrize("tight", [False, True])
+def test_batch_update_replay(tight):
     """Many LPs advancing together: blu_batch_solve_for_update + blu_batch_update (one warp per basis),
-    every basis in lockstep with its own oracle."""
+    every basis in lockstep with its own oracle.  tight: the stores start at nnz(B), so the batch
+    Reallocate protocol (all stores grown with their content, only the bases that asked re-run) runs."""
     from parity import batch_replay_parity
     nmat, m = 48, 300
     bb, be, bi, bx, rhs = gen.batch(nmat, m, 90, 4.0, 9100, 9600)
     b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()))
-    b.l_mem = 200000; b.u_mem = 200000; b.w_mem = 300000
+    if tight:
+        b.l_mem = 1500; b.u_mem = 1500; b.w_mem = 1500
+    else:
+        b.l_mem = 200000; b.u_mem = 200000; b.w_mem = 300000
     st, status = b.factorize(bb, be, bi, bx)
     assert st == 0 and (status == 0).all()
     oracles, pools = [], []
@@ -463,7 +468,10 @@ def test_batch_update_replay():
         o = oracle_for(m, len(v), 400)
         assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
         oracles.append(o); pools.append(gen.basis(9700 + k, m, 0, 3.0))
-    batch_replay_parity(b, oracles, m, pools, 12)
+    nr0 = b.info(0, "nrealloc")
+    batch_replay_parity(b, oracles, m, pools, 12 if not tight else 30)
+    if tight:
+        assert b.info(0, "nrealloc") > nr0
     st, x, sst = b.solve_dense(rhs, "T")
     assert st == 0
     for k, o in enumerate(oracles):
