@@ -318,13 +318,13 @@ def test_edge_shapes(case):
         assert so == sg and np.array_equal(xg, xo, equal_nan=True)
 
 
-@pytest.mark.parametrize("layout", ["in_order", "reversed"])
+@pytest.mark.parametrize("layout", ["in_order", "reversed", "in_order_tight"])
 def test_batch_pipelined_upload(layout):
     """Batches of >= 256 bases are uploaded in pieces while earlier chunks already factorize
     (blu_batch_factorize); the result must not depend on it, nor on where the bases sit in b_i / b_x."""
     nmat, m = 320, 60
     mats = [gen.basis(4000 + k, m, 20, 3.0) for k in range(nmat)]
-    order = range(nmat) if layout == "in_order" else range(nmat - 1, -1, -1)
+    order = range(nmat) if layout.startswith("in_order") else range(nmat - 1, -1, -1)
     off = {}
     pos = 0
     idxs, vals = [], []
@@ -336,8 +336,12 @@ def test_batch_pipelined_upload(layout):
     be = np.concatenate([mats[k][0][1:] + off[k] for k in range(nmat)])
     rhs = np.concatenate([gen.rhs(4500 + k, m) for k in range(nmat)])
     b = BLUBatch(nmat, m, max(len(t[1]) for t in mats))
+    if layout.endswith("tight"):      # Reallocate inside the pipelined path: the classic grow-and-re-run loop takes over
+        b.l_mem = 250; b.u_mem = 250; b.w_mem = 250
     st, status = b.factorize(bb, be, bi, bx)
     assert st == 0 and (status == 0).all()
+    if layout.endswith("tight"):
+        assert b.info(0, "nrealloc") > 0
     st, x, sst = b.solve_dense(rhs, "N")
     assert st == 0 and (sst == 0).all()
     for k in range(0, nmat, 7):
