@@ -203,3 +203,54 @@ def batch_replay_parity(b, oracles, m, pools, niter):
             assert o.update(xt[k]) == stat[k], (it, k, stat[k])
             for name in ("nupdate", "nforrest", "u_nz", "r_nz", "pivot_error", "max_eta", "l_flops", "u_flops", "r_flops"):
                 assert b.info(k, name) == o.info(name), (it, k, name)
+
+
+TUNABLES = dict(            # the `pub` tunables of LU (lu.rs:10-66), values on both sides of the defaults
+    droptol=[1e-20, 1e-12, 1e-6, 1e-2],
+    abstol=[1e-14, 1e-8, 1e-3],
+    reltol=[0.1, 0.01, 0.5, 0.9, 1.0],
+    nzbias=[0, -1, 1, -3],
+    maxsearch=[1, 2, 3, 4, 8],
+    pad=[1, 2, 4, 8],
+    stretch=[0.1, 0.3, 1.0],
+    compress_thres=[0.05, 0.5, 1.0],
+    sparse_thres=[0.0, 0.05, 0.5, 1.0],
+)
+
+
+def draw_tunables(seed):
+    rng = np.random.default_rng(seed)
+    return {k: v[int(rng.integers(len(v)))] for k, v in TUNABLES.items()}
+
+
+def tunables_case(make_gpu, m, seed, nupd=12, dens=4.0):
+    """One random setting of every tunable on both objects, then the whole public surface in lockstep:
+    factorize, get_factors, dense + sparse solves, a few column replacements.  Returns the setting."""
+    from blu_b200 import gen
+    t = draw_tunables(seed)
+    cp, ri, v = gen.basis(seed, m, m // 3, dens)
+    pool = gen.basis(seed + 1, m, 0, 3.0)
+    o = oracle_for(m, len(v), 400)
+    g = make_gpu(m, len(v))
+    for k, x in t.items():
+        o.set_param(k, x)
+        setattr(g, k, x)
+    so = o.factorize(cp[:-1], cp[1:], ri, v)
+    sg = g.factorize(cp[:-1], cp[1:], ri, v)
+    assert so == sg, (t, so, sg)
+    if so not in (0, 2):
+        return t
+    assert_factor_parity(g, o)
+    b = gen.rhs(seed + 2, m)
+    for tr in "NT":
+        _, xo = o.solve_dense(b, tr)
+        sg, xg = g.solve_dense(b, tr)
+        assert sg == 0 and np.array_equal(xg, xo), (t, tr)
+    assert_sparse_solve_parity(g, o, m, seed + 3, sizes=(1, 4, 30))
+    if so == 0:
+        replay_updates(g, o, m, pool, nupd, check_dense=False)
+        for tr in "NT":
+            _, xo = o.solve_dense(b, tr)
+            sg, xg = g.solve_dense(b, tr)
+            assert sg == 0 and np.array_equal(xg, xo), (t, tr, "after updates")
+    return t

@@ -250,3 +250,11 @@ def test_emu_batch_replay(emu, tight):
     for k, o in enumerate(oracles):
         _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
         assert np.array_equal(x[k], xo)
+
+
+@pytest.mark.parametrize("seed", range(300, 306))
+def test_emu_tunables(emu, seed):
+    """Every `pub` tunable of LU (lu.rs:10-66) drawn at random on both sides: the CUDA path follows the
+    oracle through each of them (thresholds, search depth, line padding, sparse/dense switch)."""
+    from parity import tunables_case
+    tunables_case(lambda m, nnz: BLU(m, nnz, lib=emu), 70, seed, nupd=6)

@@ -481,3 +481,13 @@ def test_batch_update_replay(tight):
     for k, o in enumerate(oracles):
         _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "T")
         assert np.array_equal(x[k], xo)
+
+
+@pytest.mark.parametrize("seed", range(400, 412))
+def test_tunables_sweep(seed):
+    """Every `pub` tunable of LU (lu.rs:10-66) drawn at random on both sides (pivot thresholds, drop
+    tolerance, search depth, Markowitz bias, line padding, compression and sparse/dense switch): factors,
+    dense and sparse solves and a run of column replacements stay bit-identical to the oracle's."""
+    from parity import tunables_case
+    m = 200 + 150 * (seed % 5)
+    tunables_case(lambda m, nnz: BLU(m, nnz), m, seed, nupd=25, dens=3.0 + seed % 3)
