@@ -18,6 +18,7 @@ static inline long long clock64() { return 0; }
 #endif
 #define FULLMASK 0xffffffffu
 #define KEY_INF 0xffffffffffffffffull
+#define KEY_PARK 0x8000000000000000ull   /* see mkckey */
 #define STAMP_BITS 40
 #define MAXROW_SMALL 64 /* pivot.rs:22 */
 #define MAXCAND 32      /* upper bound on maxsearch honoured by the search kernel */
@@ -120,7 +121,15 @@ template <int NT> __device__ __forceinline__ void bsync() {
 __device__ __forceinline__ unsigned lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 
 __device__ __forceinline__ u64 mkkey(int cnt, i64 stamp) { return ((u64)(unsigned)cnt << STAMP_BITS) | (u64)stamp; }
-__device__ __forceinline__ int key_cnt(u64 k) { return (int)(k >> STAMP_BITS); }
+__device__ __forceinline__ int key_cnt(u64 k) { return (int)((k & ~KEY_PARK) >> STAMP_BITS); }
+/* Column key.  A non-empty column whose maximum fell below abstol without the column being emptied (its
+ * pivot-row entry was dropped from U, so pivot.rs:96-106 never looked at it) stays in its count list but
+ * the search passes over it without counting it (markowitz.rs:88-90 with D6 repaired): the top bit hides
+ * it from the candidate scan until an update rewrites the key. */
+__device__ __forceinline__ u64 mkckey(int cnt, i64 stamp, double cmx, double abstol) {
+    const u64 k = mkkey(cnt, stamp);
+    return (cnt > 0 && (cmx == 0.0 || cmx < abstol)) ? (k | KEY_PARK) : k;
+}
 
 /* ---- warp primitives ---- */
 __device__ __forceinline__ int warp_incl_scan(int v) {

@@ -141,7 +141,7 @@ template <int NT> __device__ void markowitz_search(Shm &S) {
             #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const u64 k = kk[u]; const int j = jj[u];
-                if (k == KEY_INF || (have_prev && k <= prev)) continue;
+                if (k >= KEY_PARK || (have_prev && k <= prev)) continue;      /* dead (KEY_INF) or passed over (mkckey) */
                 if (k < k2) {
                     if (k < k1) {
                         k2 = k1; j2 = j1;
@@ -303,6 +303,8 @@ __device__ __forceinline__ void warp_remove_col(Shm &S, int j) {
 /* pivot.rs:96-106: after a step, empty every touched column whose max is 0 or < abstol */
 template <int NT> __device__ void post_remove_cols(Shm &S, int rank) {
     Mat &M = S.M;
+    /* the flag was raised before the pivot step's closing barrier, so every thread reads the same value
+     * here; it is lowered only after a barrier of its own, when every thread has read it */
     if (S.need_remove) {
         if ((threadIdx.x >> 5) == 0) {
             const double abstol = M.prm.abstol;
@@ -311,9 +313,9 @@ template <int NT> __device__ void post_remove_cols(Shm &S, int rank) {
                 double c = M.colpiv[j];
                 if (c == 0.0 || c < abstol) warp_remove_col(S, j);
             }
-            if ((threadIdx.x & 31) == 0) S.need_remove = 0;
         }
         bsync<NT>();
+        if (threadIdx.x == 0) S.need_remove = 0;
     }
 }
 
@@ -523,7 +525,7 @@ template <int NT> __device__ void pivot_general(Shm &S, const bool small) {
         if (lane == 0) {
             M.lbeg[j] = beg; M.lend[j] = put; M.lcap[j] = cap;
             M.colpiv[j] = cmx;
-            M.ckey[j] = mkkey(put - beg, cbase + k);
+            M.ckey[j] = mkckey(put - beg, cbase + k, cmx, abstol);
             if (small) M.cancelled[k - 1] = cmask;
             if (fabs(xrj) > droptol) { M.u_idx[ubase + k - 1] = j; M.u_val[ubase + k - 1] = xrj; }
             else { M.u_idx[ubase + k - 1] = -2; M.u_val[ubase + k - 1] = 0.0; S.flag_a = 1; }
@@ -850,7 +852,7 @@ template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
         if (lane == 0) {
             M.lbeg[j] = beg; M.lend[j] = put; M.lcap[j] = cap;
             M.colpiv[j] = cmx;
-            M.ckey[j] = mkkey(put - beg, cbase + k);
+            M.ckey[j] = mkckey(put - beg, cbase + k, cmx, abstol);
             if (small) M.cancelled[k - 1] = cmask;
             if (fabs(xrj) > droptol) { M.u_idx[ubase + k - 1] = j; M.u_val[ubase + k - 1] = xrj; }
             else { M.u_idx[ubase + k - 1] = -2; M.u_val[ubase + k - 1] = 0.0; S.flag_a = 1; }
@@ -1085,7 +1087,7 @@ template <int NT> __device__ void pivot_singleton_col(Shm &S) {
             M.w_idx[where] = M.w_idx[end - 1];
             M.w_val[where] = M.w_val[end - 1];
             M.lend[j] = end - 1;
-            M.ckey[j] = mkkey(end - 1 - beg, cbase + q);
+            M.ckey[j] = mkckey(end - 1 - beg, cbase + q, cmx, abstol);
             M.colpiv[j] = cmx;
             if (cmx == 0.0 || cmx < abstol) S.need_remove = 1;
             acc_bytes += 12.0 * (2 * (end - beg) - 1);
@@ -1183,11 +1185,13 @@ template <int NT> __device__ void pivot_doubleton_col(Shm &S) {
                     M.w_idx[wp] = other_row; M.w_val[wp] = x;
                     kd = 1;
                     if (xa > cmx) cmx = xa;
+                    const u64 kk = M.ckey[j] & ~KEY_PARK;      /* same list position, new maximum */
+                    M.ckey[j] = (cmx == 0.0 || cmx < abstol) ? (kk | KEY_PARK) : kk;
                 } else {
                     end--;
                     M.w_idx[wp] = M.w_idx[end]; M.w_val[wp] = M.w_val[end];
                     M.lend[j] = end;
-                    M.ckey[j] = mkkey(end - beg, cbase + k);
+                    M.ckey[j] = mkckey(end - beg, cbase + k, cmx, abstol);
                 }
             } else {
                 end--;
@@ -1202,7 +1206,7 @@ template <int NT> __device__ void pivot_doubleton_col(Shm &S) {
                     kd = 2; S.flag_b = 1;
                 } else if (xa > cmx) cmx = xa;
                 M.lend[j] = end;
-                M.ckey[j] = mkkey(end - beg, cbase + k);
+                M.ckey[j] = mkckey(end - beg, cbase + k, cmx, abstol);
             }
             kind[k] = kd;
             M.colpiv[j] = cmx;

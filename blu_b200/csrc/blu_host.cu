@@ -106,7 +106,7 @@ static void free_stores(blu_b200 *o) {
 }
 
 static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_cap, int device, int single) {
-    if (!out || m < 1 || nmat < 1 || bnz_cap < 0 || m > 0x3fffffff) return BLU_ERROR_INVALID_ARGUMENT;
+    if (!out || m < 1 || nmat < 1 || bnz_cap < 0 || m > 0x7fffff /* line counts live in 23 bits of the search keys, blu_dev_common.cuh:mkckey */) return BLU_ERROR_INVALID_ARGUMENT;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
         fprintf(stderr, "blu_b200: no CUDA device (this library has no CPU path)\n");

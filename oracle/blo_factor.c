@@ -344,7 +344,7 @@ int blo_markowitz(blo_lu *lu) {
             assert(w_end[j] - w_begin[j] == nz);
             double cmx = colmax[j];
             assert(cmx >= 0.0);
-            if (cmx == 0.0 || cmx < abstol) continue; /* D6 repaired: advance j (unreachable) */
+            if (cmx == 0.0 || cmx < abstol) continue; /* D6 repaired: advance j.  Reached when a column keeps entries but its pivot-row entry was dropped from U, so pivot.rs:96-106 never emptied it */
             double tol = fmax(abstol, reltol * cmx);
             for (lint pos = w_begin[j]; pos < w_end[j]; pos++) {
                 double x = fabs(w_value[pos]);

@@ -1,0 +1,50 @@
+"""Bug hunt, not a test: random STRUCTURES (sign matrices that cancel exactly, rank-deficient ones,
+permuted triangles, arrowheads, dense blocks, badly scaled entries) under random tunables, CUDA path
+vs the oracle (tests/parity.py:tunables_case).
+usage: python scripts/structure_hunt.py [first_seed] [count] [max_m] [--emu]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from blu_b200 import BLU, load_library  # noqa: E402
+from parity import tunables_case, structured_case  # noqa: E402
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+first = int(args[0]) if len(args) > 0 else 9000
+count = int(args[1]) if len(args) > 1 else 200
+max_m = int(args[2]) if len(args) > 2 else 600
+lib = load_library(os.path.join(ROOT, "tests", "emu", "libblu_emu.so")) if "--emu" in sys.argv else None
+
+
+bad, t0 = 0, time.time()
+kinds, aborted = {}, 0
+for seed in range(first, first + count):
+    m = 8 + (seed * 37) % max_m
+    kind = seed % 6
+    if "--verbose" in sys.argv:
+        print("seed", seed, "kind", kind, "m", m, flush=True)
+    # one child per case: an input on which the reference itself breaks trips a live assert of the oracle
+    # (abort), which must not end the hunt; CUDA is first touched in the child
+    pid = os.fork()
+    if pid == 0:
+        rc = 0
+        try:
+            structured_case(lambda m, nnz: BLU(m, nnz, lib=lib) if lib else BLU(m, nnz), m, seed)
+        except AssertionError as e:
+            print("FAIL seed", seed, "kind", kind, "m", m, str(e)[:400], flush=True)
+            rc = 1
+        os._exit(rc)
+    _, st = os.waitpid(pid, 0)
+    if os.WIFSIGNALED(st):
+        aborted += 1
+        print("seed", seed, "kind", kind, "m", m, "ended by signal", os.WTERMSIG(st), "(oracle assert: the reference breaks on this input)", flush=True)
+    elif os.WEXITSTATUS(st) != 0:
+        bad += 1
+        if bad > 8:
+            break
+    else:
+        kinds[kind] = kinds.get(kind, 0) + 1
+print(f"{count} cases, {bad} failures, {aborted} outside the reference's domain, passed per kind {sorted(kinds.items())}, {time.time() - t0:.1f} s")

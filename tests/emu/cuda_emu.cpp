@@ -1,5 +1,7 @@
 /* cuda_emu.cpp -- scheduler of the SIMT emulator (test/debug infrastructure, see cuda_emu.h) */
 #include "cuda_emu.h"
+#include <execinfo.h>
+#include <dlfcn.h>
 
 emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 unsigned char *emu_dyn_smem = nullptr;
@@ -15,6 +17,8 @@ static const size_t STACK = 256 * 1024;
 void yield_wait(unsigned *gen, unsigned mygen) {
     Fiber &f = fibers[cur];
     f.state = 1; f.gen = gen; f.mygen = mygen;
+    static const int trace = getenv("EMU_TRACE") != nullptr;
+    f.nbt = trace ? backtrace(f.bt, 10) : 0;
     int me = cur;
     swapcontext(&f.ctx, &sched_ctx);
     cur = me;
@@ -89,9 +93,15 @@ void launch(emu_dim3 grid, emu_dim3 block, size_t smem, std::function<void()> bo
             if (!progressed) {
                 fprintf(stderr, "cuda_emu: DEADLOCK in block %u (divergent barrier?)\n", b);
                 for (int t = 0; t < nthreads; t++)
-                    if (fibers[t].state == 1)
-                        fprintf(stderr, "  thread %d waits on %s barrier\n", t,
+                    if (fibers[t].state == 1) {
+                        fprintf(stderr, "  thread %d waits on %s barrier", t,
                                 fibers[t].gen == &blk_gen ? "block" : "warp");
+                        for (int q = 0; q < fibers[t].nbt; q++) {      /* offsets into this library, for addr2line -e */
+                            Dl_info di;
+                            if (dladdr(fibers[t].bt[q], &di) && di.dli_fbase) fprintf(stderr, " +0x%zx", (size_t)((char *)fibers[t].bt[q] - (char *)di.dli_fbase));
+                        }
+                        fprintf(stderr, "\n");
+                    }
                 abort();
             }
         }

@@ -53,6 +53,7 @@ struct Fiber {
     int state;      /* 0 runnable, 1 waiting, 2 done */
     unsigned *gen;  /* generation counter waited on */
     unsigned mygen;
+    void *bt[10]; int nbt;   /* EMU_TRACE=1: call stack of the barrier waited on, printed on deadlock */
 };
 struct Warp {
     unsigned gen; int arrived; int live;

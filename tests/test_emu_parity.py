@@ -258,3 +258,13 @@ def test_emu_tunables(emu, seed):
     oracle through each of them (thresholds, search depth, line padding, sparse/dense switch)."""
     from parity import tunables_case
     tunables_case(lambda m, nnz: BLU(m, nnz, lib=emu), 70, seed, nupd=6)
+
+
+@pytest.mark.parametrize("seed,m", [(9004, 56), (9040, 88), (9000, 8), (9001, 45), (9002, 82), (9003, 19), (9005, 93)])
+def test_emu_structures(emu, seed, m):
+    """Structures the synthetic generator does not produce, under random tunables.  Seeds 9004 and 9040
+    are regressions: badly scaled columns whose maximum falls below abstol while their pivot-row entry is
+    dropped from U stay non-empty, and the search passes over them without counting them
+    (markowitz.rs:88-90, defect D6 repaired); 9004 also caught a divergent barrier in post_remove_cols."""
+    from parity import structured_case
+    structured_case(lambda m, nnz: BLU(m, nnz, lib=emu), m, seed)

@@ -491,3 +491,12 @@ def test_tunables_sweep(seed):
     from parity import tunables_case
     m = 200 + 150 * (seed % 5)
     tunables_case(lambda m, nnz: BLU(m, nnz), m, seed, nupd=25, dens=3.0 + seed % 3)
+
+
+@pytest.mark.parametrize("seed,m", [(9004, 56), (9040, 88)] + [(9100 + k, 60 + 90 * k) for k in range(12)])
+def test_structures_sweep(seed, m):
+    """Sign matrices that cancel exactly, permuted triangles, arrowheads, dense blocks, badly scaled
+    entries, empty rows and columns -- each under a random setting of the tunables.  9004 / 9040:
+    columns passed over by the search (markowitz.rs:88-90), see tests/test_emu_parity.py."""
+    from parity import structured_case
+    structured_case(lambda m, nnz: BLU(m, nnz), m, seed, nupd=20)
