@@ -493,7 +493,10 @@ def test_tunables_sweep(seed):
     tunables_case(lambda m, nnz: BLU(m, nnz), m, seed, nupd=25, dens=3.0 + seed % 3)
 
 
-@pytest.mark.parametrize("seed,m", [(9004, 56), (9040, 88)] + [(9100 + k, 60 + 90 * k) for k in range(12)])
+# (9106, 600) is left out: there the search ends without a pivot column, an input on which the reference itself
+# breaks (factorize_bump.rs:22 assert; the oracle's live assert aborts the process, the device reports -100)
+@pytest.mark.parametrize("seed,m", [(9004, 56), (9040, 88), (9112, 600), (9118, 600)]
+                         + [(9100 + k, 60 + 90 * k) for k in range(12) if k != 6])
 def test_structures_sweep(seed, m):
     """Sign matrices that cancel exactly, permuted triangles, arrowheads, dense blocks, badly scaled
     entries, empty rows and columns -- each under a random setting of the tunables.  9004 / 9040:
