@@ -307,6 +307,7 @@ def structured_case(make_gpu, m, seed, nupd=12):
     import scipy.sparse as sp
     rng = np.random.default_rng(seed)
     M = structured_matrix(seed % 6, m, rng)
-    pool = _csc(sp.random(m, 40, density=min(1.0, 3.0 / m) + 0.01, format="csc", random_state=rng)
-                + sp.csc_matrix((np.ones(40), (rng.integers(0, m, 40), np.arange(40))), shape=(m, 40)))
+    nc = max(40, nupd)
+    pool = _csc(sp.random(m, nc, density=min(1.0, 3.0 / m) + 0.01, format="csc", random_state=rng)
+                + sp.csc_matrix((np.ones(nc), (rng.integers(0, m, nc), np.arange(nc))), shape=(m, nc)))
     return tunables_case(make_gpu, m, seed, nupd=nupd, matrix=M, pool=pool)
