@@ -311,3 +311,42 @@ def structured_case(make_gpu, m, seed, nupd=12):
     pool = _csc(sp.random(m, nc, density=min(1.0, 3.0 / m) + 0.01, format="csc", random_state=rng)
                 + sp.csc_matrix((np.ones(nc), (rng.integers(0, m, nc), np.arange(nc))), shape=(m, nc)))
     return tunables_case(make_gpu, m, seed, nupd=nupd, matrix=M, pool=pool)
+
+
+def batch_structured_case(make_batch, m, seed0):
+    """One batch holding five different structures (structured_matrix kinds 0,1,2,3,5) under one random
+    setting of the tunables: status, factors, counters and dense solves of every basis equal those of an
+    oracle instance given the same basis alone."""
+    t = draw_tunables(seed0)
+    mats = [structured_matrix(kind, m, np.random.default_rng(seed0 + k)) for k, kind in enumerate([0, 1, 2, 3, 5])]
+    n = len(mats)
+    off, bb, be = 0, [], []
+    for cp, ri, v in mats:
+        bb.append(cp[:-1] + off); be.append(cp[1:] + off); off += len(v)
+    bb, be = np.concatenate(bb), np.concatenate(be)
+    bi, bx = np.concatenate([x[1] for x in mats]), np.concatenate([x[2] for x in mats])
+    b = make_batch(n, m, max(len(x[2]) for x in mats))
+    for a, x in t.items():
+        setattr(b, a, x)
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0
+    rhs = np.random.default_rng(seed0).uniform(-1, 1, n * m)
+    outs = {tr: np.asarray(b.solve_dense(rhs, tr)[1]).reshape(-1) for tr in "NT"}
+    for k, (cp, ri, v) in enumerate(mats):
+        o = oracle_for(m, len(v), 400)
+        for a, x in t.items():
+            o.set_param(a, x)
+        so = o.factorize(cp[:-1], cp[1:], ri, v)
+        assert so == status[k], (k, so, status[k])
+        if so not in (0, 2):
+            continue
+        _, fo = o.get_factors()
+        stg, fg = b.get_factors(k)
+        assert stg == 0
+        for name in fo:
+            assert np.array_equal(fo[name], fg[name]), (k, name)
+        for name in STATS:
+            assert o.info(name) == b.info(k, name), (k, name)
+        for tr in "NT":
+            _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], tr)
+            assert np.array_equal(outs[tr][k * m:(k + 1) * m], xo), (k, tr)

@@ -268,3 +268,9 @@ def test_emu_structures(emu, seed, m):
     (markowitz.rs:88-90, defect D6 repaired); 9004 also caught a divergent barrier in post_remove_cols."""
     from parity import structured_case
     structured_case(lambda m, nnz: BLU(m, nnz, lib=emu), m, seed)
+
+
+@pytest.mark.parametrize("m,seed0", [(41, 610), (96, 660), (151, 710)])
+def test_emu_batch_structures(emu, m, seed0):
+    from parity import batch_structured_case
+    batch_structured_case(lambda n, m, cap: BLUBatch(n, m, cap, lib=emu), m, seed0)

@@ -503,3 +503,10 @@ def test_structures_sweep(seed, m):
     columns passed over by the search (markowitz.rs:88-90), see tests/test_emu_parity.py."""
     from parity import structured_case
     structured_case(lambda m, nnz: BLU(m, nnz), m, seed, nupd=20)
+
+
+@pytest.mark.parametrize("m,seed0", [(41, 610), (151, 710), (700, 800), (1900, 900)])
+def test_batch_structures(m, seed0):
+    """Different structures side by side in one batch, random tunables: every basis as if factorized alone."""
+    from parity import batch_structured_case
+    batch_structured_case(lambda n, m, cap: BLUBatch(n, m, cap), m, seed0)
