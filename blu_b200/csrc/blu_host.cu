@@ -70,7 +70,10 @@ static int cuda_ok(cudaError_t e, const char *what) {
 template <typename T> static int dalloc(blu_b200 *o, T **p, size_t n) {
     void *q = nullptr;
     if (cudaMalloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return BLU_ERROR_OUT_OF_MEMORY; }
-    if (cudaMemset(q, 0, (n ? n : 1) * sizeof(T)) != cudaSuccess) return BLU_ERROR_CUDA;
+    /* cudaMemset of device memory returns before it has run, on the legacy stream -- which the library's
+     * non-blocking streams do not wait for.  Without the synchronize, work queued right after an allocation
+     * (the copy of the old content when a store grows) could be overtaken by the zero fill. */
+    if (cudaMemset(q, 0, (n ? n : 1) * sizeof(T)) != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) { cudaFree(q); return BLU_ERROR_CUDA; }
     *p = (T *)q;
     o->allocs.push_back(q);
     return BLU_OK;
