@@ -170,7 +170,9 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
         /* nupdate = None until the first factorization (lu.rs:329-331) */
         o->hinfo.assign(n, BluInfo());
         for (auto &I : o->hinfo) { memset(&I, 0, sizeof I); I.nupdate = -1; I.m = (int)m; I.ftran_for_update = I.btran_for_update = -1; I.update_cost_denom = 1.0; }
-        if (cudaMemcpy(d.info, o->hinfo.data(), n * sizeof(BluInfo), cudaMemcpyHostToDevice) != cudaSuccess) st = BLU_ERROR_CUDA;
+        /* (pageable host memory: the call may return with the DMA still in flight on the legacy stream, which the
+         * library's non-blocking stream does not wait for -- hence the synchronize) */
+        if (cudaMemcpy(d.info, o->hinfo.data(), n * sizeof(BluInfo), cudaMemcpyHostToDevice) != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) st = BLU_ERROR_CUDA;
     }
     if (st == BLU_OK && single) {
         if (cudaMallocHost((void **)&o->h_scal, 16 * sizeof(int)) != cudaSuccess ||
@@ -628,7 +630,7 @@ extern "C" int blu_set_param(blu_t *o, int what, double v) {
         if (st != BLU_OK) return st;
         /* the factors are gone */
         for (auto &I : o->hinfo) I.nupdate = -1;
-        if (cudaMemcpy(o->d.info, o->hinfo.data(), o->hinfo.size() * sizeof(BluInfo), cudaMemcpyHostToDevice) != cudaSuccess) return BLU_ERROR_CUDA;
+        if (cudaMemcpy(o->d.info, o->hinfo.data(), o->hinfo.size() * sizeof(BluInfo), cudaMemcpyHostToDevice) != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) return BLU_ERROR_CUDA;
         break;
     }
     default: return BLU_ERROR_INVALID_ARGUMENT;
