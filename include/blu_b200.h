@@ -65,7 +65,9 @@ enum {
 /* ------------------------------------------------------------------ */
 typedef struct blu_b200 blu_t;
 
-/* BLU::new(m, b_nz), blu.rs:61-70.  device < 0: current device. */
+/* BLU::new(m, b_nz), blu.rs:61-70.  device < 0: current device.
+ * 1 <= m < 2^23 (BLU_ERROR_INVALID_ARGUMENT otherwise); each of the L, U and W stores holds fewer than 2^30
+ * (W: 2^29) entries per basis, beyond which growing them reports BLU_ERROR_OUT_OF_MEMORY. */
 int blu_create(blu_t **out, int64_t m, int64_t b_nz, int device);
 void blu_destroy(blu_t *o);
 
