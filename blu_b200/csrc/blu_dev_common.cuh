@@ -15,6 +15,8 @@ typedef blu_i64 i64;
 
 #ifdef BLU_EMU
 static inline long long clock64() { return 0; }
+static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }
+static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x, 8); return r; }
 #endif
 #define FULLMASK 0xffffffffu
 #define KEY_INF 0xffffffffffffffffull
@@ -46,6 +48,7 @@ struct Mat {
     int *rowmark, *colmark, *marked, *iwork1, *pstack, *acols, *tmpi;
     u64 *cancelled;
     double *work0, *work1, *gwork;
+    double *dn_val; BluKey2 *dn_key; unsigned *dn_rbits, *dn_cbits;
     BluInfo *info;
 };
 
@@ -78,6 +81,11 @@ __device__ __forceinline__ void mat_view(Mat &M, const BluDev &D, int s) {
     M.cancelled = D.cancelled + S * m;
     M.work0 = D.work0 + S * m; M.work1 = D.work1 + S * m;
     M.gwork = D.gwork + S * (size_t)D.gwork_warps * m;
+    {
+        const size_t kd = (size_t)D.dense_k, kw = kd / 32;
+        M.dn_val = D.dn_val + S * kd * kd; M.dn_key = D.dn_key + S * kd * kd;
+        M.dn_rbits = D.dn_rbits + S * kd * kw; M.dn_cbits = D.dn_cbits + S * kd * kw;
+    }
     M.info = D.info + s;
 }
 
@@ -112,7 +120,18 @@ struct Shm {
     int dyn_bytes;            /* size of the dynamic shared memory (reused as scratch outside the pivot loop) */
     int wc, wr;               /* position of the pivot in its column / row (single writer) */
     double elim_bytes; i64 nelim_div;
-    i64 t_phase[12]; i64 n_kind[8];
+    i64 t_phase[16]; i64 n_kind[8];
+    /* dense tail (blu_factor_dense.cuh) */
+    unsigned char *dyn;       /* base of the dynamic shared memory */
+    int dense;                /* 1 while the active submatrix lives in the dense arrays */
+    int kd, kw;               /* slots per side (multiple of 32) and words per bitmap row */
+    int nrs, ncs;             /* row / column slots handed out at entry */
+    int dpt, dpc;             /* slots of the pivot row / column */
+    unsigned ekc, ekr;        /* next storage-order key of a column entry / a row entry */
+    int dense_entries, dense_block_rank;
+    u64 *skeyc, *scm; double *cvalp; int *drow, *dcol; unsigned *keyc, *keyr;
+    unsigned *cmask, *rmask, *rfull;
+    unsigned short *clist, *rlist, *posr, *rnz, *cnz, *tmps, *tmpr;
 };
 
 template <int NT> __device__ __forceinline__ void bsync() {

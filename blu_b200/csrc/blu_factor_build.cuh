@@ -330,7 +330,9 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
             S.elim_bytes = 0.0; S.nelim_div = 0;
             S.w_used = 0; S.w_limit = (int)D.w_mem; S.w_half = 0;
             S.wc = -1; S.wr = -1;
-            for (int q = 0; q < 12; q++) S.t_phase[q] = 0;
+            S.dyn = dyn; S.dense = 0; S.kd = D.dense_k; S.kw = D.dense_k / 32;
+            S.dense_entries = 0; S.dense_block_rank = 0;
+            for (int q = 0; q < 16; q++) S.t_phase[q] = 0;
             for (int q = 0; q < 8; q++) S.n_kind[q] = 0;
         }
         bsync<NT>();
@@ -354,7 +356,7 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
             I->elim_bytes = S.elim_bytes; I->nelim_div = S.nelim_div;
             I->w_half = S.w_half; I->w_used = S.w_used;
             I->cstamp = S.cstamp; I->rstamp = S.rstamp;
-            for (int q = 0; q < 12; q++) I->t_phase[q] = S.t_phase[q];
+            for (int q = 0; q < 16; q++) I->t_phase[q] = S.t_phase[q];
             for (int q = 0; q < 8; q++) I->n_kind[q] = S.n_kind[q];
             int st = S.status;
             if (st == BLU_OK) {

@@ -1296,28 +1296,39 @@ template <int NT> __device__ void pivot_doubleton_col(Shm &S) {
     bsync<NT>();
 }
 
+#include "blu_factor_dense.cuh"
+
 /* ------------------------------------------------------------------ */
 /* pivot dispatcher (pivot.rs:48-112) + driver (factorize_bump.rs)     */
 /* ------------------------------------------------------------------ */
+#define DENSE_MIN_ROWS 4      /* the last pivots are singletons / doubletons: not worth a conversion */
+#define DENSE_MAX_ENTRIES 8   /* conversions per factorization (each costs O(kd^2)) */
 template <int NT> __device__ void phase_bump(Shm &S) {
     Mat &M = S.M;
     const int m = M.m, tid = threadIdx.x;
     while (S.rank + S.rankdef < m) {
         i64 t0 = clock64();
-        markowitz_search<NT>(S);
+        if (!S.dense && S.kd > 0 && m - S.rank <= S.kd && m - S.rank >= DENSE_MIN_ROWS &&
+            S.rank >= S.dense_block_rank && S.dense_entries < DENSE_MAX_ENTRIES && M.prm.search_rows == 0) {
+            dense_enter<NT>(S);
+            if (tid == 0) S.t_phase[13] += clock64() - t0;
+            if (S.status != BLU_OK) return;
+            t0 = clock64();
+        }
+        if (S.dense) dense_search<NT>(S); else markowitz_search<NT>(S);
         if (tid == 0) S.t_phase[3] += clock64() - t0;
         if (S.status != BLU_OK) return;
         const int pc = S.pivot_col, pr = S.pivot_row;
         if (pr < 0) {
             /* empty column: drop it, no pivot (factorize_bump.rs:23-31) */
             bsync<NT>();
-            if (tid == 0) { M.ckey[pc] = KEY_INF; S.ndead++; S.rankdef++; }
+            if (tid == 0) { M.ckey[pc] = KEY_INF; if (S.dense) S.skeyc[S.dpc] = KEY_INF; S.ndead++; S.rankdef++; }
             bsync<NT>();
             continue;
         }
         const int rank = S.rank;
-        const int nz_col = M.lend[pc] - M.lbeg[pc];
-        const int nz_row = M.lend[m + pr] - M.lbeg[m + pr];
+        const int nz_col = S.dense ? (int)S.cnz[S.dpc] : M.lend[pc] - M.lbeg[pc];
+        const int nz_row = S.dense ? (int)S.rnz[S.dpt] : M.lend[m + pr] - M.lbeg[m + pr];
         /* room in L and U, pivot.rs:69-81 */
         {
             int room = M.l_mem - M.l_begin_p[rank];
@@ -1328,6 +1339,30 @@ template <int NT> __device__ void phase_bump(Shm &S) {
             if (st != BLU_OK) { bsync<NT>(); if (tid == 0) S.status = st; bsync<NT>(); return; }
         }
         t0 = clock64();
+        if (S.dense) {
+            if (nz_row > 1 && nz_col > 2) {
+                const bool small = nz_col - 1 <= MAXROW_SMALL;
+                dense_pivot<NT>(S, small);
+                if (tid == 0) { S.t_phase[12] += clock64() - t0; S.n_kind[small ? 3 : 4]++; }
+                if (S.status != BLU_OK) return;
+                if (S.need_remove) {      /* pivot.rs:96-106 works on the line file */
+                    t0 = clock64();
+                    dense_exit<NT>(S);
+                    if (tid == 0) S.t_phase[13] += clock64() - t0;
+                    if (S.status != BLU_OK) return;
+                    t0 = clock64();
+                    post_remove_cols<NT>(S, rank);
+                    if (tid == 0) S.t_phase[10] += clock64() - t0;
+                    if (S.status != BLU_OK) return;
+                }
+                continue;
+            }
+            /* singleton row / column or doubleton column: back to the line file, same pivot */
+            dense_exit<NT>(S);
+            if (tid == 0) S.t_phase[13] += clock64() - t0;
+            if (S.status != BLU_OK) return;
+            t0 = clock64();
+        }
         int kind;
         if (nz_row == 1) { pivot_singleton_row<NT>(S); kind = 0; }
         else if (nz_col == 1) { pivot_singleton_col<NT>(S); kind = 1; }

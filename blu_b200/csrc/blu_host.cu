@@ -108,6 +108,30 @@ static void free_stores(blu_b200 *o) {
     d.l_idx = d.u_idx = d.w_idx = nullptr; d.l_val = d.u_val = d.w_val = nullptr;
 }
 
+/* the dense-tail arrays (blu_factor_dense.cuh); dense_k = 0 disables the dense tail */
+static void free_dense(blu_b200 *o) {
+    BluDev &d = o->d;
+    dfree(o, d.dn_val); dfree(o, d.dn_key); dfree(o, d.dn_rbits); dfree(o, d.dn_cbits);
+    d.dn_val = nullptr; d.dn_key = nullptr; d.dn_rbits = d.dn_cbits = nullptr;
+}
+static int alloc_dense(blu_b200 *o, int want) {
+    BluDev &d = o->d;
+    free_dense(o);
+    int kd = want < 0 ? 0 : want;
+    const int mcap = (d.m + 31) & ~31;
+    if (kd > mcap) kd = mcap;
+    kd &= ~31;
+    if (kd > 4096) kd = 4096;
+    d.dense_k = kd;
+    const size_t n = (size_t)d.nmat, k = (size_t)kd;
+    int st = dalloc(o, &d.dn_val, n * k * k);
+    if (st == BLU_OK) st = dalloc(o, &d.dn_key, n * k * k);
+    if (st == BLU_OK) st = dalloc(o, &d.dn_rbits, n * k * (k / 32));
+    if (st == BLU_OK) st = dalloc(o, &d.dn_cbits, n * k * (k / 32));
+    if (st != BLU_OK) { free_dense(o); d.dense_k = 0; }
+    return st;
+}
+
 static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_cap, int device, int single) {
     if (!out || m < 1 || nmat < 1 || bnz_cap < 0 || m > 0x7fffff /* line counts live in 23 bits of the search keys, blu_dev_common.cuh:mkckey */) return BLU_ERROR_INVALID_ARGUMENT;
     int ndev = 0;
@@ -166,6 +190,11 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     o->b_cap = 0; o->db_i = nullptr; o->db_x = nullptr;
     o->gf_i = nullptr; o->gf_x = nullptr; o->gf_cap = 0;
     if (st == BLU_OK) st = alloc_stores(o);
+    if (st == BLU_OK) {
+        int kd = 256;
+        if (const char *e = getenv("BLU_B200_DENSE_K")) kd = atoi(e);      /* tuning knob, same as BLU_P_DENSE_K */
+        st = alloc_dense(o, kd);
+    }
     if (st == BLU_OK) {
         /* nupdate = None until the first factorization (lu.rs:329-331) */
         o->hinfo.assign(n, BluInfo());
@@ -246,7 +275,8 @@ static void timer_stop(blu_b200 *o, int which) {
 }
 
 template <int NT> static int launch_factorize_nt(blu_b200 *o, cudaStream_t stream, int slot0, int nslot) {
-    const size_t smem = blu_factor_smem_bytes(o->cap, NT / 32, o->d.m);
+    size_t smem = blu_factor_smem_bytes(o->cap, NT / 32, o->d.m);
+    if (o->d.dense_k > 0) smem = std::max(smem, blu_dense_smem_bytes(o->d.dense_k));
 #ifndef BLU_EMU
     /* static + dynamic shared memory beyond 48 KB needs the opt-in (the static part is ~2.2 KB) */
     if (smem > 40 * 1024) CK(cudaFuncSetAttribute(k_factorize<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -581,7 +611,7 @@ static double info_value(blu_b200 *o, const BluInfo &I, int what) {
     case BLU_I_STATUS: return I.status;
     case BLU_I_NREALLOC: return o->nrealloc;
     default:
-        if (what >= BLU_I_T_PHASE0 && what < BLU_I_T_PHASE0 + 12) return (double)I.t_phase[what - BLU_I_T_PHASE0];
+        if (what >= BLU_I_T_PHASE0 && what < BLU_I_T_PHASE0 + 16) return (double)I.t_phase[what - BLU_I_T_PHASE0];
         if (what >= BLU_I_N_KIND0 && what < BLU_I_N_KIND0 + 8) return (double)I.n_kind[what - BLU_I_N_KIND0];
         if (what >= BLU_I_NORMS_CYC0 && what < BLU_I_NORMS_CYC0 + 16) return (double)I.norms_cycles[what - BLU_I_NORMS_CYC0];
         return 0.0;
@@ -614,6 +644,14 @@ extern "C" int blu_set_param(blu_t *o, int what, double v) {
         p.search_rows = 0; break;
     case BLU_P_REALLOC_FACTOR: o->realloc_factor = v; break;
     case BLU_P_NORMS: o->norms = v != 0.0; break;
+    case BLU_P_DENSE_K: {
+        if (v < 0 || v > 4096) return BLU_ERROR_INVALID_ARGUMENT;
+        if (cudaSetDevice(o->device) != cudaSuccess) return BLU_ERROR_CUDA;
+        cudaStreamSynchronize(o->stream);
+        int st = alloc_dense(o, (int)v);
+        if (st != BLU_OK) return st;
+        break;
+    }
     case BLU_P_THREADS_PER_BASIS: {
         int t = (int)v;
         if (t != 32 && t != 64 && t != 128 && t != 256 && t != 512 && t != 1024) return BLU_ERROR_INVALID_ARGUMENT;
@@ -657,6 +695,7 @@ extern "C" double blu_get_param(const blu_t *o, int what) {
     case BLU_P_U_MEM: return (double)o->d.u_mem;
     case BLU_P_W_MEM: return (double)o->d.w_mem;
     case BLU_P_THREADS_PER_BASIS: return o->nthreads;
+    case BLU_P_DENSE_K: return o->d.dense_k;
     default: return 0.0;
     }
 }

@@ -22,6 +22,9 @@
 typedef unsigned long long blu_u64;
 typedef long long blu_i64;
 
+/* storage-order keys of one entry of the dense tail */
+struct BluKey2 { unsigned c, r; };
+
 /* lu.rs:17-66, defaults lu.rs:250-259 */
 struct BluParams {
     double droptol, abstol, reltol, stretch, compress_thres, sparse_thres;
@@ -54,9 +57,9 @@ struct BluInfo {
     double elim_bytes;      /* algorithmic bytes of the elimination */
     double condest_l, condest_u, norm_l, norm_u, normest_l_inv, normest_u_inv;
     double onenorm, infnorm, residual_test;
-    blu_i64 t_phase[12];    /* SM clock cycles per phase (thread 0): 0 validate+transpose 1 singleton queue 2 setup_bump 3 search 4 pivot singleton row 5 singleton col 6 doubleton 7 small 8 any 9 build_factors 10 remove_cols 11 total */
-    blu_i64 n_kind[8];
-    blu_i64 norms_cycles[16]; /* SM cycles of the four warps of k_factor_norms: condest(L), condest(U), residual forward + norms, residual transposed */      /* pivots per variant, same numbering minus 4 */
+    blu_i64 t_phase[16];    /* SM clock cycles per phase (thread 0): 0 validate+transpose 1 singleton queue 2 setup_bump 3 search 4 pivot singleton row 5 singleton col 6 doubleton 7 small 8 any 9 build_factors 10 remove_cols 11 total 12 dense-tail steps 13 dense-tail entry/exit conversions */
+    blu_i64 n_kind[8];      /* pivots per variant, same numbering minus 4; 5 = steps taken in the dense tail, 6 = entries into it */
+    blu_i64 norms_cycles[16]; /* SM cycles of the four warps of k_factor_norms: condest(L), condest(U), residual forward + norms, residual transposed */
 };
 
 /* Batch-wide device pointers.  Per-slot strides follow from m and the *_mem sizes. */
@@ -100,6 +103,12 @@ struct BluDev {
     double *work0, *work1;      /* m each */
     double *gwork;              /* gwork_warps*m: per-warp scatter space when a pivot column exceeds the smem cache */
     int gwork_warps;
+    /* dense tail (blu_factor_dense.cuh): the last dense_k x dense_k active submatrix as a row-major value
+     * array, per-entry storage-order keys, and row/column presence bitmaps.  dense_k = 0: disabled. */
+    int dense_k;
+    double *dn_val;             /* dense_k^2 per basis */
+    BluKey2 *dn_key;            /* dense_k^2 per basis: (position key in its column, position key in its row) */
+    unsigned *dn_rbits, *dn_cbits; /* dense_k * dense_k/32 each per basis */
     BluInfo *info;              /* nmat */
 };
 

@@ -46,6 +46,7 @@ enum {
     BLU_P_REALLOC_FACTOR, BLU_P_L_MEM, BLU_P_U_MEM, BLU_P_W_MEM,
     BLU_P_THREADS_PER_BASIS,            /* CTA size of the factorization kernel (32..1024) */
     BLU_P_NORMS,                        /* 1 (default): factorize also runs condest x2 + residual_test as factorize.rs:121-147 does; 0: skip them (their getters then read 0) */
+    BLU_P_DENSE_K,                      /* order at which the active submatrix switches to the dense-tail representation (multiple of 32, <= 4096; 0 = never; default 256).  Results do not depend on it. */
     BLU_I_M = 100, BLU_I_RANK, BLU_I_BUMP_SIZE, BLU_I_BUMP_NZ, BLU_I_MATRIX_NZ, BLU_I_L_NZ,
     BLU_I_U_NZ, BLU_I_R_NZ, BLU_I_NSEARCH_PIVOT, BLU_I_NEXPAND, BLU_I_NGARBAGE,
     BLU_I_FACTOR_FLOPS, BLU_I_MIN_PIVOT, BLU_I_MAX_PIVOT, BLU_I_MAX_ETA, BLU_I_NUPDATE,
@@ -55,8 +56,8 @@ enum {
     BLU_I_ONENORM, BLU_I_INFNORM, BLU_I_RESIDUAL_TEST, BLU_I_PIVOT_ERROR, BLU_I_UPDATE_COST,
     BLU_I_TIME_FACTORIZE, BLU_I_TIME_SOLVE, BLU_I_TIME_UPDATE, BLU_I_ELIM_BYTES, BLU_I_NELIM_DIV,
     BLU_I_PIVOTLEN, BLU_I_RANKDEF, BLU_I_INTERNAL_ERROR, BLU_I_STATUS, BLU_I_NREALLOC,
-    BLU_I_T_PHASE0 = 200, /* +0..11: SM cycles per phase of the factorization kernel (diagnostic) */
-    BLU_I_N_KIND0 = 220,  /* +0..4: pivots taken by singleton-row / singleton-col / doubleton / small / any */
+    BLU_I_T_PHASE0 = 200, /* +0..15: SM cycles per phase of the factorization kernel (diagnostic) */
+    BLU_I_N_KIND0 = 220,  /* +0..4: pivots taken by singleton-row / singleton-col / doubleton / small / any; +5: of those, steps taken in the dense tail; +6: entries into it */
     BLU_I_NORMS_CYC0 = 230 /* +0..3: SM cycles of condest(L), condest(U), residual forward, residual transposed (diagnostic) */
 };
 
