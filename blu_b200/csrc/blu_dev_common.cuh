@@ -24,7 +24,6 @@ static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x
 #define STAMP_BITS 40
 #define MAXROW_SMALL 64 /* pivot.rs:22 */
 #define MAXCAND 32      /* upper bound on maxsearch honoured by the search kernel */
-#define SMARK_MAX 8192   /* largest m whose row/column marks are kept in shared memory */
 
 /* per-slot view of BluDev */
 struct Mat {
@@ -127,11 +126,12 @@ struct Shm {
     int kd, kw;               /* slots per side (multiple of 32) and words per bitmap row */
     int nrs, ncs;             /* row / column slots handed out at entry */
     int dpt, dpc;             /* slots of the pivot row / column */
-    unsigned ekc, ekr;        /* next storage-order key of a column entry / a row entry */
+    unsigned epoch;           /* number of the next dense step (storage-order keys, BluKey2) */
     int dense_entries, dense_block_rank;
-    u64 *skeyc, *scm; double *cvalp; int *drow, *dcol; unsigned *keyc, *keyr;
-    unsigned *cmask, *rmask, *rfull;
-    unsigned short *clist, *rlist, *posr, *rnz, *cnz, *tmps, *tmpr;
+    int mode, suspend;        /* BLU_MODE_*; 1 = park for the tail kernel, 2 = park for the build kernel */
+    int dv_smem;              /* the launch has room for the dense values and bitmaps in shared memory */
+    int lput, uput;           /* fill pointers of L and U (= l_begin_p[rank], u_begin[rank]) */
+    int dpcand;               /* stash row of the pivot column's keys (-1: none) */
 };
 
 template <int NT> __device__ __forceinline__ void bsync() {

@@ -288,12 +288,6 @@ __device__ __forceinline__ void shm_carve(Shm &S, unsigned char *dyn, int cap, i
         S.cm = (unsigned char *)(S.rm + ((m + 1) & ~1));
     }
 }
-static inline size_t blu_factor_smem_bytes(int cap, int nw, int m) {
-    size_t n = (size_t)cap * 8 + (size_t)nw * cap * 8 + (size_t)cap * 4 * 2;
-    if (m <= SMARK_MAX) n += (size_t)cap * 4 * 6 + (size_t)((m + 1) & ~1) * 2 + (size_t)((m + 15) & ~15);
-    return n;
-}
-
 #ifndef FACT_MINB
 /* resident CTAs per SM the register allocation is sized for.  Measured on B200 with 128-thread
  * CTAs (profiles/r1b_sweep.txt, r1h_sweep.txt): 4 CTAs/SM (128 registers) 7.3 k bases/s, 6 (80) 8.6 k,
@@ -301,52 +295,79 @@ static inline size_t blu_factor_smem_bytes(int cap, int nw, int m) {
  * pays until the spills cost more than the extra warps hide. */
 #define FACT_MINB(NT) (896 / (NT) > 0 ? 896 / (NT) : 1)
 #endif
-template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factorize(BluDev D, int cap) {
+/* mode (blu_types.h): BLU_MODE_WHOLE runs everything; HEAD stops where the dense tail would begin and parks
+ * the basis (status BLU_SUSPENDED_TAIL); TAIL resumes parked bases, finishes the pivot loop and parks them
+ * for BUILD, which assembles the factors.  dense_kd: order of the dense tail for this factorization;
+ * dense_smem != 0: the launch has room for the dense values in shared memory. */
+template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factorize(BluDev D, int cap, int mode, int dense_kd, int dense_smem) {
     BLU_DYN_SMEM(dyn);
     __shared__ Shm S;
     const int tid = threadIdx.x;
     for (int s = D.slot0 + blockIdx.x; s < D.slot0 + D.nslot; s += gridDim.x) {
+        const bool fresh = mode == BLU_MODE_WHOLE || mode == BLU_MODE_HEAD;
+        if (!fresh && D.info[s].status != (mode == BLU_MODE_TAIL ? BLU_SUSPENDED_TAIL : BLU_SUSPENDED_BUILD)) continue;
         if (tid == 0) {
             mat_view(S.M, D, s);
             shm_carve(S, dyn, cap, NT / 32, D.m);
             BluInfo *I = S.M.info;
-            /* LU::reset, lu.rs:329-396 (cumulative counters survive) */
-            I->m = D.m;
-            I->nupdate = -1; I->nforrest = 0; I->l_nz = I->u_nz = I->r_nz = 0;
-            I->min_pivot = I->max_pivot = I->max_eta = 0.0;
-            I->update_cost_numer = 0.0; I->update_cost_denom = 1.0;
-            I->l_flops = I->u_flops = I->r_flops = 0;
-            I->matrix_nz = 0; I->rank = 0; I->bump_size = 0; I->bump_nz = 0;
-            I->nsearch_pivot = I->nexpand = I->ngarbage = I->factor_flops = 0;
-            I->pivot_error = 0.0; I->ftran_for_update = I->btran_for_update = -1;
-            I->marker = 0; I->pivotlen = 0; I->rankdef = 0;
-            I->addmem_l = I->addmem_u = I->addmem_w = 0;
-            I->internal_error = 0; I->elim_bytes = 0.0; I->nelim_div = 0; I->have_ur = 0;
-            I->condest_l = I->condest_u = I->norm_l = I->norm_u = 0.0;
-            I->normest_l_inv = I->normest_u_inv = I->onenorm = I->infnorm = I->residual_test = 0.0;
             S.status = BLU_OK;
-            S.rank = 0; S.rankdef = 0; S.need_remove = 0;
-            S.nexpand = 0; S.ngarbage = 0; S.nsearch = 0; S.factor_flops = 0;
-            S.elim_bytes = 0.0; S.nelim_div = 0;
-            S.w_used = 0; S.w_limit = (int)D.w_mem; S.w_half = 0;
+            S.need_remove = 0;
             S.wc = -1; S.wr = -1;
-            S.dyn = dyn; S.dense = 0; S.kd = D.dense_k; S.kw = D.dense_k / 32;
-            S.dense_entries = 0; S.dense_block_rank = 0;
-            for (int q = 0; q < 16; q++) S.t_phase[q] = 0;
-            for (int q = 0; q < 8; q++) S.n_kind[q] = 0;
+            S.dyn = dyn; S.dense = 0; S.kd = dense_kd; S.kw = dense_kd / 32; S.dv_smem = dense_smem;
+            S.mode = mode; S.suspend = 0;
+            if (fresh) {
+                /* LU::reset, lu.rs:329-396 (cumulative counters survive) */
+                I->m = D.m;
+                I->nupdate = -1; I->nforrest = 0; I->l_nz = I->u_nz = I->r_nz = 0;
+                I->min_pivot = I->max_pivot = I->max_eta = 0.0;
+                I->update_cost_numer = 0.0; I->update_cost_denom = 1.0;
+                I->l_flops = I->u_flops = I->r_flops = 0;
+                I->matrix_nz = 0; I->rank = 0; I->bump_size = 0; I->bump_nz = 0;
+                I->nsearch_pivot = I->nexpand = I->ngarbage = I->factor_flops = 0;
+                I->pivot_error = 0.0; I->ftran_for_update = I->btran_for_update = -1;
+                I->marker = 0; I->pivotlen = 0; I->rankdef = 0;
+                I->addmem_l = I->addmem_u = I->addmem_w = 0;
+                I->internal_error = 0; I->elim_bytes = 0.0; I->nelim_div = 0; I->have_ur = 0;
+                I->condest_l = I->condest_u = I->norm_l = I->norm_u = 0.0;
+                I->normest_l_inv = I->normest_u_inv = I->onenorm = I->infnorm = I->residual_test = 0.0;
+                S.rank = 0; S.rankdef = 0;
+                S.nexpand = 0; S.ngarbage = 0; S.nsearch = 0; S.factor_flops = 0;
+                S.elim_bytes = 0.0; S.nelim_div = 0;
+                S.w_used = 0; S.w_limit = (int)D.w_mem; S.w_half = 0;
+                S.dense_entries = 0; S.dense_block_rank = 0;
+                for (int q = 0; q < 16; q++) S.t_phase[q] = 0;
+                for (int q = 0; q < 8; q++) S.n_kind[q] = 0;
+            } else {
+                /* pick up where the previous launch parked this basis */
+                S.rank = I->rank; S.rankdef = I->rankdef;
+                S.nexpand = (int)I->nexpand; S.ngarbage = (int)I->ngarbage; S.nsearch = I->nsearch_pivot; S.factor_flops = I->factor_flops;
+                S.elim_bytes = I->elim_bytes; S.nelim_div = I->nelim_div;
+                S.w_half = I->w_half; S.w_used = (int)I->w_used; S.w_limit = (S.w_half + 1) * (int)D.w_mem;
+                S.cstamp = I->cstamp; S.rstamp = I->rstamp;
+                S.nact = I->nact; S.ndead = I->ndead;
+                S.dense_entries = I->dense_entries; S.dense_block_rank = I->dense_block_rank;
+                for (int q = 0; q < 16; q++) S.t_phase[q] = I->t_phase[q];
+                for (int q = 0; q < 8; q++) S.n_kind[q] = I->n_kind[q];
+            }
         }
         bsync<NT>();
-        for (int i = tid; i < D.m; i += NT) S.M.marked[i] = 0;
+        if (fresh) for (int i = tid; i < D.m; i += NT) S.M.marked[i] = 0;
         if (S.smarks) for (int i = tid; i < D.m; i += NT) { S.rm[i] = 0; S.cm[i] = 0; }
         const i64 tstart = clock64();
-        phase_singletons<NT>(S);
-        i64 t0 = clock64();
-        if (S.status == BLU_OK) phase_setup_bump<NT>(S);
-        if (tid == 0) S.t_phase[2] += clock64() - t0;
-        if (S.status == BLU_OK) phase_bump<NT>(S);
+        i64 t0;
+        if (fresh) {
+            phase_singletons<NT>(S);
+            t0 = clock64();
+            if (S.status == BLU_OK) phase_setup_bump<NT>(S);
+            if (tid == 0) S.t_phase[2] += clock64() - t0;
+        } else bsync<NT>();
+        if (S.status == BLU_OK && mode != BLU_MODE_BUILD) {
+            phase_bump<NT>(S);
+            if (mode == BLU_MODE_TAIL && S.status == BLU_OK) { bsync<NT>(); if (tid == 0) S.suspend = 2; bsync<NT>(); }
+        }
         t0 = clock64();
-        if (S.status == BLU_OK) phase_build_factors<NT>(S);
-        if (tid == 0) { S.t_phase[9] += clock64() - t0; S.t_phase[11] = clock64() - tstart; }
+        if (S.status == BLU_OK && !S.suspend) phase_build_factors<NT>(S);
+        if (tid == 0) { if (!S.suspend) S.t_phase[9] += clock64() - t0; S.t_phase[11] += clock64() - tstart; }
         bsync<NT>();
         if (tid == 0) {
             BluInfo *I = S.M.info;
@@ -356,10 +377,13 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
             I->elim_bytes = S.elim_bytes; I->nelim_div = S.nelim_div;
             I->w_half = S.w_half; I->w_used = S.w_used;
             I->cstamp = S.cstamp; I->rstamp = S.rstamp;
+            I->nact = S.nact; I->ndead = S.ndead;
+            I->dense_entries = S.dense_entries; I->dense_block_rank = S.dense_block_rank;
             for (int q = 0; q < 16; q++) I->t_phase[q] = S.t_phase[q];
             for (int q = 0; q < 8; q++) I->n_kind[q] = S.n_kind[q];
             int st = S.status;
-            if (st == BLU_OK) {
+            if (st == BLU_OK && S.suspend) st = S.suspend == 1 ? BLU_SUSPENDED_TAIL : BLU_SUSPENDED_BUILD;
+            else if (st == BLU_OK) {
                 I->nupdate = 0; I->nfactorize++;
                 /* cost model, factorize.rs:160-166 */
                 double factor_cost = 0.04 * (double)D.m + 0.07 * (double)I->matrix_nz + 0.20 * (double)I->bump_nz +

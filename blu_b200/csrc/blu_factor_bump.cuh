@@ -326,9 +326,12 @@ __device__ __forceinline__ void finish_step(Shm &S, int rank, int lput, int uput
     const int m = M.m, pc = S.pivot_col, pr = S.pivot_row;
     M.l_begin_p[rank + 1] = lput;
     M.u_begin[rank + 1] = uput;
+    S.lput = lput; S.uput = uput;
     M.colpiv[pc] = pivot;
-    M.lend[pc] = M.lbeg[pc];
-    M.lend[m + pr] = M.lbeg[m + pr];
+    if (!S.dense) {      /* (the dense tail rebuilds the line table when it ends) */
+        M.lend[pc] = M.lbeg[pc];
+        M.lend[m + pr] = M.lbeg[m + pr];
+    }
     M.ckey[pc] = KEY_INF;
     M.rkey[pr] = KEY_INF;
     S.ndead++;
@@ -1303,51 +1306,70 @@ template <int NT> __device__ void pivot_doubleton_col(Shm &S) {
 /* ------------------------------------------------------------------ */
 #define DENSE_MIN_ROWS 4      /* the last pivots are singletons / doubletons: not worth a conversion */
 #define DENSE_MAX_ENTRIES 8   /* conversions per factorization (each costs O(kd^2)) */
+/* dense-tail dispatch: RES (values in shared memory) is a launch property, uniform over the block */
+template <int NT> __device__ __forceinline__ void dense_enter_d(Shm &S) { if (S.dv_smem) dense_enter<NT, true>(S); else dense_enter<NT, false>(S); }
+template <int NT> __device__ __forceinline__ void dense_exit_d(Shm &S) { if (S.dv_smem) dense_exit<NT, true>(S); else dense_exit<NT, false>(S); }
+template <int NT> __device__ __forceinline__ void dense_search_d(Shm &S) { if (S.dv_smem) dense_search<NT, true>(S); else dense_search<NT, false>(S); }
+template <int NT> __device__ __forceinline__ void dense_pivot_d(Shm &S, bool small) {
+    if (S.dv_smem) { if (small) dense_pivot<NT, true, true>(S); else dense_pivot<NT, true, false>(S); }
+    else { if (small) dense_pivot<NT, false, true>(S); else dense_pivot<NT, false, false>(S); }
+}
+
 template <int NT> __device__ void phase_bump(Shm &S) {
     Mat &M = S.M;
     const int m = M.m, tid = threadIdx.x;
+    BLU_DYN_SMEM(dyn_);
+    DenseSm dsm; dense_view(dsm, dyn_, S.kd, S.kw);
+    if (tid == 0) { S.lput = M.l_begin_p[S.rank]; S.uput = M.u_begin[S.rank]; }
+    bsync<NT>();
     while (S.rank + S.rankdef < m) {
         i64 t0 = clock64();
         if (!S.dense && S.kd > 0 && m - S.rank <= S.kd && m - S.rank >= DENSE_MIN_ROWS &&
             S.rank >= S.dense_block_rank && S.dense_entries < DENSE_MAX_ENTRIES && M.prm.search_rows == 0) {
-            dense_enter<NT>(S);
+            if (S.mode == BLU_MODE_HEAD) {      /* the tail kernel takes over from here */
+                bsync<NT>();
+                if (tid == 0) S.suspend = 1;
+                bsync<NT>();
+                return;
+            }
+            dense_enter_d<NT>(S);
             if (tid == 0) S.t_phase[13] += clock64() - t0;
             if (S.status != BLU_OK) return;
             t0 = clock64();
         }
-        if (S.dense) dense_search<NT>(S); else markowitz_search<NT>(S);
-        if (tid == 0) S.t_phase[3] += clock64() - t0;
+        if (S.dense) dense_search_d<NT>(S); else markowitz_search<NT>(S);
+        if (tid == 0) { if (S.dense) S.t_phase[13] += clock64() - t0; else S.t_phase[3] += clock64() - t0; }
         if (S.status != BLU_OK) return;
         const int pc = S.pivot_col, pr = S.pivot_row;
         if (pr < 0) {
             /* empty column: drop it, no pivot (factorize_bump.rs:23-31) */
             bsync<NT>();
-            if (tid == 0) { M.ckey[pc] = KEY_INF; if (S.dense) S.skeyc[S.dpc] = KEY_INF; S.ndead++; S.rankdef++; }
+            if (tid == 0) { M.ckey[pc] = KEY_INF; if (S.dense) dsm.skeyc[S.dpc] = KEY_INF; S.ndead++; S.rankdef++; }
             bsync<NT>();
             continue;
         }
         const int rank = S.rank;
-        const int nz_col = S.dense ? (int)S.cnz[S.dpc] : M.lend[pc] - M.lbeg[pc];
-        const int nz_row = S.dense ? (int)S.rnz[S.dpt] : M.lend[m + pr] - M.lbeg[m + pr];
-        /* room in L and U, pivot.rs:69-81 */
+        const int nz_col = S.dense ? (int)dsm.cnz[S.dpc] : M.lend[pc] - M.lbeg[pc];
+        const int nz_row = S.dense ? (int)dsm.rnz[S.dpt] : M.lend[m + pr] - M.lbeg[m + pr];
+        /* room in L and U, pivot.rs:69-81 (S.lput / S.uput mirror l_begin_p[rank] / u_begin[rank]) */
         {
-            int room = M.l_mem - M.l_begin_p[rank];
+            int room = M.l_mem - S.lput;
             int st = BLU_OK;
             if (room < nz_col) { if (tid == 0) M.info->addmem_l = nz_col - room; st = BLU_REALLOCATE; }
-            room = M.u_mem - M.u_begin[rank];
+            room = M.u_mem - S.uput;
             if (room < nz_row - 1) { if (tid == 0) M.info->addmem_u = nz_row - 1 - room; st = BLU_REALLOCATE; }
             if (st != BLU_OK) { bsync<NT>(); if (tid == 0) S.status = st; bsync<NT>(); return; }
         }
         t0 = clock64();
         if (S.dense) {
-            if (nz_row > 1 && nz_col > 2) {
+            if (nz_row > 1 && nz_col > 2 && S.epoch < 255) {      /* (eight bits of epoch in the keys) */
                 const bool small = nz_col - 1 <= MAXROW_SMALL;
-                dense_pivot<NT>(S, small);
+                dense_pivot_d<NT>(S, small);
                 if (tid == 0) { S.t_phase[12] += clock64() - t0; S.n_kind[small ? 3 : 4]++; }
                 if (S.status != BLU_OK) return;
                 if (S.need_remove) {      /* pivot.rs:96-106 works on the line file */
                     t0 = clock64();
-                    dense_exit<NT>(S);
+                    dense_exit_d<NT>(S);
                     if (tid == 0) S.t_phase[13] += clock64() - t0;
                     if (S.status != BLU_OK) return;
                     t0 = clock64();
@@ -1358,7 +1380,7 @@ template <int NT> __device__ void phase_bump(Shm &S) {
                 continue;
             }
             /* singleton row / column or doubleton column: back to the line file, same pivot */
-            dense_exit<NT>(S);
+            dense_exit_d<NT>(S);
             if (tid == 0) S.t_phase[13] += clock64() - t0;
             if (S.status != BLU_OK) return;
             t0 = clock64();

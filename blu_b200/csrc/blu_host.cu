@@ -8,7 +8,7 @@
 #endif
 #include "blu_types.h"
 #include "blu_dev_common.cuh"
-#include "blu_factor_build.cuh"
+#include "blu_fact_launch.h"
 #include "blu_solve.cuh"
 #include "blu_sparse.cuh"
 
@@ -27,6 +27,10 @@ struct blu_b200 {
     BluDev d;
     double realloc_factor;
     int nthreads;               /* CTA size of the factorization kernel */
+    int tail_threads;           /* CTA size of the dense-tail launch of a split batch factorization */
+    int num_sms, smem_optin;    /* device properties */
+    int kd_smem_max;            /* largest dense-tail order whose values fit in shared memory */
+    int split_min;              /* batches of more bases than this run as head / tail / build launches */
     int cap;                    /* smem line cache entries */
     std::vector<void *> allocs; /* every device allocation */
     std::vector<void **> store_ptrs;
@@ -121,10 +125,11 @@ static int alloc_dense(blu_b200 *o, int want) {
     const int mcap = (d.m + 31) & ~31;
     if (kd > mcap) kd = mcap;
     kd &= ~31;
-    if (kd > 4096) kd = 4096;
+    if (kd > BLU_DENSE_K_MAX) kd = BLU_DENSE_K_MAX;
     d.dense_k = kd;
     const size_t n = (size_t)d.nmat, k = (size_t)kd;
-    int st = dalloc(o, &d.dn_val, n * k * k);
+    /* up to kd_smem_max the values live in shared memory (blu_factor_dense.cuh); beyond, in HBM */
+    int st = dalloc(o, &d.dn_val, kd > o->kd_smem_max ? n * k * k : 1);
     if (st == BLU_OK) st = dalloc(o, &d.dn_key, n * k * k);
     if (st == BLU_OK) st = dalloc(o, &d.dn_rbits, n * k * (k / 32));
     if (st == BLU_OK) st = dalloc(o, &d.dn_cbits, n * k * (k / 32));
@@ -143,7 +148,14 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     blu_b200 *o = new blu_b200();
     o->device = device; o->single = single;
     o->realloc_factor = 1.5;   /* blu.rs:68 */
-    o->nthreads = 128; o->cap = 256;
+    o->nthreads = 128; o->cap = 256; o->tail_threads = 512;
+    o->num_sms = 148; o->smem_optin = 232448;
+    cudaDeviceGetAttribute(&o->num_sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&o->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    o->kd_smem_max = 0;
+    for (int kd = 32; kd <= BLU_DENSE_K_MAX; kd += 32)
+        if (blu_dense_smem_bytes_resident(kd) + 4096 /* static Shm */ <= (size_t)o->smem_optin) o->kd_smem_max = kd;
+    o->split_min = o->num_sms;
     if (const char *e = getenv("BLU_B200_CAP")) { int c = atoi(e); if (c >= 64 && c <= 4096) o->cap = c & ~31; }   /* tuning knob: entries of the shared-memory line caches */
     o->launches = 0; o->nrealloc = 0; o->last_ms[0] = o->last_ms[1] = 0.0;
     o->have_b = 0; o->info_dirty = 0; o->norms = 1; o->last_norms_ms = 0.0;
@@ -191,7 +203,7 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     o->gf_i = nullptr; o->gf_x = nullptr; o->gf_cap = 0;
     if (st == BLU_OK) st = alloc_stores(o);
     if (st == BLU_OK) {
-        int kd = 256;
+        int kd = o->kd_smem_max;
         if (const char *e = getenv("BLU_B200_DENSE_K")) kd = atoi(e);      /* tuning knob, same as BLU_P_DENSE_K */
         st = alloc_dense(o, kd);
     }
@@ -274,28 +286,39 @@ static void timer_stop(blu_b200 *o, int which) {
 #endif
 }
 
-template <int NT> static int launch_factorize_nt(blu_b200 *o, cudaStream_t stream, int slot0, int nslot) {
-    size_t smem = blu_factor_smem_bytes(o->cap, NT / 32, o->d.m);
-    if (o->d.dense_k > 0) smem = std::max(smem, blu_dense_smem_bytes(o->d.dense_k));
-#ifndef BLU_EMU
-    /* static + dynamic shared memory beyond 48 KB needs the opt-in (the static part is ~2.2 KB) */
-    if (smem > 40 * 1024) CK(cudaFuncSetAttribute(k_factorize<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
+static int launch_factorize_mode(blu_b200 *o, cudaStream_t stream, int slot0, int nslot, int nt, int mode) {
+    const int kd = o->d.dense_k;
+    const bool dense_here = kd > 0 && (mode == BLU_MODE_WHOLE || mode == BLU_MODE_TAIL);
+    const bool resident = dense_here && kd <= o->kd_smem_max;
+    if (nt != 32 && nt != 64 && nt != 256 && nt != 512 && nt != 1024) nt = 128;
+    size_t smem = blu_factor_smem_bytes(o->cap, nt / 32, o->d.m);
+    if (dense_here) smem = std::max(smem, resident ? blu_dense_smem_bytes_resident(kd) : blu_dense_smem_bytes(kd));
     BluDev dv = o->d; dv.slot0 = slot0; dv.nslot = nslot;
-    BLU_LAUNCH(k_factorize<NT>, nslot, NT, smem, stream, dv, o->cap);
+    int e;
+    switch (nt) {
+    case 32: e = blu_launch_factorize_32(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, smem); break;
+    case 64: e = blu_launch_factorize_64(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, smem); break;
+    case 256: e = blu_launch_factorize_256(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, smem); break;
+    case 512: e = blu_launch_factorize_512(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, smem); break;
+    case 1024: e = blu_launch_factorize_1024(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, smem); break;
+    default: e = blu_launch_factorize_128(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, smem); break;
+    }
     o->launches++;
-    CK(cudaGetLastError());
+    CK((cudaError_t)e);
     return BLU_OK;
 }
+/* One launch for a single basis or a small batch.  A large batch whose dense tail fits in shared memory runs
+ * as three launches: the sparse head wants many small CTAs per SM (the pivot loop is a latency chain), the
+ * tail one CTA per SM with the whole active submatrix on chip, build_factors many small CTAs again. */
 static int launch_factorize(blu_b200 *o, cudaStream_t stream, int slot0, int nslot) {
-    switch (o->nthreads) {
-    case 32: return launch_factorize_nt<32>(o, stream, slot0, nslot);
-    case 64: return launch_factorize_nt<64>(o, stream, slot0, nslot);
-    case 256: return launch_factorize_nt<256>(o, stream, slot0, nslot);
-    case 512: return launch_factorize_nt<512>(o, stream, slot0, nslot);
-    case 1024: return launch_factorize_nt<1024>(o, stream, slot0, nslot);
-    default: return launch_factorize_nt<128>(o, stream, slot0, nslot);
+    const int kd = o->d.dense_k;
+    if (kd > 0 && kd <= o->kd_smem_max && nslot > o->split_min) {
+        int st = launch_factorize_mode(o, stream, slot0, nslot, o->nthreads, BLU_MODE_HEAD);
+        if (st == BLU_OK) st = launch_factorize_mode(o, stream, slot0, nslot, o->tail_threads, BLU_MODE_TAIL);
+        if (st == BLU_OK) st = launch_factorize_mode(o, stream, slot0, nslot, o->nthreads, BLU_MODE_BUILD);
+        return st;
     }
+    return launch_factorize_mode(o, stream, slot0, nslot, o->nthreads, BLU_MODE_WHOLE);
 }
 
 static int fetch_info(blu_b200 *o) {
@@ -645,18 +668,20 @@ extern "C" int blu_set_param(blu_t *o, int what, double v) {
     case BLU_P_REALLOC_FACTOR: o->realloc_factor = v; break;
     case BLU_P_NORMS: o->norms = v != 0.0; break;
     case BLU_P_DENSE_K: {
-        if (v < 0 || v > 4096) return BLU_ERROR_INVALID_ARGUMENT;
+        if (v < 0 || v > BLU_DENSE_K_MAX) return BLU_ERROR_INVALID_ARGUMENT;
         if (cudaSetDevice(o->device) != cudaSuccess) return BLU_ERROR_CUDA;
         cudaStreamSynchronize(o->stream);
         int st = alloc_dense(o, (int)v);
         if (st != BLU_OK) return st;
         break;
     }
-    case BLU_P_THREADS_PER_BASIS: {
+    case BLU_P_THREADS_PER_BASIS: case BLU_P_TAIL_THREADS: {
         int t = (int)v;
         if (t != 32 && t != 64 && t != 128 && t != 256 && t != 512 && t != 1024) return BLU_ERROR_INVALID_ARGUMENT;
-        o->nthreads = t; break;
+        if (what == BLU_P_TAIL_THREADS) o->tail_threads = t; else o->nthreads = t;
+        break;
     }
+    case BLU_P_SPLIT_MIN: o->split_min = (int)v; break;
     case BLU_P_L_MEM: case BLU_P_U_MEM: case BLU_P_W_MEM: {
         int64_t n = (int64_t)v;
         if (n < 1) return BLU_ERROR_INVALID_ARGUMENT;
@@ -696,6 +721,8 @@ extern "C" double blu_get_param(const blu_t *o, int what) {
     case BLU_P_W_MEM: return (double)o->d.w_mem;
     case BLU_P_THREADS_PER_BASIS: return o->nthreads;
     case BLU_P_DENSE_K: return o->d.dense_k;
+    case BLU_P_TAIL_THREADS: return o->tail_threads;
+    case BLU_P_SPLIT_MIN: return o->split_min;
     default: return 0.0;
     }
 }

@@ -18,12 +18,17 @@
 #ifndef BLU_TYPES_H
 #define BLU_TYPES_H
 #include <stdint.h>
+#include <stddef.h>
 
 typedef unsigned long long blu_u64;
 typedef long long blu_i64;
 
-/* storage-order keys of one entry of the dense tail */
-struct BluKey2 { unsigned c, r; };
+/* storage-order keys of one entry of the dense tail: (epoch << 8 | position), epoch = number of the dense
+ * step that wrote the entry (0 = as found in the line file), position = place in that step's pivot column
+ * (.c) / pivot row (.r).  Eight bits each: at most 255 steps and lines of at most 256 entries, hence
+ * dense_k <= 256. */
+struct BluKey2 { unsigned short c, r; };
+#define BLU_DENSE_K_MAX 256
 
 /* lu.rs:17-66, defaults lu.rs:250-259 */
 struct BluParams {
@@ -44,6 +49,7 @@ struct BluInfo {
     int nact;               /* entries of the active-column list */
     int internal_error;     /* line number of a failed device-side invariant, 0 = none */
     int have_ur;            /* the sorted row-wise copy of U (ur_*) matches the current factors */
+    int ndead, dense_entries, dense_block_rank; /* pivot-loop cursors carried from one kernel of a split factorization to the next */
     blu_i64 matrix_nz, bump_nz, l_nz, u_nz, r_nz;
     blu_i64 nsearch_pivot, nexpand, ngarbage, factor_flops;
     blu_i64 l_flops, u_flops, r_flops;
@@ -112,7 +118,38 @@ struct BluDev {
     BluInfo *info;              /* nmat */
 };
 
+/* shared-memory budgets of k_factorize (host and device agree on the carve-up) */
+#define SMARK_MAX 8192   /* largest m whose row/column marks are kept in shared memory */
+#define DENSE_STASH 4    /* candidate columns whose keys the dense-tail search leaves in shared memory for the pivot step */
+#if defined(__CUDACC__)
+#define BLU_HD __host__ __device__ static inline
+#else
+#define BLU_HD static inline
+#endif
+BLU_HD size_t blu_factor_smem_bytes(int cap, int nw, int m) {
+    size_t n = (size_t)cap * 8 + (size_t)nw * cap * 8 + (size_t)cap * 4 * 2;
+    if (m <= SMARK_MAX) n += (size_t)cap * 4 * 6 + (size_t)((m + 1) & ~1) * 2 + (size_t)((m + 15) & ~15);
+    return n;
+}
+/* per-step arrays of the dense tail (always in shared memory) */
+BLU_HD size_t blu_dense_smem_bytes(int kd) {
+    return (((size_t)kd * (3 * 8 + 4 * 4 + 7 * 2 + DENSE_STASH * 4) + (size_t)(kd / 32) * 3 * 4) + 15) & ~(size_t)15;
+}
+/* with the presence bitmaps and the values in shared memory as well */
+BLU_HD size_t blu_dense_smem_bytes_resident(int kd) {
+    return blu_dense_smem_bytes(kd) + (size_t)2 * kd * (kd / 32) * 4 + (size_t)kd * kd * 8;
+}
+
 /* status codes live in the public header */
 #include "blu_b200.h"
+/* A batch factorization runs as three launches (blu_factor_build.cuh, k_factorize): the sparse head with many
+ * small CTAs per SM, the dense tail with one CTA per SM and the active submatrix in shared memory, then
+ * build_factors.  Between launches a basis is parked with one of these internal codes (never returned). */
+#define BLU_SUSPENDED_TAIL 101
+#define BLU_SUSPENDED_BUILD 102
+#define BLU_MODE_WHOLE 0
+#define BLU_MODE_HEAD 1
+#define BLU_MODE_TAIL 2
+#define BLU_MODE_BUILD 3
 
 #endif

@@ -46,7 +46,9 @@ enum {
     BLU_P_REALLOC_FACTOR, BLU_P_L_MEM, BLU_P_U_MEM, BLU_P_W_MEM,
     BLU_P_THREADS_PER_BASIS,            /* CTA size of the factorization kernel (32..1024) */
     BLU_P_NORMS,                        /* 1 (default): factorize also runs condest x2 + residual_test as factorize.rs:121-147 does; 0: skip them (their getters then read 0) */
-    BLU_P_DENSE_K,                      /* order at which the active submatrix switches to the dense-tail representation (multiple of 32, <= 4096; 0 = never; default 256).  Results do not depend on it. */
+    BLU_P_DENSE_K,                      /* order at which the active submatrix switches to the dense-tail representation (multiple of 32, <= 256; 0 = never; default: the largest order whose values fit in shared memory, 160 on B200).  Results do not depend on it. */
+    BLU_P_TAIL_THREADS,                 /* CTA size of the dense-tail launch of a split batch factorization (default 512) */
+    BLU_P_SPLIT_MIN,                    /* batches of more bases than this run as three launches: sparse head, dense tail with one CTA per SM, build_factors (default: the SM count) */
     BLU_I_M = 100, BLU_I_RANK, BLU_I_BUMP_SIZE, BLU_I_BUMP_NZ, BLU_I_MATRIX_NZ, BLU_I_L_NZ,
     BLU_I_U_NZ, BLU_I_R_NZ, BLU_I_NSEARCH_PIVOT, BLU_I_NEXPAND, BLU_I_NGARBAGE,
     BLU_I_FACTOR_FLOPS, BLU_I_MIN_PIVOT, BLU_I_MAX_PIVOT, BLU_I_MAX_ETA, BLU_I_NUPDATE,

@@ -1,5 +1,5 @@
 """Tuning sweep, not a test: k_factorize of the configs[1] batch for several dense-tail orders and CTA sizes.
-usage: python scripts/sweep_factorize.py [nmat] [dense_k,dense_k,...] [threads,threads,...]
+usage: python scripts/sweep_factorize.py [nmat] [dense_k,dense_k,...] [threads,threads,...] [tail_threads,...]
 Prints ms per launch and the mean per-phase SM cycles of a sample of bases (BluInfo.t_phase)."""
 import os
 import sys
@@ -13,17 +13,19 @@ from blu_b200 import BLUBatch, gen  # noqa: E402
 nmat = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 kds = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 128, 256, 384, 512]
 nts = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [128]
+tails = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [512]
 M = 2000
 t0 = time.time()
 bb, be, bi, bx, rhs = gen.batch(nmat, M, 700, 5.0, 2000, 3000)
 print(f"generated {nmat} bases in {time.time() - t0:.1f} s", flush=True)
 cap = int((be - bb).reshape(nmat, M).sum(1).max())
-names = ["validate", "singl", "setup", "search", "p_srow", "p_scol", "p_dbl", "p_small", "p_any", "build", "remove", "total", "dense", "convert"]
-for nt in nts:
-    for kd in kds:
+names = ["validate", "singl", "setup", "search", "p_srow", "p_scol", "p_dbl", "p_small", "p_any", "build", "remove", "total", "dense", "dsearch+convert", "d_gather", "d_sweep"]
+for nt, kd, tail in [(a, b_, c) for a in nts for b_ in kds for c in (tails if b_ else tails[:1])]:
+    if True:
         b = BLUBatch(nmat, M, cap, device=0)
         b.threads_per_basis = nt
         b.dense_k = kd
+        b.tail_threads = tail
         b.l_mem = 100000; b.u_mem = 100000; b.w_mem = 900000
         assert b.upload(bb, be, bi, bx, rhs) == 0
         ms = []
@@ -31,10 +33,10 @@ for nt in nts:
             assert b.factorize_resident() == 0
             ms.append(b.last_kernel_ms(0) - b.last_kernel_ms(2))
         sample = range(0, nmat, max(1, nmat // 64))
-        ph = np.array([[b.info(k, f"t_phase{q}") for q in range(14)] for k in sample]).mean(0)
-        kinds = np.array([[b.info(k, f"n_kind{q}") for q in range(7)] for k in sample]).mean(0)
+        ph = np.array([[b.info(k, f"t_phase{q}") for q in range(16)] for k in sample]).mean(0)
+        kinds = np.array([[b.info(k, f"n_kind{q}") for q in range(8)] for k in sample]).mean(0)
         bad = sum(int(b.info(k, "status")) != 0 for k in sample)
-        print(f"nt {nt} dense_k {kd}: k_factorize {min(ms):.1f} ms (runs {[round(x, 1) for x in ms]}), norms {b.last_kernel_ms(2):.1f} ms, bad {bad}", flush=True)
+        print(f"nt {nt} dense_k {kd} tail {tail}: k_factorize {min(ms):.1f} ms (runs {[round(x, 1) for x in ms]}), norms {b.last_kernel_ms(2):.1f} ms, bad {bad}", flush=True)
         print("   kcycles/basis: " + " ".join(f"{n}={v / 1e3:.0f}" for n, v in zip(names, ph)), flush=True)
-        print("   pivots/basis: srow %.1f scol %.1f dbl %.1f small %.1f any %.1f | dense steps %.1f entries %.2f" % tuple(kinds), flush=True)
+        print("   pivots/basis: srow %.1f scol %.1f dbl %.1f small %.1f any %.1f | dense steps %.1f entries %.2f d_finish kcycles %.0f" % tuple(list(kinds[:7]) + [kinds[7] / 1e3]), flush=True)
         b.close()

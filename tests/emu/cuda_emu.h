@@ -32,6 +32,7 @@ extern emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __shared__ static
 #define __restrict__
 #define __launch_bounds__(...)
@@ -171,6 +172,8 @@ inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaGetDevice(int *d) { *d = 0; return 0; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
+enum { cudaDevAttrMultiProcessorCount = 16, cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
+inline cudaError_t cudaDeviceGetAttribute(int *v, int attr, int) { *v = attr == cudaDevAttrMultiProcessorCount ? 148 : 232448; return 0; }
 inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaPeekAtLastError() { return 0; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emu"; }

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.fixture(scope="module")
 def emu():
-    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emu")])
+    subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(HERE, "emu")])
     return load_library(os.path.join(HERE, "emu", "libblu_emu.so"))
 
 
@@ -274,3 +274,64 @@ def test_emu_structures(emu, seed, m):
 def test_emu_batch_structures(emu, m, seed0):
     from parity import batch_structured_case
     batch_structured_case(lambda n, m, cap: BLUBatch(n, m, cap, lib=emu), m, seed0)
+
+
+@pytest.mark.parametrize("kd,nt", [(0, 64), (32, 64), (64, 128), (160, 32), (256, 64)])
+def test_emu_dense_tail_orders(emu, kd, nt):
+    """The dense tail (blu_factor_dense.cuh) never changes a result: the same basis for several switch
+    orders -- 0 = sparse to the end, <= 160 = values in shared memory, larger = values in HBM -- pivot_any and
+    pivot_small both running inside it."""
+    m = 230
+    cp, ri, v = gen.basis(313, m, 0, 12.0, cap=60)
+    o = oracle_for(m, len(v), 400)
+    assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+    g = BLU(m, len(v), lib=emu)
+    g.threads_per_basis = nt
+    g.dense_k = kd
+    assert g.factorize(cp[:-1], cp[1:], ri, v) == 0
+    assert_factor_parity(g, o)
+    assert g.info("n_kind4") > 0 and g.info("n_kind3") > 0
+    steps = g.info("n_kind5")
+    assert (steps == 0) if kd == 0 else (steps >= min(kd, m) - 8)
+
+
+@pytest.mark.parametrize("kd,tail", [(64, 128), (160, 256)])
+def test_emu_split_batch(emu, kd, tail):
+    """A batch run as three launches (sparse head, dense tail with the active submatrix in shared memory,
+    build_factors: blu_factor_build.cuh k_factorize modes) equals the oracle basis by basis."""
+    from parity import STATS
+    nmat, m = 3, 170
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 30, 5.0, 9100, 9600)
+    b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()), lib=emu)
+    b.dense_k = kd; b.split_min = 0; b.threads_per_basis = 64; b.tail_threads = tail
+    l0 = b.launch_count()
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all()
+    assert b.launch_count() - l0 == 4       # head, tail, build + the condest/residual kernel
+    st, x, sst = b.solve_dense(rhs, "T")
+    assert st == 0 and (sst == 0).all()
+    for k in range(nmat):
+        cp, ri, v = gen.basis(9100 + k, m, 30, 5.0)
+        o = oracle_for(m, len(v), 400)
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        _, fo = o.get_factors()
+        _, fg = b.get_factors(k)
+        for key in fo:
+            assert np.array_equal(fo[key], fg[key]), (k, key)
+        for name in STATS:
+            assert o.info(name) == b.info(k, name), (k, name)
+        assert b.info(k, "n_kind5") > 0
+        _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "T")
+        assert np.array_equal(x[k], xo)
+
+
+def test_emu_dense_tail_structures(emu):
+    """Exact cancellation, rank deficiency and columns that fall below abstol inside the dense tail
+    (the paths that leave it early: dense_exit + pivot.rs:96-106 on the line file)."""
+    from parity import structured_case
+    os.environ["BLU_B200_DENSE_K"] = "64"
+    try:
+        for seed, m in [(9000, 120), (9003, 140), (9005, 90), (9006, 150), (9012, 100)]:
+            structured_case(lambda mm, nnz: BLU(mm, nnz, lib=emu), m, seed, nupd=2)
+    finally:
+        del os.environ["BLU_B200_DENSE_K"]

@@ -2,12 +2,14 @@
 same seeded inputs.  Bit-exact for pivots, permutations, rank, L/U patterns AND values, and for every
 solve (dense and sparse): the kernels perform the reference's roundings in the reference's order
 (no FMA, ordered sums), so np.array_equal is the bar -- the north star's 1e-12 is met with room."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
 
 from blu_b200 import BLU, BLUBatch, gen
-from parity import oracle_for, assert_factor_parity, assert_backward_error
+from parity import oracle_for, assert_factor_parity, assert_backward_error, structured_case
 
 pytestmark = pytest.mark.gpu
 
@@ -510,3 +512,63 @@ def test_batch_structures(m, seed0):
     """Different structures side by side in one batch, random tunables: every basis as if factorized alone."""
     from parity import batch_structured_case
     batch_structured_case(lambda n, m, cap: BLUBatch(n, m, cap), m, seed0)
+
+
+@pytest.mark.parametrize("kd", [0, 64, 160, 256])
+def test_dense_tail_orders(kd):
+    """configs[1] basis for several dense-tail switch orders (blu_factor_dense.cuh): 0 = sparse to the end,
+    <= 160 values in shared memory, 256 values in HBM.  Nothing observable may change."""
+    (cp, ri, v), rhs = gen.config2_matrix(5)
+    m = 2000
+    o = oracle_for(m, len(v))
+    assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+    g = BLU(m, len(v))
+    g.dense_k = kd
+    assert g.factorize(cp[:-1], cp[1:], ri, v) == 0
+    assert_factor_parity(g, o)
+    steps = g.info("n_kind5")
+    assert (steps == 0) if kd == 0 else (steps >= kd - 8)
+    _, xo = o.solve_dense(rhs, "N")
+    _, xg = g.solve_dense(rhs, "N")
+    assert np.array_equal(xg, xo)
+
+
+@pytest.mark.parametrize("kd,tail,nt", [(160, 512, 128), (96, 256, 64), (160, 1024, 256)])
+def test_split_batch_parity(kd, tail, nt):
+    """A batch large enough to run as head / tail / build launches (the bench path): every basis equals the
+    oracle, including the counters."""
+    from parity import STATS
+    nmat, m = 160, 600
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 200, 5.0, 9200, 9700)
+    b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()))
+    b.dense_k = kd; b.tail_threads = tail; b.threads_per_basis = nt; b.split_min = 100
+    l0 = b.launch_count()
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all()
+    assert b.launch_count() - l0 == 4
+    st, x, sst = b.solve_dense(rhs, "N")
+    assert st == 0 and (sst == 0).all()
+    for k in range(0, nmat, 13):
+        cp, ri, v = gen.basis(9200 + k, m, 200, 5.0)
+        o = oracle_for(m, len(v))
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        _, fo = o.get_factors()
+        _, fg = b.get_factors(k)
+        for key in fo:
+            assert np.array_equal(fo[key], fg[key]), (k, key)
+        for name in STATS:
+            assert o.info(name) == b.info(k, name), (k, name)
+        assert b.info(k, "n_kind5") > 0
+        _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
+        assert np.array_equal(x[k], xo)
+
+
+def test_dense_tail_structures():
+    """tests/parity.py structures (exact cancellation, rank deficiency, columns below abstol) with a small
+    dense-tail order so that the tail is entered, left early (dense_exit) and re-entered."""
+    os.environ["BLU_B200_DENSE_K"] = "64"
+    try:
+        for seed, m in [(9000, 300), (9003, 500), (9005, 400), (9006, 640), (9012, 350), (9018, 420)]:
+            structured_case(lambda mm, nnz: BLU(mm, nnz), m, seed, nupd=4)
+    finally:
+        del os.environ["BLU_B200_DENSE_K"]
