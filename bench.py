@@ -4,9 +4,10 @@
 Workload (BASELINE.json configs[1]): a batch of 4,096 independent 2,000 x 2,000 simplex-style
 bases (35 % slack columns, structural columns 1+Poisson(5) entries, synthetic, seeded), each
 basis = factorize + solve_dense('N').  A *step* is one pass over the whole batch.  The bases
-shard across GPUs by index with no data-path collective; under torchrun every
-rank owns a full 4,096-basis batch of its own seeds ("weak" scaling) and `value` is all ranks'
-bases divided by the max-over-ranks device time.
+shard across GPUs by index with no data-path collective (blu_b200/shard.py): under
+torchrun the ONE 4,096-basis batch of BASELINE.json is split into contiguous ranges of 4096/N bases
+per rank ("strong" scaling, the default; --scaling weak gives every rank its own 4,096) and `value` is
+all ranks' bases divided by the max-over-ranks device time.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]         # the CUDA path (libblu_b200.so)
     python bench.py --impl reference ...                         # the CPU restatement of rwl/blu
@@ -96,8 +97,10 @@ class ClockSampler(threading.Thread):
 def algorithmic_bytes(b, nmat, m):
     """bytes(factorize) = singletons + setup_bump + elimination + build_factors, from
     the device's own counters (the same ones the oracle keeps); 12 B per stored nonzero, 4 B per
-    pattern index or pointer, 8 B per vector element."""
-    tot_f = tot_s = 0.0
+    pattern index or pointer, 8 B per vector element.  Returns (whole factorization, the part done by the
+    head launch of a split factorization = singletons + setup_bump + its share of the elimination,
+    solve_dense)."""
+    tot_f = tot_h = tot_s = 0.0
     for k in range(nmat):
         nnz = b.info(k, "matrix_nz"); lnz = b.info(k, "l_nz"); unz = b.info(k, "u_nz")
         bump_nz = b.info(k, "bump_nz"); bump = b.info(k, "bump_size")
@@ -105,8 +108,20 @@ def algorithmic_bytes(b, nmat, m):
         setup = 12.0 * bump_nz + 16.0 * bump_nz + 16.0 * bump
         build = 48.0 * (lnz + unz) + 40.0 * m
         tot_f += sing + setup + b.info(k, "elim_bytes") + build
+        tot_h += sing + setup + b.info(k, "elim_bytes_head")
         tot_s += 12.0 * (lnz + unz) + 24.0 * m + 12.0 * m
-    return tot_f, tot_s
+    return tot_f, tot_h, tot_s
+
+
+def kernel_source_hash():
+    """Identifies the kernel sources a profile was taken with (profiles/traffic.json is only quoted when
+    it matches the sources being benchmarked)."""
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted(glob.glob(os.path.join(ROOT, "blu_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(ROOT, "blu_b200", "csrc", "*.h"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
 
 
 _REAL_STDOUT = None
@@ -138,10 +153,11 @@ def run_reference(args, rank, world):
     value = nsample * len(times) / T
     sample = f"{nsample} of the {args.nmat} bases per step (seeds 2000..), factorize+solve_dense each, {nt} threads, file_diff asserts on (setup_bump.rs:228-251)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[1]: 4096 x (2000x2000 simplex-style basis, ~6 nnz/col) factorize+solve_dense",
-                       "m": M, "bases_per_gpu": args.nmat, "reference_arm": "CPU only: rwl/blu restated in C (oracle/), no Rust toolchain in the image"},
+                       "m": M, "bases": args.nmat, "reference_arm": "CPU only: rwl/blu restated in C (oracle/), no Rust toolchain in the image; "
+                       "one instance per host core of this box whatever --gpus says (rank 0 alone runs it)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -154,7 +170,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nmat", type=int, default=4096, help="bases per GPU")
+    ap.add_argument("--nmat", type=int, default=4096, help="bases of the batch (strong scaling: in all; weak: per GPU)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--dense-k", type=int, default=-1, help="dense-tail order (library default if < 0)")
     ap.add_argument("--threads-per-basis", type=int, default=0)
     ap.add_argument("--ref-per-core", type=int, default=16, help="bases per host core in one reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -185,11 +203,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from blu_b200 import BLUBatch, gen
+    from blu_b200.shard import shard_range
 
-    nmat = args.nmat
-    seed0 = 2000 + rank * nmat
+    if args.scaling == "strong":
+        lo, hi = shard_range(args.nmat, rank, world)      # rank's contiguous range of the ONE batch
+        total = args.nmat
+    else:
+        lo, hi = rank * args.nmat, (rank + 1) * args.nmat
+        total = args.nmat * world
+    nmat = hi - lo
     t0 = time.time()
-    bb, be, bi, bx, rhs = gen.batch(nmat, M, NSLACK, PMEAN, seed0, 3000 + rank * nmat)
+    bb, be, bi, bx, rhs = gen.batch(nmat, M, NSLACK, PMEAN, 2000 + lo, 3000 + lo)
     t_gen = time.time() - t0
     cap = int((be - bb).reshape(nmat, M).sum(1).max())
 
@@ -201,11 +225,13 @@ def main():
     pbb, pbe, pbi, pbx, prhs = [k[1] for k in keep]
     lhs_t = torch.empty(nmat * M, dtype=torch.float64).pin_memory()
 
+    # default store sizes (BLU::new-style, blu_host.cu create_common): a basis that needs more gets private
+    # stores and re-runs alone (blu.rs:95-118), during the warm-up steps
     b = BLUBatch(nmat, M, cap, device=local)
     if args.threads_per_basis:
         b.threads_per_basis = args.threads_per_basis
-    # sized so that no basis of the batch asks for more (a Reallocate re-runs the whole batch)
-    b.l_mem = 100000; b.u_mem = 100000; b.w_mem = 900000   # 24 MB per basis, 98 GB for 4,096: no garbage collection, no Reallocate
+    if args.dense_k >= 0:
+        b.dense_k = args.dense_k
     stream = torch.cuda.Stream()
     b.set_stream(stream.cuda_stream)
 
@@ -224,18 +250,19 @@ def main():
     assert b.upload(pbb, pbe, pbi, pbx, prhs) == 0
     for _ in range(args.warmup):
         resident_step()
+    nrealloc = int(b.info(0, "nrealloc"))      # bases that outgrew the default stores got private ones in the first pass
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = b.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fact_ms = []
-    norms_ms = []
+    fact_ms, head_ms, tail_ms, build_ms, norms_ms = [], [], [], [], []
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(args.steps):
             resident_step()
-            fact_ms.append(b.last_kernel_ms(0) - b.last_kernel_ms(2))   # k_factorize alone (2 = the condest/residual kernel)
+            fact_ms.append(b.last_kernel_ms(0) - b.last_kernel_ms(2))   # the k_factorize launches (2 = the condest/residual kernel)
+            head_ms.append(b.last_kernel_ms(3)); tail_ms.append(b.last_kernel_ms(4)); build_ms.append(b.last_kernel_ms(5))
             norms_ms.append(b.last_kernel_ms(2))
         e1.record(stream)
     barrier()
@@ -245,7 +272,7 @@ def main():
     _, x, status = b.download()
     nbad = int((status != 0).sum())
     assert nbad == 0, f"{nbad} bases did not solve"
-    nrealloc = int(b.info(0, "nrealloc"))
+    nrealloc_after = int(b.info(0, "nrealloc"))
 
     # ---------------- end to end through the C ABI with host buffers ----------------
     import ctypes
@@ -279,26 +306,37 @@ def main():
         ms, ms_e2e = float(t[0]), float(t[1])
 
     if rank == 0:
-        total = nmat * world
         value = total * args.steps / (ms * 1e-3)
         e2e_value = total * args.steps / (ms_e2e * 1e-3)
-        bytes_f, bytes_s = algorithmic_bytes(b, nmat, M)
+        bytes_f, bytes_h, bytes_s = algorithmic_bytes(b, nmat, M)
         peak, peak_src = peaks()
-        avg_fact_ms = float(np.mean(fact_ms))
-        achieved = bytes_f / (avg_fact_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_factorize", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        split = float(np.mean(tail_ms)) > 0.0
+        # the dominant kernel: the head launch of the split factorization (singletons, bump set-up and the
+        # sparse part of the elimination); not split: the one k_factorize launch with everything in it
+        dom_ms = float(np.mean(head_ms)) if split else float(np.mean(fact_ms))
+        dom_bytes = bytes_h if split else bytes_f
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_factorize<%d> %s" % (int(b.get_param("threads_per_basis")), "mode HEAD (singletons + setup_bump + sparse elimination)" if split else "(whole factorization)"),
+                    "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": bytes_f, "avg_launch_ms": avg_fact_ms,
-                    "other_kernels_ms_per_step": {"k_factor_norms (condest x2 + residual_test, factorize.rs:121-147)": float(np.mean(norms_ms)),
+                    "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
+                    "whole_factorization": {"algorithmic_bytes": bytes_f, "ms": float(np.mean(fact_ms)),
+                                            "achieved_GBps": bytes_f / (float(np.mean(fact_ms)) * 1e-3) / 1e9},
+                    "other_kernels_ms_per_step": {"k_factorize mode TAIL (dense tail in shared memory, one CTA per SM)": float(np.mean(tail_ms)),
+                                                  "k_factorize mode BUILD (build_factors)": float(np.mean(build_ms)),
+                                                  "k_factor_norms (condest x2 + residual_test, factorize.rs:121-147)": float(np.mean(norms_ms)),
                                                   "k_solve_dense": float(b.last_kernel_ms(1))}}
         tf = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tf):
             try:
                 t = json.load(open(tf))
-                # dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch (ncu --set full),
-                # measured per basis on a full wave and scaled to this launch's batch
-                roofline["traffic"] = t["k_factorize_dram_bytes_per_basis"] * nmat
-                roofline["traffic_source"] = t["source"]
+                # dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch of that kernel (ncu --set
+                # full), per basis, scaled to this launch's batch -- quoted only if taken with these very sources
+                if t.get("kernel_source_hash") == kernel_source_hash():
+                    roofline["traffic"] = t["dram_bytes_per_basis"] * nmat
+                    roofline["traffic_source"] = t["source"]
+                else:
+                    roofline["traffic_source"] = "none: profiles/traffic.json was captured with other kernel sources (%s, now %s)" % (t.get("kernel_source_hash"), kernel_source_hash())
             except Exception:
                 pass
         cpu = None
@@ -318,13 +356,15 @@ def main():
                    "sample": f"first {ns} bases of rank 0's batch, factorize+solve_dense each, one oracle instance per core ({nt} threads), file_diff asserts on",
                    "max_rel_diff_gpu_vs_cpu_solution": err}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "configs[1]: 4096 x (2000x2000 simplex-style basis, ~6 nnz/col) factorize+solve_dense",
-                           "m": M, "bases_per_gpu": nmat, "nnz_per_basis": float(len(bi)) / nmat,
-                           "sharding": f"bases by index, {world} rank(s), no collective",
+                           "m": M, "bases": total, "bases_per_gpu": nmat, "nnz_per_basis": float(len(bi)) / nmat,
+                           "sharding": f"bases by index (shard_range), {world} rank(s), no collective",
+                           "dense_k": int(b.get_param("dense_k")), "tail_threads": int(b.get_param("tail_threads")),
+                           "store_entries_per_basis": {"l_mem": int(b.get_param("l_mem")), "u_mem": int(b.get_param("u_mem")), "w_mem": int(b.get_param("w_mem"))},
                            "l2": "inputs exceed L2: %.0f MB of B + rhs are re-read every step (L2 126 MB)" % ((pbi.nbytes + pbx.nbytes + pbb.nbytes + pbe.nbytes + prhs.nbytes) / 1e6),
-                           "threads_per_basis": int(b.get_param("threads_per_basis")), "reallocations_in_warmup": nrealloc,
+                           "threads_per_basis": int(b.get_param("threads_per_basis")), "reallocations_in_warmup": nrealloc, "reallocations_in_timed_steps": nrealloc_after - nrealloc,
                            "gen_seconds": t_gen},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps, "api": "blu_batch_factorize + blu_batch_solve_dense (host pointers, pinned)"},

@@ -40,7 +40,7 @@ _INFO_NAMES = ["m", "rank", "bump_size", "bump_nz", "matrix_nz", "l_nz", "u_nz",
                "u_flops", "r_flops", "condest_l", "condest_u", "norm_l", "norm_u", "normest_l_inv",
                "normest_u_inv", "onenorm", "infnorm", "residual_test", "pivot_error", "update_cost",
                "time_factorize", "time_solve", "time_update", "elim_bytes", "nelim_div", "pivotlen",
-               "rankdef", "internal_error", "status", "nrealloc"]
+               "rankdef", "internal_error", "status", "nrealloc", "elim_bytes_head", "nruns"]
 I = {n: 100 + k for k, n in enumerate(_INFO_NAMES)}
 I.update({f"t_phase{q}": 200 + q for q in range(16)})
 I.update({f"n_kind{q}": 220 + q for q in range(8)})

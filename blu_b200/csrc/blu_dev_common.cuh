@@ -29,6 +29,7 @@ static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x
 struct Mat {
     int m;
     int l_mem, u_mem, w_mem, bnz_cap;
+    i64 b_total;
     BluParams prm;
     const i64 *b_begin, *b_end, *b_i;
     const double *b_x;
@@ -55,7 +56,7 @@ __device__ __forceinline__ void mat_view(Mat &M, const BluDev &D, int s) {
     const size_t m = (size_t)D.m, S = (size_t)s;
     M.m = D.m;
     M.l_mem = (int)D.l_mem; M.u_mem = (int)D.u_mem; M.w_mem = (int)D.w_mem; M.bnz_cap = (int)D.bnz_cap;
-    M.prm = D.prm;
+    M.prm = D.prm; M.b_total = D.b_total;
     M.b_begin = D.b_begin + S * m; M.b_end = D.b_end + S * m; M.b_i = D.b_i; M.b_x = D.b_x;
     M.bt_ptr = D.bt_ptr + S * (m + 1);
     M.bt_idx = D.bt_idx + S * (size_t)D.bnz_cap; M.bt_val = D.bt_val + S * (size_t)D.bnz_cap;
@@ -65,6 +66,12 @@ __device__ __forceinline__ void mat_view(Mat &M, const BluDev &D, int s) {
     M.l_idx = D.l_idx + S * (size_t)D.l_mem; M.l_val = D.l_val + S * (size_t)D.l_mem;
     M.u_idx = D.u_idx + S * (size_t)D.u_mem; M.u_val = D.u_val + S * (size_t)D.u_mem;
     M.w_idx = D.w_idx + S * 2 * (size_t)D.w_mem; M.w_val = D.w_val + S * 2 * (size_t)D.w_mem;
+    if (D.slot_store) {      /* private stores of a basis that outgrew the uniform ones */
+        const BluSlotStore &e = D.slot_store[s];
+        if (e.l_idx) { M.l_idx = e.l_idx; M.l_val = e.l_val; M.l_mem = (int)e.l_mem; }
+        if (e.u_idx) { M.u_idx = e.u_idx; M.u_val = e.u_val; M.u_mem = (int)e.u_mem; }
+        if (e.w_idx) { M.w_idx = e.w_idx; M.w_val = e.w_val; M.w_mem = (int)e.w_mem; }
+    }
     M.lbeg = D.lbeg + S * 2 * m; M.lend = D.lend + S * 2 * m; M.lcap = D.lcap + S * 2 * m;
     M.ckey = D.ckey + S * m; M.rkey = D.rkey + S * m;
     M.l_begin_p = D.l_begin_p + S * (m + 1); M.u_begin = D.u_begin + S * (m + 1);

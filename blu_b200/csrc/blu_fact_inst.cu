@@ -14,7 +14,7 @@
 #define BLU_CAT2(a, b) a##b
 #define BLU_CAT(a, b) BLU_CAT2(a, b)
 
-int BLU_CAT(blu_launch_factorize_, FACT_NT)(cudaStream_t stream, const BluDev &dv, int nslot, int cap, int mode, int kd, int resident, size_t smem) {
+int BLU_CAT(blu_launch_factorize_, FACT_NT)(cudaStream_t stream, const BluDev &dv, int nslot, int cap, int mode, int kd, int resident, int rerun, size_t smem) {
 #ifndef BLU_EMU
     /* static + dynamic shared memory beyond 48 KB needs the opt-in (the static part is ~2.4 KB) */
     if (smem > 40 * 1024) {
@@ -22,6 +22,6 @@ int BLU_CAT(blu_launch_factorize_, FACT_NT)(cudaStream_t stream, const BluDev &d
         if (e != cudaSuccess) return (int)e;
     }
 #endif
-    BLU_LAUNCH(k_factorize<FACT_NT>, nslot, FACT_NT, smem, stream, dv, cap, mode, kd, resident);
+    BLU_LAUNCH(k_factorize<FACT_NT>, nslot, FACT_NT, smem, stream, dv, cap, mode, kd, resident, rerun);
     return (int)cudaGetLastError();
 }

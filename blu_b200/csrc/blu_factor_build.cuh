@@ -297,15 +297,17 @@ __device__ __forceinline__ void shm_carve(Shm &S, unsigned char *dyn, int cap, i
 #endif
 /* mode (blu_types.h): BLU_MODE_WHOLE runs everything; HEAD stops where the dense tail would begin and parks
  * the basis (status BLU_SUSPENDED_TAIL); TAIL resumes parked bases, finishes the pivot loop and parks them
- * for BUILD, which assembles the factors.  dense_kd: order of the dense tail for this factorization;
+ * for BUILD, which assembles the factors.  rerun != 0: only bases whose status is BLU_REALLOCATE start over.
+ * dense_kd: order of the dense tail for this factorization;
  * dense_smem != 0: the launch has room for the dense values in shared memory. */
-template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factorize(BluDev D, int cap, int mode, int dense_kd, int dense_smem) {
+template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factorize(BluDev D, int cap, int mode, int dense_kd, int dense_smem, int rerun) {
     BLU_DYN_SMEM(dyn);
     __shared__ Shm S;
     const int tid = threadIdx.x;
     for (int s = D.slot0 + blockIdx.x; s < D.slot0 + D.nslot; s += gridDim.x) {
         const bool fresh = mode == BLU_MODE_WHOLE || mode == BLU_MODE_HEAD;
         if (!fresh && D.info[s].status != (mode == BLU_MODE_TAIL ? BLU_SUSPENDED_TAIL : BLU_SUSPENDED_BUILD)) continue;
+        if (fresh && rerun && D.info[s].status != BLU_REALLOCATE) continue;      /* only the bases that asked for more memory run again */
         if (tid == 0) {
             mat_view(S.M, D, s);
             shm_carve(S, dyn, cap, NT / 32, D.m);
@@ -317,7 +319,7 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
             S.mode = mode; S.suspend = 0;
             if (fresh) {
                 /* LU::reset, lu.rs:329-396 (cumulative counters survive) */
-                I->m = D.m;
+                I->m = D.m; I->nruns++;
                 I->nupdate = -1; I->nforrest = 0; I->l_nz = I->u_nz = I->r_nz = 0;
                 I->min_pivot = I->max_pivot = I->max_eta = 0.0;
                 I->update_cost_numer = 0.0; I->update_cost_denom = 1.0;
@@ -333,7 +335,7 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
                 S.rank = 0; S.rankdef = 0;
                 S.nexpand = 0; S.ngarbage = 0; S.nsearch = 0; S.factor_flops = 0;
                 S.elim_bytes = 0.0; S.nelim_div = 0;
-                S.w_used = 0; S.w_limit = (int)D.w_mem; S.w_half = 0;
+                S.w_used = 0; S.w_limit = S.M.w_mem; S.w_half = 0;
                 S.dense_entries = 0; S.dense_block_rank = 0;
                 for (int q = 0; q < 16; q++) S.t_phase[q] = 0;
                 for (int q = 0; q < 8; q++) S.n_kind[q] = 0;
@@ -342,7 +344,7 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
                 S.rank = I->rank; S.rankdef = I->rankdef;
                 S.nexpand = (int)I->nexpand; S.ngarbage = (int)I->ngarbage; S.nsearch = I->nsearch_pivot; S.factor_flops = I->factor_flops;
                 S.elim_bytes = I->elim_bytes; S.nelim_div = I->nelim_div;
-                S.w_half = I->w_half; S.w_used = (int)I->w_used; S.w_limit = (S.w_half + 1) * (int)D.w_mem;
+                S.w_half = I->w_half; S.w_used = (int)I->w_used; S.w_limit = (S.w_half + 1) * S.M.w_mem;
                 S.cstamp = I->cstamp; S.rstamp = I->rstamp;
                 S.nact = I->nact; S.ndead = I->ndead;
                 S.dense_entries = I->dense_entries; S.dense_block_rank = I->dense_block_rank;
@@ -375,6 +377,7 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
             I->nsearch_pivot = S.nsearch; I->nexpand = S.nexpand; I->ngarbage = S.ngarbage;
             I->factor_flops = S.factor_flops;
             I->elim_bytes = S.elim_bytes; I->nelim_div = S.nelim_div;
+            if (fresh) I->elim_bytes_head = S.elim_bytes;
             I->w_half = S.w_half; I->w_used = S.w_used;
             I->cstamp = S.cstamp; I->rstamp = S.rstamp;
             I->nact = S.nact; I->ndead = S.ndead;

@@ -44,7 +44,8 @@ template <int NT> __device__ void phase_validate_transpose(Shm &S) {
     i64 nnz = 0;
     for (int j = tid; j < m; j += NT) {
         i64 bb = M.b_begin[j], be = M.b_end[j];
-        if (be < bb) bad = 1; else nnz += be - bb;
+        /* (a pointer outside b_i / b_x is an invalid argument too: the reference would panic on the slice) */
+        if (be < bb || bb < 0 || be > M.b_total) bad = 1; else nnz += be - bb;
     }
     bad = block_max<NT>(bad, S.iscr);
     nnz = block_sum64<NT>(nnz, S.kscr);

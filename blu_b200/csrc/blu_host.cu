@@ -33,11 +33,13 @@ struct blu_b200 {
     int split_min;              /* batches of more bases than this run as head / tail / build launches */
     int cap;                    /* smem line cache entries */
     std::vector<void *> allocs; /* every device allocation */
+    std::vector<BluSlotStore> hslot; BluSlotStore *d_slot; /* per-basis store overrides (host mirror, device table) */
+    std::vector<void *> ext_blocks; int have_overrides;     /* private stores of bases that outgrew the uniform ones */
     std::vector<void **> store_ptrs;
     /* resizable stores */
     cudaStream_t stream; int own_stream;
-    cudaEvent_t ev0, ev1;
-    double last_ms[2];
+    cudaEvent_t ev0, ev1, ev_k[4];
+    double last_ms[2], last_part_ms[3]; int parts_timed;
     int64_t launches;
     int nrealloc;
     /* device staging for B, rhs, lhs, status */
@@ -105,11 +107,46 @@ static int alloc_stores(blu_b200 *o) {
     if ((st = dalloc(o, &d.w_val, n * 2 * d.w_mem + PADDING))) return st;
     return BLU_OK;
 }
+/* Replace the L/U/W stores by ones of the sizes now in o->d.  The new stores are allocated first: if that
+ * fails the old ones (and the old sizes) stay, so the object keeps working. */
+struct StoreSet { int *l_idx, *u_idx, *w_idx, *ur_idx; double *l_val, *u_val, *w_val, *ur_val; };
+static void free_stores(blu_b200 *o);
+static int clear_overrides(blu_b200 *o);
+static int swap_stores(blu_b200 *o, int64_t l_mem, int64_t u_mem, int64_t w_mem) {
+    BluDev &d = o->d;
+    const StoreSet old = {d.l_idx, d.u_idx, d.w_idx, d.ur_idx, d.l_val, d.u_val, d.w_val, d.ur_val};
+    const blu_i64 ol = d.l_mem, ou = d.u_mem, ow = d.w_mem;
+    d.l_mem = l_mem; d.u_mem = u_mem; d.w_mem = w_mem;
+    d.l_idx = d.u_idx = d.w_idx = d.ur_idx = nullptr; d.l_val = d.u_val = d.w_val = d.ur_val = nullptr;
+    int st = alloc_stores(o);
+    if (st != BLU_OK) {
+        free_stores(o);      /* whatever part of the new set was allocated */
+        d.l_idx = old.l_idx; d.u_idx = old.u_idx; d.w_idx = old.w_idx; d.ur_idx = old.ur_idx;
+        d.l_val = old.l_val; d.u_val = old.u_val; d.w_val = old.w_val; d.ur_val = old.ur_val;
+        d.l_mem = ol; d.u_mem = ou; d.w_mem = ow;
+        return st;
+    }
+    dfree(o, old.l_idx); dfree(o, old.l_val); dfree(o, old.u_idx); dfree(o, old.u_val);
+    dfree(o, old.w_idx); dfree(o, old.w_val); dfree(o, old.ur_idx); dfree(o, old.ur_val);
+    return clear_overrides(o);
+}
 static void free_stores(blu_b200 *o) {
     BluDev &d = o->d;
     dfree(o, d.l_idx); dfree(o, d.l_val); dfree(o, d.u_idx); dfree(o, d.u_val); dfree(o, d.w_idx); dfree(o, d.w_val);
     dfree(o, d.ur_idx); dfree(o, d.ur_val); d.ur_idx = nullptr; d.ur_val = nullptr;
     d.l_idx = d.u_idx = d.w_idx = nullptr; d.l_val = d.u_val = d.w_val = nullptr;
+}
+
+/* drop every per-basis override (their content is gone or has been folded into the uniform stores) */
+static int clear_overrides(blu_b200 *o) {
+    if (!o->d_slot) return BLU_OK;
+    for (void *p : o->ext_blocks) dfree(o, p);
+    o->ext_blocks.clear();
+    BluSlotStore z; memset(&z, 0, sizeof z);
+    o->hslot.assign((size_t)o->d.nmat, z);
+    o->have_overrides = 0;
+    if (cudaMemcpy(o->d_slot, o->hslot.data(), o->hslot.size() * sizeof(BluSlotStore), cudaMemcpyHostToDevice) != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) return BLU_ERROR_CUDA;
+    return BLU_OK;
 }
 
 /* the dense-tail arrays (blu_factor_dense.cuh); dense_k = 0 disables the dense tail */
@@ -157,7 +194,8 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
         if (blu_dense_smem_bytes_resident(kd) + 4096 /* static Shm */ <= (size_t)o->smem_optin) o->kd_smem_max = kd;
     o->split_min = o->num_sms;
     if (const char *e = getenv("BLU_B200_CAP")) { int c = atoi(e); if (c >= 64 && c <= 4096) o->cap = c & ~31; }   /* tuning knob: entries of the shared-memory line caches */
-    o->launches = 0; o->nrealloc = 0; o->last_ms[0] = o->last_ms[1] = 0.0;
+    o->launches = 0; o->nrealloc = 0; o->last_ms[0] = o->last_ms[1] = 0.0; o->last_part_ms[0] = o->last_part_ms[1] = o->last_part_ms[2] = 0.0;
+    o->d_slot = nullptr; o->have_overrides = 0;
     o->have_b = 0; o->info_dirty = 0; o->norms = 1; o->last_norms_ms = 0.0;
     o->have_pipe = 0; o->d_chunk_end = nullptr; o->h_chunk_end = nullptr;
     o->dm_rhs = o->dm_lhs = o->dm_work = nullptr; o->dm_status = nullptr; o->multi_cap = 0;
@@ -172,7 +210,7 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     /* lu.rs:245-259.  The reference starts every store at b_nz and grows on demand; the
      * device build starts larger because a Reallocate costs a full re-run here. */
     d.l_mem = d.u_mem = 8 * d.bnz_cap + 4 * m;
-    d.w_mem = 8 * d.bnz_cap + 8 * m;
+    d.w_mem = 24 * d.bnz_cap + 16 * m;     /* room for the fill of the sparse head without garbage collection (measured on configs[1]: 8*nnz + 8*m collects 1.4 times per basis and costs 10 %) */
     d.prm.droptol = 1e-20; d.prm.abstol = 1e-14; d.prm.reltol = 0.1;
     d.prm.nzbias = 1; d.prm.maxsearch = 3; d.prm.pad = 4; d.prm.stretch = 0.3;
     d.prm.compress_thres = 0.5; d.prm.sparse_thres = 0.05; d.prm.search_rows = 0;
@@ -195,6 +233,7 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     A(d.cancelled, n * M); A(d.work0, n * M); A(d.work1, n * M);
     A(d.gwork, n * (size_t)d.gwork_warps * M);
     A(d.info, n);
+    A(o->d_slot, n);
     A(o->db_begin, n * M); A(o->db_end, n * M);
     A(o->d_rhs, n * M); A(o->d_lhs, n * M); A(o->d_status, n);
     if (single) { A(o->d_irhs, M); A(o->d_xrhs, M); A(o->d_ilhs, M); A(o->d_xout, M); A(o->d_scal, 16); A(d.ur_ptr, M + 1); A(d.dep_ur, M); }
@@ -202,6 +241,7 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     o->b_cap = 0; o->db_i = nullptr; o->db_x = nullptr;
     o->gf_i = nullptr; o->gf_x = nullptr; o->gf_cap = 0;
     if (st == BLU_OK) st = alloc_stores(o);
+    if (st == BLU_OK) { d.slot_store = o->d_slot; st = clear_overrides(o); }
     if (st == BLU_OK) {
         int kd = o->kd_smem_max;
         if (const char *e = getenv("BLU_B200_DENSE_K")) kd = atoi(e);      /* tuning knob, same as BLU_P_DENSE_K */
@@ -224,6 +264,7 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     o->own_stream = 1;
 #ifndef BLU_EMU
     if (st == BLU_OK && (cudaEventCreate(&o->ev0) != cudaSuccess || cudaEventCreate(&o->ev1) != cudaSuccess)) st = BLU_ERROR_CUDA;
+    for (int q = 0; q < 4 && st == BLU_OK; q++) if (cudaEventCreate(&o->ev_k[q]) != cudaSuccess) st = BLU_ERROR_CUDA;
 #endif
     if (st != BLU_OK) {
         for (void *p : o->allocs) cudaFree(p);
@@ -247,6 +288,7 @@ static void destroy_common(blu_b200 *o) {
     if (o->h_xout) cudaFreeHost(o->h_xout);
 #ifndef BLU_EMU
     cudaEventDestroy(o->ev0); cudaEventDestroy(o->ev1);
+    for (int q = 0; q < 4; q++) cudaEventDestroy(o->ev_k[q]);
 #endif
     if (o->have_pipe) {
 #ifndef BLU_EMU
@@ -286,7 +328,7 @@ static void timer_stop(blu_b200 *o, int which) {
 #endif
 }
 
-static int launch_factorize_mode(blu_b200 *o, cudaStream_t stream, int slot0, int nslot, int nt, int mode) {
+static int launch_factorize_mode(blu_b200 *o, cudaStream_t stream, int slot0, int nslot, int nt, int mode, int rerun) {
     const int kd = o->d.dense_k;
     const bool dense_here = kd > 0 && (mode == BLU_MODE_WHOLE || mode == BLU_MODE_TAIL);
     const bool resident = dense_here && kd <= o->kd_smem_max;
@@ -296,12 +338,12 @@ static int launch_factorize_mode(blu_b200 *o, cudaStream_t stream, int slot0, in
     BluDev dv = o->d; dv.slot0 = slot0; dv.nslot = nslot;
     int e;
     switch (nt) {
-    case 32: e = blu_launch_factorize_32(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, smem); break;
-    case 64: e = blu_launch_factorize_64(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, smem); break;
-    case 256: e = blu_launch_factorize_256(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, smem); break;
-    case 512: e = blu_launch_factorize_512(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, smem); break;
-    case 1024: e = blu_launch_factorize_1024(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, smem); break;
-    default: e = blu_launch_factorize_128(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, smem); break;
+    case 32: e = blu_launch_factorize_32(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, rerun, smem); break;
+    case 64: e = blu_launch_factorize_64(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, rerun, smem); break;
+    case 256: e = blu_launch_factorize_256(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, rerun, smem); break;
+    case 512: e = blu_launch_factorize_512(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, rerun, smem); break;
+    case 1024: e = blu_launch_factorize_1024(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, rerun, smem); break;
+    default: e = blu_launch_factorize_128(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, rerun, smem); break;
     }
     o->launches++;
     CK((cudaError_t)e);
@@ -310,15 +352,75 @@ static int launch_factorize_mode(blu_b200 *o, cudaStream_t stream, int slot0, in
 /* One launch for a single basis or a small batch.  A large batch whose dense tail fits in shared memory runs
  * as three launches: the sparse head wants many small CTAs per SM (the pivot loop is a latency chain), the
  * tail one CTA per SM with the whole active submatrix on chip, build_factors many small CTAs again. */
-static int launch_factorize(blu_b200 *o, cudaStream_t stream, int slot0, int nslot) {
+static int launch_factorize(blu_b200 *o, cudaStream_t stream, int slot0, int nslot, int rerun = 0) {
     const int kd = o->d.dense_k;
+    const bool timed = stream == o->stream;      /* (the pipelined chunks overlap: no per-launch times there) */
+    auto mark = [&](int q) {
+#ifndef BLU_EMU
+        if (timed) cudaEventRecord(o->ev_k[q], stream);
+#endif
+    };
+    o->parts_timed = 0;
     if (kd > 0 && kd <= o->kd_smem_max && nslot > o->split_min) {
-        int st = launch_factorize_mode(o, stream, slot0, nslot, o->nthreads, BLU_MODE_HEAD);
-        if (st == BLU_OK) st = launch_factorize_mode(o, stream, slot0, nslot, o->tail_threads, BLU_MODE_TAIL);
-        if (st == BLU_OK) st = launch_factorize_mode(o, stream, slot0, nslot, o->nthreads, BLU_MODE_BUILD);
+        mark(0);
+        int st = launch_factorize_mode(o, stream, slot0, nslot, o->nthreads, BLU_MODE_HEAD, rerun);
+        mark(1);
+        if (st == BLU_OK) st = launch_factorize_mode(o, stream, slot0, nslot, o->tail_threads, BLU_MODE_TAIL, 0);
+        mark(2);
+        if (st == BLU_OK) st = launch_factorize_mode(o, stream, slot0, nslot, o->nthreads, BLU_MODE_BUILD, 0);
+        mark(3);
+        if (timed) o->parts_timed = 3;
         return st;
     }
-    return launch_factorize_mode(o, stream, slot0, nslot, o->nthreads, BLU_MODE_WHOLE);
+    mark(0);
+    int st = launch_factorize_mode(o, stream, slot0, nslot, o->nthreads, BLU_MODE_WHOLE, rerun);
+    mark(1);
+    if (timed) o->parts_timed = 1;
+    return st;
+}
+
+/* blu.rs:345-377 for a batch: every basis that answered Reallocate gets private stores of
+ * realloc_factor * (mem + addmem) entries (only the kinds it asked for); nobody else moves. */
+static int grow_hungry_slots(blu_b200 *o) {
+    BluDev &d = o->d;
+    const double f = o->realloc_factor < 1.0 ? 1.0 : o->realloc_factor;
+    struct Need { int k; int64_t l, u, w; };
+    std::vector<Need> needs;
+    size_t bytes = 0;
+    auto rnd = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    for (int k = 0; k < d.nmat; k++) {
+        const BluInfo &I = o->hinfo[(size_t)k];
+        if (I.status != BLU_REALLOCATE) continue;
+        const BluSlotStore &e = o->hslot[(size_t)k];
+        Need n = {k, 0, 0, 0};
+        if (I.addmem_l > 0) n.l = (int64_t)(f * (double)((e.l_idx ? e.l_mem : d.l_mem) + I.addmem_l)) + 1;
+        if (I.addmem_u > 0) n.u = (int64_t)(f * (double)((e.u_idx ? e.u_mem : d.u_mem) + I.addmem_u)) + 1;
+        if (I.addmem_w > 0) n.w = (int64_t)(f * (double)((e.w_idx ? e.w_mem : d.w_mem) + I.addmem_w)) + 1;
+        if (n.l > 0x3fffffff || n.u > 0x3fffffff || n.w > 0x1fffffff) return BLU_ERROR_OUT_OF_MEMORY;
+        if (!n.l && !n.u && !n.w) return BLU_ERROR_INTERNAL;
+        if (n.l) bytes += rnd((size_t)(n.l + PADDING) * 4) + rnd((size_t)(n.l + PADDING) * 8);
+        if (n.u) bytes += rnd((size_t)(n.u + PADDING) * 4) + rnd((size_t)(n.u + PADDING) * 8);
+        if (n.w) bytes += rnd((size_t)(2 * n.w + PADDING) * 4) + rnd((size_t)(2 * n.w + PADDING) * 8);
+        needs.push_back(n);
+    }
+    if (needs.empty()) return BLU_OK;
+    unsigned char *blk = nullptr;
+    int st = dalloc(o, &blk, bytes);
+    if (st != BLU_OK) return st;
+    o->ext_blocks.push_back(blk);
+    size_t off = 0;
+    auto take = [&](size_t b) { unsigned char *p = blk + off; off += rnd(b); return p; };
+    for (const Need &n : needs) {
+        BluSlotStore &e = o->hslot[(size_t)n.k];
+        if (n.l) { e.l_idx = (int *)take((size_t)(n.l + PADDING) * 4); e.l_val = (double *)take((size_t)(n.l + PADDING) * 8); e.l_mem = n.l; }
+        if (n.u) { e.u_idx = (int *)take((size_t)(n.u + PADDING) * 4); e.u_val = (double *)take((size_t)(n.u + PADDING) * 8); e.u_mem = n.u; }
+        if (n.w) { e.w_idx = (int *)take((size_t)(2 * n.w + PADDING) * 4); e.w_val = (double *)take((size_t)(2 * n.w + PADDING) * 8); e.w_mem = n.w; }
+    }
+    o->have_overrides = 1;
+    CK(cudaMemcpyAsync(o->d_slot, o->hslot.data(), o->hslot.size() * sizeof(BluSlotStore), cudaMemcpyHostToDevice, o->stream));
+    CK(cudaStreamSynchronize(o->stream));
+    o->nrealloc++;
+    return BLU_OK;
 }
 
 static int fetch_info(blu_b200 *o) {
@@ -336,18 +438,31 @@ static int ensure_info(blu_b200 *o) {
 }
 
 /* factorize what is resident in db_*; loops on Reallocate like blu.rs:95-118 */
-static int factorize_resident(blu_b200 *o) {
+static int factorize_resident(blu_b200 *o, int hungry_known = 0) {
     CK(cudaSetDevice(o->device));
     BluDev &d = o->d;
     d.b_begin = (const blu_i64 *)o->db_begin; d.b_end = (const blu_i64 *)o->db_end;
     d.b_i = (const blu_i64 *)o->db_i; d.b_x = o->db_x;
     double total_ms = 0.0;
-    for (int attempt = 0; attempt < 40; attempt++) {
+    if (hungry_known && !o->single) {      /* a pipelined first pass already ran: hinfo says who wants more memory */
+        int st = grow_hungry_slots(o);
+        if (st != BLU_OK) return st;
+        total_ms = o->last_ms[0];
+    } else hungry_known = 0;
+    for (int attempt = hungry_known ? 1 : 0; attempt < 40; attempt++) {
         timer_start(o);
-        int st = launch_factorize(o, o->stream, 0, d.nmat);
+        /* after the first pass only the bases that asked for more memory run again (batches) */
+        int st = launch_factorize(o, o->stream, 0, d.nmat, attempt > 0 && !o->single);
         if (st != BLU_OK) return st;
         timer_stop(o, 0);
         total_ms += o->last_ms[0];
+#ifndef BLU_EMU
+        for (int q = 0; q < 3; q++) {
+            float pm = 0;
+            if (q < o->parts_timed) cudaEventElapsedTime(&pm, o->ev_k[q], o->ev_k[q + 1]);
+            o->last_part_ms[q] = pm;
+        }
+#endif
         if ((st = fetch_info(o)) != BLU_OK) return st;
         int64_t al = 0, au = 0, aw = 0; int need = 0;
         for (auto &I : o->hinfo) {
@@ -374,13 +489,16 @@ static int factorize_resident(blu_b200 *o) {
             return BLU_OK;
         }
         /* lu_realloc_obj, blu.rs:345-377 */
+        if (!o->single) {
+            if ((st = grow_hungry_slots(o)) != BLU_OK) return st;
+            continue;
+        }
         double f = o->realloc_factor < 1.0 ? 1.0 : o->realloc_factor;
-        if (al > 0) d.l_mem = (int64_t)(f * (double)(d.l_mem + al)) + 1;
-        if (au > 0) d.u_mem = (int64_t)(f * (double)(d.u_mem + au)) + 1;
-        if (aw > 0) d.w_mem = (int64_t)(f * (double)(d.w_mem + aw)) + 1;
-        if (d.l_mem > 0x3fffffff || d.u_mem > 0x3fffffff || d.w_mem > 0x1fffffff) return BLU_ERROR_OUT_OF_MEMORY;
-        free_stores(o);
-        if ((st = alloc_stores(o)) != BLU_OK) return st;
+        const int64_t nl = al > 0 ? (int64_t)(f * (double)(d.l_mem + al)) + 1 : d.l_mem;
+        const int64_t nu = au > 0 ? (int64_t)(f * (double)(d.u_mem + au)) + 1 : d.u_mem;
+        const int64_t nw = aw > 0 ? (int64_t)(f * (double)(d.w_mem + aw)) + 1 : d.w_mem;
+        if (nl > 0x3fffffff || nu > 0x3fffffff || nw > 0x1fffffff) return BLU_ERROR_OUT_OF_MEMORY;
+        if ((st = swap_stores(o, nl, nu, nw)) != BLU_OK) return st;
         o->nrealloc++;
     }
     return BLU_ERROR_INTERNAL;
@@ -410,6 +528,7 @@ extern "C" int blu_batch_upload(blu_batch_t *o, const int64_t *b_begin, const in
             CK(cudaMemcpyAsync(o->db_x, b_x, (size_t)bnz_total * sizeof(double), cudaMemcpyHostToDevice, o->stream));
         }
         o->have_b = 1;
+        o->d.b_total = bnz_total;
     }
     if (rhs) CK(cudaMemcpyAsync(o->d_rhs, rhs, n * m * sizeof(double), cudaMemcpyHostToDevice, o->stream));
     CK(cudaStreamSynchronize(o->stream));
@@ -502,6 +621,7 @@ static int factorize_pipelined(blu_b200 *o, const int64_t *b_begin, const int64_
         CK(cudaEventRecord(o->ev_up[p], cs));
     }
     o->have_b = 1;
+    d.b_total = bnz_total;
     CK(cudaEventSynchronize(o->ev_up[14]));        /* the chunk ranges are on the host now */
     d.b_begin = (const blu_i64 *)o->db_begin; d.b_end = (const blu_i64 *)o->db_end;
     d.b_i = (const blu_i64 *)o->db_i; d.b_x = o->db_x;
@@ -510,7 +630,7 @@ static int factorize_pipelined(blu_b200 *o, const int64_t *b_begin, const int64_
         const int s0 = c * per, ns = std::min(per, n - s0);
         if (ns <= 0) break;
         int64_t need = o->h_chunk_end[c];
-        if (need > bnz_total) need = bnz_total;     /* out-of-range pointers are the kernel's business (InvalidArgument) */
+        if (need > bnz_total) need = bnz_total;     /* pointers beyond b_total: the kernel answers InvalidArgument (phase_validate_transpose) */
         const int p = psz > 0 && need > 0 ? (int)std::min<int64_t>(NP - 1, (need - 1) / psz) : 0;
         /* each chunk on its own stream: the next chunk fills the SMs while this one drains */
         cudaStream_t ks = o->chunk_stream[c];
@@ -548,7 +668,7 @@ extern "C" int blu_batch_factorize(blu_batch_t *o, const int64_t *b_begin, const
     if (o->d.nmat >= 256 && bnz_total > 0 && b_i && b_x) {
         CK(cudaSetDevice(o->device));
         st = factorize_pipelined(o, b_begin, b_end, b_i, b_x, bnz_total);
-        if (st == BLU_REALLOCATE) st = factorize_resident(o);      /* B is resident: grow and re-run */
+        if (st == BLU_REALLOCATE) st = factorize_resident(o, 1);      /* B is resident: grow the bases that asked and re-run them */
     } else
 #endif
     {
@@ -583,7 +703,12 @@ extern "C" int blu_batch_synchronize(blu_batch_t *o) {
     CK(cudaStreamSynchronize(o->stream));
     return BLU_OK;
 }
-extern "C" double blu_batch_last_kernel_ms(blu_batch_t *o, int which) { return !o ? 0.0 : which == 2 ? o->last_norms_ms : (which >= 0 && which < 2 ? o->last_ms[which] : 0.0); }
+extern "C" double blu_batch_last_kernel_ms(blu_batch_t *o, int which) {
+    if (!o) return 0.0;
+    if (which == 2) return o->last_norms_ms;
+    if (which >= 3 && which <= 5) return o->last_part_ms[which - 3];
+    return which >= 0 && which < 2 ? o->last_ms[which] : 0.0;
+}
 extern "C" int64_t blu_batch_launch_count(blu_batch_t *o) { return o ? o->launches : 0; }
 
 static double info_value(blu_b200 *o, const BluInfo &I, int what) {
@@ -633,6 +758,8 @@ static double info_value(blu_b200 *o, const BluInfo &I, int what) {
     case BLU_I_INTERNAL_ERROR: return I.internal_error;
     case BLU_I_STATUS: return I.status;
     case BLU_I_NREALLOC: return o->nrealloc;
+    case BLU_I_NRUNS: return I.nruns;
+    case BLU_I_ELIM_BYTES_HEAD: return I.elim_bytes_head;
     default:
         if (what >= BLU_I_T_PHASE0 && what < BLU_I_T_PHASE0 + 16) return (double)I.t_phase[what - BLU_I_T_PHASE0];
         if (what >= BLU_I_N_KIND0 && what < BLU_I_N_KIND0 + 8) return (double)I.n_kind[what - BLU_I_N_KIND0];
@@ -655,7 +782,11 @@ extern "C" int blu_set_param(blu_t *o, int what, double v) {
     case BLU_P_ABSTOL: p.abstol = v; break;
     case BLU_P_RELTOL: p.reltol = v; break;
     case BLU_P_NZBIAS: p.nzbias = (int)v; break;
-    case BLU_P_MAXSEARCH: p.maxsearch = (int)v; break;
+    case BLU_P_MAXSEARCH:
+        /* the search kernels keep at most MAXCAND candidate columns; a larger value would silently search fewer
+         * columns than the reference (markowitz.rs:117-119) */
+        if ((int)v > MAXCAND) return BLU_ERROR_INVALID_ARGUMENT;
+        p.maxsearch = (int)v; break;
     case BLU_P_PAD: p.pad = (int)v; break;
     case BLU_P_STRETCH: p.stretch = v; break;
     case BLU_P_COMPRESS_THRES: p.compress_thres = v; break;
@@ -687,10 +818,8 @@ extern "C" int blu_set_param(blu_t *o, int what, double v) {
         if (n < 1) return BLU_ERROR_INVALID_ARGUMENT;
         if (cudaSetDevice(o->device) != cudaSuccess) return BLU_ERROR_CUDA;
         cudaStreamSynchronize(o->stream);
-        if (what == BLU_P_L_MEM) o->d.l_mem = n; else if (what == BLU_P_U_MEM) o->d.u_mem = n; else o->d.w_mem = n;
-        free_stores(o);
-        int st = alloc_stores(o);
-        if (st != BLU_OK) return st;
+        int st = swap_stores(o, what == BLU_P_L_MEM ? n : o->d.l_mem, what == BLU_P_U_MEM ? n : o->d.u_mem, what == BLU_P_W_MEM ? n : o->d.w_mem);
+        if (st != BLU_OK) return st;      /* the old stores and the factors in them are untouched */
         /* the factors are gone */
         for (auto &I : o->hinfo) I.nupdate = -1;
         if (cudaMemcpy(o->d.info, o->hinfo.data(), o->hinfo.size() * sizeof(BluInfo), cudaMemcpyHostToDevice) != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) return BLU_ERROR_CUDA;
@@ -907,6 +1036,7 @@ static int sparse_call(blu_b200 *o, int64_t nzrhs, const int64_t *irhs, const do
     const int64_t nup = (for_update && tr) ? 1 : nzrhs;
     const int64_t ncopy = (nup < 0 || nup > m) ? 0 : nup;
     if (ncopy > 0 && !irhs) return BLU_ERROR_INVALID_ARGUMENT;
+    if (!for_update && ncopy > 0 && !xrhs) return BLU_ERROR_ARGUMENT_MISSING;   /* the reference's xrhs is a slice, never absent (solve_sparse.rs:35) */
     if (ncopy > 0) {
         CK(cudaMemcpyAsync(o->d_irhs, irhs, (size_t)ncopy * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
         if (xrhs && !(for_update && tr)) CK(cudaMemcpyAsync(o->d_xrhs, xrhs, (size_t)ncopy * sizeof(double), cudaMemcpyHostToDevice, o->stream));
@@ -999,8 +1129,6 @@ extern "C" int blu_solve_dense_multi(blu_t *o, int64_t nrhs, const double *rhs, 
     if ((int64_t)n > o->multi_cap) {
         dfree(o, o->dm_rhs); dfree(o, o->dm_lhs); dfree(o, o->dm_work); dfree(o, o->dm_status);
         o->dm_rhs = o->dm_lhs = o->dm_work = nullptr; o->dm_status = nullptr; o->multi_cap = 0;
-    o->sm_ints = o->sm_markers = o->sm_scal = nullptr; o->sm_dbls = o->sm_xout = nullptr; o->sm_ilhs = o->sm_begin = nullptr; o->smulti_cap = 0;
-    o->sm_irhs = nullptr; o->sm_xrhs = nullptr; o->smulti_rhs_cap = 0;
         int st = dalloc(o, &o->dm_rhs, n * m);
         if (st == BLU_OK) st = dalloc(o, &o->dm_lhs, n * m);
         if (st == BLU_OK) st = dalloc(o, &o->dm_work, n * m);
@@ -1101,41 +1229,35 @@ static int grow_batch_stores(blu_b200 *o) {
     int64_t al = 0, au = 0, aw = 0;
     /* the kernels zero addmem_* on entry: only the bases that returned Reallocate carry a request */
     for (auto &I : o->hinfo) { al = std::max<int64_t>(al, I.addmem_l); au = std::max<int64_t>(au, I.addmem_u); aw = std::max<int64_t>(aw, I.addmem_w); }
+    if (al <= 0 && au <= 0 && aw <= 0) return BLU_ERROR_INTERNAL;
     const double f = o->realloc_factor < 1.0 ? 1.0 : o->realloc_factor;
     const size_t n = (size_t)d.nmat;
     CK(cudaStreamSynchronize(o->stream));
-    for (int which = 0; which < 2; which++) {
-        const int64_t add = which == 0 ? al : au;
-        if (add <= 0) continue;
-        blu_i64 &mem = which == 0 ? d.l_mem : d.u_mem;
-        const int64_t newmem = (int64_t)(f * (double)(mem + add)) + 1;
-        if (newmem > 0x3fffffff) return BLU_ERROR_OUT_OF_MEMORY;
-        int *ni = nullptr; double *nv = nullptr;
-        st = dalloc(o, &ni, n * (size_t)newmem + PADDING);
-        if (st == BLU_OK) st = dalloc(o, &nv, n * (size_t)newmem + PADDING);
-        if (st != BLU_OK) return st;
-        int *&oi = which == 0 ? d.l_idx : d.u_idx; double *&ov = which == 0 ? d.l_val : d.u_val;
-        CK(cudaMemcpy2DAsync(ni, (size_t)newmem * sizeof(int), oi, (size_t)mem * sizeof(int), (size_t)mem * sizeof(int), n, cudaMemcpyDeviceToDevice, o->stream));
-        CK(cudaMemcpy2DAsync(nv, (size_t)newmem * sizeof(double), ov, (size_t)mem * sizeof(double), (size_t)mem * sizeof(double), n, cudaMemcpyDeviceToDevice, o->stream));
-        CK(cudaStreamSynchronize(o->stream));
-        dfree(o, oi); dfree(o, ov); oi = ni; ov = nv; mem = newmem;
-    }
-    if (aw > 0) {
-        const int64_t newmem = (int64_t)(f * (double)(d.w_mem + aw)) + 1;
-        if (newmem > 0x1fffffff) return BLU_ERROR_OUT_OF_MEMORY;
-        int *ni = nullptr; double *nv = nullptr;
-        st = dalloc(o, &ni, n * 2 * (size_t)newmem + PADDING);
-        if (st == BLU_OK) st = dalloc(o, &nv, n * 2 * (size_t)newmem + PADDING);
-        if (st != BLU_OK) return st;
-        BLU_LAUNCH(k_w_regrow_batch, d.nmat, 256, 0, o->stream, d, (const int *)d.w_idx, (const double *)d.w_val, d.w_mem, ni, nv, (blu_i64)newmem);
-        o->launches++;
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(o->stream));
-        dfree(o, d.w_idx); dfree(o, d.w_val); d.w_idx = ni; d.w_val = nv; d.w_mem = newmem;
-    }
+    /* the new uniform sizes cover the largest private store too, so that every override can be folded back */
+    int64_t cl = d.l_mem, cu = d.u_mem, cw = d.w_mem;
+    for (auto &e : o->hslot) { if (e.l_idx) cl = std::max<int64_t>(cl, e.l_mem); if (e.u_idx) cu = std::max<int64_t>(cu, e.u_mem); if (e.w_idx) cw = std::max<int64_t>(cw, e.w_mem); }
+    const bool fold = o->have_overrides != 0;
+    const int64_t nl = al > 0 ? (int64_t)(f * (double)(cl + al)) + 1 : cl;
+    const int64_t nu = au > 0 ? (int64_t)(f * (double)(cu + au)) + 1 : cu;
+    const int64_t nw = aw > 0 ? (int64_t)(f * (double)(cw + aw)) + 1 : cw;
+    if (nl > 0x3fffffff || nu > 0x3fffffff || nw > 0x1fffffff) return BLU_ERROR_OUT_OF_MEMORY;
+    const bool gl = al > 0 || fold, gu = au > 0 || fold, gw = aw > 0 || fold;
+    int *li = nullptr, *ui = nullptr, *wi = nullptr; double *lv = nullptr, *uv = nullptr, *wv = nullptr;
+    if (gl) { st = dalloc(o, &li, n * (size_t)nl + PADDING); if (st == BLU_OK) st = dalloc(o, &lv, n * (size_t)nl + PADDING); if (st != BLU_OK) return st; }
+    if (gu) { st = dalloc(o, &ui, n * (size_t)nu + PADDING); if (st == BLU_OK) st = dalloc(o, &uv, n * (size_t)nu + PADDING); if (st != BLU_OK) return st; }
+    if (gw) { st = dalloc(o, &wi, n * 2 * (size_t)nw + PADDING); if (st == BLU_OK) st = dalloc(o, &wv, n * 2 * (size_t)nw + PADDING); if (st != BLU_OK) return st; }
+    /* every basis copies its own content (read through its view, private or uniform) into the new stores */
+    BLU_LAUNCH(k_store_regrow, d.nmat, 256, 0, o->stream, d, li, lv, (blu_i64)nl, ui, uv, (blu_i64)nu, wi, wv, (blu_i64)nw);
+    o->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(o->stream));
+    if (gl) { dfree(o, d.l_idx); dfree(o, d.l_val); d.l_idx = li; d.l_val = lv; d.l_mem = nl; }
+    if (gu) { dfree(o, d.u_idx); dfree(o, d.u_val); d.u_idx = ui; d.u_val = uv; d.u_mem = nu; }
+    if (gw) { dfree(o, d.w_idx); dfree(o, d.w_val); d.w_idx = wi; d.w_val = wv; d.w_mem = nw; }
+    if (fold && (st = clear_overrides(o)) != BLU_OK) return st;
     o->nrealloc++;
     o->info_dirty = 1;
-    return (al > 0 || au > 0 || aw > 0) ? BLU_OK : BLU_ERROR_INTERNAL;
+    return BLU_OK;
 }
 
 static int ensure_batch_sparse(blu_b200 *o, int64_t tot) {

@@ -518,7 +518,10 @@ __global__ void __launch_bounds__(32) k_solve_sparse(BluDev D, int nrhs, const i
     else if (for_update && I->nforrest == m) st = BLU_ERROR_MAXIMUM_UPDATES;   /* solve_for_update.rs:93-95 */
     else {
         int bad = 0;
-        if (for_update && tr) { i64 j = irhs64[0]; bad = j < 0 || j >= m; nrhs = 1; }
+        if (for_update && tr) {
+            if (units && nrhs < 1) bad = 1;      /* an empty slice names no column to replace */
+            else { i64 j = irhs64[0]; bad = j < 0 || j >= m; nrhs = 1; }
+        }
         else if (nrhs < 0 || nrhs > m) bad = 1;
         else for (int n = lane; n < nrhs; n += 32) { i64 i = irhs64[n]; if (i < 0 || i >= m) bad = 1; }
         if (__any_sync(FULLMASK, bad)) st = BLU_ERROR_INVALID_ARGUMENT;
@@ -1169,20 +1172,34 @@ __global__ void __launch_bounds__(32) k_update(BluDev D, double xtbl, int *scal,
     }
 }
 
-/* batch: move every basis' live half of W into a store with a larger per-basis size and rebase its line table */
-__global__ void k_w_regrow_batch(BluDev D, const int *old_idx, const double *old_val, blu_i64 old_w_mem, int *new_idx, double *new_val, blu_i64 new_w_mem) {
+/* lu_realloc_obj (blu.rs:345-377) for a batch: every basis copies the content of its L / U / W store --
+ * read through its own view, i.e. from its private store if it has one -- into slot s of new uniform
+ * stores of nl / nu / nw entries per basis (a null target = that store stays).  Of W only the live half
+ * moves; it becomes half 0 and the line table is shifted accordingly. */
+__global__ void k_store_regrow(BluDev D, int *nl_i, double *nl_v, blu_i64 nl, int *nu_i, double *nu_v, blu_i64 nu,
+                               int *nw_i, double *nw_v, blu_i64 nw) {
     __shared__ Mat M;
     const int s = blockIdx.x;
     if (threadIdx.x == 0) mat_view(M, D, s);
     __syncthreads();
-    const int half = M.info->w_half;
-    const size_t src = (size_t)s * 2 * (size_t)old_w_mem + (size_t)half * (size_t)old_w_mem, dst = (size_t)s * 2 * (size_t)new_w_mem;
-    const int used = (int)(M.info->w_used - (blu_i64)half * old_w_mem);
-    for (int q = threadIdx.x; q < used; q += blockDim.x) { new_idx[dst + q] = old_idx[src + q]; new_val[dst + q] = old_val[src + q]; }
-    const int delta = half * (int)old_w_mem;
-    for (int l = threadIdx.x; l < 2 * M.m; l += blockDim.x) { M.lbeg[l] -= delta; M.lend[l] -= delta; M.lcap[l] -= delta; }
-    __syncthreads();
-    if (threadIdx.x == 0) { M.info->w_used -= delta; M.info->w_half = 0; }
+    if (nl_i) {
+        const size_t dst = (size_t)s * (size_t)nl;
+        for (int q = threadIdx.x; q < M.l_mem; q += blockDim.x) { nl_i[dst + q] = M.l_idx[q]; nl_v[dst + q] = M.l_val[q]; }
+    }
+    if (nu_i) {
+        const size_t dst = (size_t)s * (size_t)nu;
+        for (int q = threadIdx.x; q < M.u_mem; q += blockDim.x) { nu_i[dst + q] = M.u_idx[q]; nu_v[dst + q] = M.u_val[q]; }
+    }
+    if (nw_i) {
+        const int half = M.info->w_half;
+        const size_t src = (size_t)half * (size_t)M.w_mem, dst = (size_t)s * 2 * (size_t)nw;
+        const int delta = half * M.w_mem;
+        const int used = (int)(M.info->w_used - (blu_i64)delta);
+        for (int q = threadIdx.x; q < used; q += blockDim.x) { nw_i[dst + q] = M.w_idx[src + q]; nw_v[dst + q] = M.w_val[src + q]; }
+        for (int l = threadIdx.x; l < 2 * M.m; l += blockDim.x) { M.lbeg[l] -= delta; M.lend[l] -= delta; M.lcap[l] -= delta; }
+        __syncthreads();
+        if (threadIdx.x == 0) { M.info->w_used -= delta; M.info->w_half = 0; }
+    }
 }
 
 /* after the host moved the live half of W into a larger store: shift the line table */

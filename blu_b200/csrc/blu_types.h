@@ -49,6 +49,7 @@ struct BluInfo {
     int nact;               /* entries of the active-column list */
     int internal_error;     /* line number of a failed device-side invariant, 0 = none */
     int have_ur;            /* the sorted row-wise copy of U (ur_*) matches the current factors */
+    int nruns;              /* how many times a factorization of this basis was started (Reallocate re-runs included) */
     int ndead, dense_entries, dense_block_rank; /* pivot-loop cursors carried from one kernel of a split factorization to the next */
     blu_i64 matrix_nz, bump_nz, l_nz, u_nz, r_nz;
     blu_i64 nsearch_pivot, nexpand, ngarbage, factor_flops;
@@ -61,6 +62,7 @@ struct BluInfo {
     double min_pivot, max_pivot, max_eta, pivot_error;
     double update_cost_numer, update_cost_denom;
     double elim_bytes;      /* algorithmic bytes of the elimination */
+    double elim_bytes_head; /* the part of elim_bytes done by the head launch of a split factorization (= elim_bytes when not split) */
     double condest_l, condest_u, norm_l, norm_u, normest_l_inv, normest_u_inv;
     double onenorm, infnorm, residual_test;
     blu_i64 t_phase[16];    /* SM clock cycles per phase (thread 0): 0 validate+transpose 1 singleton queue 2 setup_bump 3 search 4 pivot singleton row 5 singleton col 6 doubleton 7 small 8 any 9 build_factors 10 remove_cols 11 total 12 dense-tail steps 13 dense-tail entry/exit conversions */
@@ -68,11 +70,21 @@ struct BluInfo {
     blu_i64 norms_cycles[16]; /* SM cycles of the four warps of k_factor_norms: condest(L), condest(U), residual forward + norms, residual transposed */
 };
 
+/* Per-basis override of the L/U/W stores.  A batch starts with uniform strides (slot s of l_idx is
+ * l_idx + s*l_mem); a basis that asks for more memory (Reallocate, blu.rs:95-118) gets private, larger stores
+ * and runs again alone -- the other bases neither move nor re-run.  A null pointer = the uniform store. */
+struct BluSlotStore {
+    int *l_idx; double *l_val; int *u_idx; double *u_val; int *w_idx; double *w_val;
+    blu_i64 l_mem, u_mem, w_mem;
+};
+
 /* Batch-wide device pointers.  Per-slot strides follow from m and the *_mem sizes. */
 struct BluDev {
     int m, nmat;
     int slot0, nslot;   /* the range of slots this launch works on (a batch can be processed in pipelined chunks) */
     blu_i64 l_mem, u_mem, w_mem, bnz_cap;
+    blu_i64 b_total;            /* entries of b_i / b_x: every column pointer must lie in [0, b_total] */
+    const BluSlotStore *slot_store; /* nmat overrides (null pointers inside = uniform store), or null */
     BluParams prm;
     /* input B */
     const blu_i64 *b_begin, *b_end, *b_i; /* b_begin/b_end: nmat*m; positions into b_i/b_x */

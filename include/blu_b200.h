@@ -58,6 +58,8 @@ enum {
     BLU_I_ONENORM, BLU_I_INFNORM, BLU_I_RESIDUAL_TEST, BLU_I_PIVOT_ERROR, BLU_I_UPDATE_COST,
     BLU_I_TIME_FACTORIZE, BLU_I_TIME_SOLVE, BLU_I_TIME_UPDATE, BLU_I_ELIM_BYTES, BLU_I_NELIM_DIV,
     BLU_I_PIVOTLEN, BLU_I_RANKDEF, BLU_I_INTERNAL_ERROR, BLU_I_STATUS, BLU_I_NREALLOC,
+    BLU_I_ELIM_BYTES_HEAD,              /* part of BLU_I_ELIM_BYTES done by the head launch of a split batch factorization */
+    BLU_I_NRUNS,                        /* factorization passes started on this basis since creation (a Reallocate re-run counts) */
     BLU_I_T_PHASE0 = 200, /* +0..15: SM cycles per phase of the factorization kernel (diagnostic) */
     BLU_I_N_KIND0 = 220,  /* +0..4: pivots taken by singleton-row / singleton-col / doubleton / small / any; +5: of those, steps taken in the dense tail; +6: entries into it */
     BLU_I_NORMS_CYC0 = 230 /* +0..3: SM cycles of condest(L), condest(U), residual forward, residual transposed (diagnostic) */
@@ -161,7 +163,7 @@ void *blu_batch_stream(blu_batch_t *b);
 int blu_batch_set_stream(blu_batch_t *b, void *cuda_stream);
 int blu_batch_synchronize(blu_batch_t *b);
 /* device time of the last factorize / solve kernels, measured with CUDA events on the launching stream */
-double blu_batch_last_kernel_ms(blu_batch_t *b, int which /*0 factorize (all kernels of the call), 1 solve_dense, 2 the condest/residual_test kernel alone*/);
+double blu_batch_last_kernel_ms(blu_batch_t *b, int which /*0 factorize (all kernels of the call), 1 solve_dense, 2 the condest/residual_test kernel alone, 3 / 4 / 5 the head / tail / build launch of the last split factorization pass (3 = the single launch when not split)*/);
 /* number of kernels this library launched since creation */
 int64_t blu_batch_launch_count(blu_batch_t *b);
 

@@ -335,3 +335,92 @@ def test_emu_dense_tail_structures(emu):
             structured_case(lambda mm, nnz: BLU(mm, nnz, lib=emu), m, seed, nupd=2)
     finally:
         del os.environ["BLU_B200_DENSE_K"]
+
+
+def hungry_batch(nmat, m, heavy):
+    """Sparse bases plus a few (`heavy`) much denser ones, in the batch ABI layout."""
+    mats = [gen.basis(9400 + k, m, 0 if k in heavy else m // 2, 9.0 if k in heavy else 2.5, cap=40) for k in range(nmat)]
+    off, bb, be = 0, [], []
+    for cp, ri, v in mats:
+        bb.append(cp[:-1] + off); be.append(cp[1:] + off); off += len(v)
+    return mats, np.concatenate(bb), np.concatenate(be), np.concatenate([x[1] for x in mats]), np.concatenate([x[2] for x in mats])
+
+
+def check_hungry(b, mats, heavy, m):
+    for k, (cp, ri, v) in enumerate(mats):
+        o = oracle_for(m, len(v), 400)
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        _, fo = o.get_factors()
+        _, fg = b.get_factors(k)
+        for key in fo:
+            assert np.array_equal(fo[key], fg[key]), (k, key)
+        # blu.rs:95-118 re-runs the basis that asked for memory -- and only that one
+        assert (b.info(k, "nruns") > 1) == (k in heavy), (k, b.info(k, "nruns"))
+    assert b.info(0, "nrealloc") >= 1
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_emu_per_basis_reallocate(emu, split):
+    """One hungry basis in a batch gets private, larger stores and runs again alone (grow_hungry_slots);
+    afterwards a Reallocate in the update path folds the private stores back (grow_batch_stores)."""
+    nmat, m, heavy = 5, 120, {3}
+    mats, bb, be, bi, bx = hungry_batch(nmat, m, heavy)
+    b = BLUBatch(nmat, m, max(len(x[2]) for x in mats), lib=emu)
+    b.threads_per_basis = 64
+    if split:
+        b.split_min = 0; b.dense_k = 64; b.tail_threads = 128
+    light = max(len(x[2]) for k, x in enumerate(mats) if k not in heavy)
+    b.l_mem = 8 * light; b.u_mem = 8 * light; b.w_mem = 10 * light
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all(), status
+    check_hungry(b, mats, heavy, m)
+    rhs = np.random.default_rng(1).uniform(-1, 1, nmat * m)
+    st, x, sst = b.solve_dense(rhs, "N")
+    assert st == 0 and (sst == 0).all()
+    for k, (cp, ri, v) in enumerate(mats):
+        o = oracle_for(m, len(v), 400)
+        o.factorize(cp[:-1], cp[1:], ri, v)
+        _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
+        assert np.array_equal(x[k], xo), k
+
+
+def test_emu_bad_column_pointers(emu):
+    """Column pointers outside b_i / b_x are an invalid argument for that basis (the reference would panic on
+    the slice), never an out-of-bounds read."""
+    nmat, m = 3, 60
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 20, 3.0, 9500, 9550)
+    b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()), lib=emu)
+    be2 = be.copy(); be2[m + 5] = len(bi) + 7          # basis 1: a column ends beyond the arrays
+    bb2 = bb.copy(); bb2[2 * m + 1] = -3               # basis 2: a column starts before them
+    st, status = b.factorize(bb2, be2, bi, bx)
+    assert st == 0 and list(status) == [0, -4, -4]
+    g = BLU(m, 10, lib=emu)
+    assert g.set_param("maxsearch", 33) == -4 and g.set_param("maxsearch", 32) == 0   # MAXCAND
+
+
+def test_emu_batch_replay_after_private_stores(emu):
+    """Tight stores: every basis gets private stores during factorize (grow_hungry_slots); the first
+    Reallocate of the update path then folds them back into uniform ones with their content
+    (grow_batch_stores / k_store_regrow) and the replay goes on, in lockstep with one oracle per basis."""
+    from parity import batch_replay_parity
+    nmat, m = 3, 90
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 27, 4.0, 9100, 9600)
+    b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()), lib=emu)
+    b.l_mem = 450; b.u_mem = 450; b.w_mem = 450
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all()
+    nr0 = b.info(0, "nrealloc")
+    assert nr0 >= 1
+    oracles, pools = [], []
+    for k in range(nmat):
+        cp, ri, v = gen.basis(9100 + k, m, 27, 4.0)
+        o = oracle_for(m, len(v), 400)
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        oracles.append(o); pools.append(gen.basis(9700 + k, m, 0, 3.0))
+    batch_replay_parity(b, oracles, m, pools, 25)
+    assert b.info(0, "nrealloc") > nr0
+    st, x, sst = b.solve_dense(rhs, "T")
+    assert st == 0
+    for k, o in enumerate(oracles):
+        _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "T")
+        assert np.array_equal(x[k], xo)
