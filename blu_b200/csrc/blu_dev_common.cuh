@@ -24,11 +24,12 @@ static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x
 #define STAMP_BITS 40
 #define MAXROW_SMALL 64 /* pivot.rs:22 */
 #define MAXCAND 32      /* upper bound on maxsearch honoured by the search kernel */
+#define TREE_MAX_SEARCH 4    /* ... when maxsearch is at most this (the frontier of the top-k walk lives in shared memory) */
 
 /* per-slot view of BluDev */
 struct Mat {
     int m;
-    int l_mem, u_mem, w_mem, bnz_cap;
+    int l_mem, u_mem, w_mem, bnz_cap, tree_min;
     i64 b_total;
     BluParams prm;
     const i64 *b_begin, *b_end, *b_i;
@@ -40,7 +41,7 @@ struct Mat {
     int *u_idx; double *u_val;
     int *w_idx; double *w_val;
     int *lbeg, *lend, *lcap;
-    u64 *ckey, *rkey;
+    u64 *ckey, *rkey, *ctree;
     int *l_begin_p, *u_begin, *l_begin, *lt_begin, *lt_begin_p, *p, *r_begin, *eta_row;
     int *dep_lt, *dep_lc, *dep_uc, *len_uc;
     int *ur_ptr, *ur_idx, *dep_ur; double *ur_val;
@@ -56,7 +57,7 @@ __device__ __forceinline__ void mat_view(Mat &M, const BluDev &D, int s) {
     const size_t m = (size_t)D.m, S = (size_t)s;
     M.m = D.m;
     M.l_mem = (int)D.l_mem; M.u_mem = (int)D.u_mem; M.w_mem = (int)D.w_mem; M.bnz_cap = (int)D.bnz_cap;
-    M.prm = D.prm; M.b_total = D.b_total;
+    M.prm = D.prm; M.b_total = D.b_total; M.tree_min = D.tree_min;
     M.b_begin = D.b_begin + S * m; M.b_end = D.b_end + S * m; M.b_i = D.b_i; M.b_x = D.b_x;
     M.bt_ptr = D.bt_ptr + S * (m + 1);
     M.bt_idx = D.bt_idx + S * (size_t)D.bnz_cap; M.bt_val = D.bt_val + S * (size_t)D.bnz_cap;
@@ -74,6 +75,7 @@ __device__ __forceinline__ void mat_view(Mat &M, const BluDev &D, int s) {
     }
     M.lbeg = D.lbeg + S * 2 * m; M.lend = D.lend + S * 2 * m; M.lcap = D.lcap + S * 2 * m;
     M.ckey = D.ckey + S * m; M.rkey = D.rkey + S * m;
+    M.ctree = D.ctree + S * (m / 31 + 72);
     M.l_begin_p = D.l_begin_p + S * (m + 1); M.u_begin = D.u_begin + S * (m + 1);
     M.l_begin = D.l_begin + S * (m + 1); M.lt_begin = D.lt_begin + S * (m + 1);
     M.lt_begin_p = D.lt_begin_p + S * (m + 1); M.p = D.p + S * (m + 1);
@@ -137,6 +139,7 @@ struct Shm {
     int dense_entries, dense_block_rank;
     int mode, suspend;        /* BLU_MODE_*; 1 = park for the tail kernel, 2 = park for the build kernel */
     int dv_smem;              /* the launch has room for the dense values and bitmaps in shared memory */
+    int use_tree, tree_levels, tree_off[8], tree_n[8];   /* min-tree over the column keys (markowitz_search of large bumps) */
     int lput, uput;           /* fill pointers of L and U (= l_begin_p[rank], u_begin[rank]) */
     int dpcand;               /* stash row of the pivot column's keys (-1: none) */
 };

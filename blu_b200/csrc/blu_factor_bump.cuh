@@ -95,6 +95,103 @@ template <int NT> __device__ bool w_reserve(Shm &S, i64 grow) {
 }
 
 /* ------------------------------------------------------------------ */
+/* min-tree over the column keys                                       */
+/* The count buckets of list.rs:54-104 give the reference "first       */
+/* column of the smallest non-empty bucket" in O(1); with keys         */
+/* (count << 40 | stamp) the same column is the minimum key, and the   */
+/* next ones in the bucket walk (markowitz.rs:82-123) are the next     */
+/* smallest keys.  For bumps of 10^4..10^6 columns a scan of the       */
+/* active list per pivot is O(bump); this tree (fanout 32, level 0 =   */
+/* ckey itself) answers the first few minima in O(levels) and is       */
+/* repaired in O(levels) per column whose key changed.                 */
+/* ------------------------------------------------------------------ */
+__device__ __forceinline__ const u64 *ctree_level(const Shm &S, int l) { return l == 0 ? S.M.ckey : S.M.ctree + S.tree_off[l]; }
+
+template <int NT> __device__ void ctree_build(Shm &S) {
+    Mat &M = S.M;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    if (tid == 0) {
+        int n = M.m, off = 0, l = 0;
+        S.tree_n[0] = n; S.tree_off[0] = 0;
+        while (n > 32 && l < 7) { n = (n + 31) / 32; l++; S.tree_n[l] = n; S.tree_off[l] = off; off += n; }
+        S.tree_levels = l;
+    }
+    bsync<NT>();
+    for (int l = 1; l <= S.tree_levels; l++) {
+        const u64 *src = ctree_level(S, l - 1);
+        u64 *dst = M.ctree + S.tree_off[l];
+        const int nsrc = S.tree_n[l - 1];
+        for (int q = wid; q < S.tree_n[l]; q += NW) {
+            const int c = q * 32 + lane;
+            const u64 k = warp_min64(c < nsrc ? src[c] : KEY_INF);
+            if (lane == 0) dst[q] = k;
+        }
+        bsync<NT>();
+    }
+}
+
+/* the keys of columns cols[0..ncols) (and of column `extra` if >= 0) changed: repair their ancestors */
+template <int NT> __device__ void ctree_update(Shm &S, const int *cols, int ncols, int extra) {
+    Mat &M = S.M;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int tot = ncols + (extra >= 0 ? 1 : 0);
+    for (int l = 1; l <= S.tree_levels; l++) {
+        const u64 *src = ctree_level(S, l - 1);
+        u64 *dst = M.ctree + S.tree_off[l];
+        const int nsrc = S.tree_n[l - 1];
+        for (int q = wid; q < tot; q += NW) {
+            const int j = q < ncols ? cols[q] : extra;
+            const int node = j >> (5 * l);
+            const int c = node * 32 + lane;
+            const u64 k = warp_min64(c < nsrc ? src[c] : KEY_INF);
+            if (lane == 0) dst[node] = k;
+        }
+        bsync<NT>();
+    }
+}
+
+/* the first `maxsearch` live columns in ascending key order -> S.cand_col / S.ncand.  One warp; best-first
+ * walk from the root: the frontier holds rows of 32 sibling keys in shared memory (fk, fi), every lane keeps
+ * the minimum of its own column of the frontier in registers. */
+static __device__ __noinline__ void ctree_topk(Shm &S, int maxsearch, u64 *fk, int *fi, int *flev) {
+    const int lane = threadIdx.x & 31;
+    int nrows = 0, ncand = 0;
+    u64 lk = KEY_INF; int lr = -1;
+    int level = S.tree_levels, base = 0;      /* the row to add next */
+    for (;;) {
+        {   /* add the 32 children [base, base+32) of `level` */
+            const int r = nrows++;
+            const int c = base + lane;
+            const u64 k = c < S.tree_n[level] ? ctree_level(S, level)[c] : KEY_INF;
+            fk[r * 32 + lane] = k; fi[r * 32 + lane] = c;
+            if (lane == 0) flev[r] = level;
+            if (k < lk) { lk = k; lr = r; }
+            __syncwarp();
+        }
+        for (;;) {
+            const u64 best = warp_min64(lk);
+            if (best >= KEY_PARK) { if (lane == 0) S.ncand = ncand; __syncwarp(); return; }
+            const int owner = __ffs((int)__ballot_sync(FULLMASK, lk == best)) - 1;
+            const int r = __shfl_sync(FULLMASK, lr, owner);
+            const int lev = flev[r], id = fi[r * 32 + owner];
+            if (lane == owner) {      /* consume the entry; this lane's minimum is recomputed over its column */
+                fk[r * 32 + lane] = KEY_INF;
+                lk = KEY_INF; lr = -1;
+                for (int q = 0; q < nrows; q++) { const u64 k = fk[q * 32 + lane]; if (k < lk) { lk = k; lr = q; } }
+            }
+            __syncwarp();
+            if (lev == 0) {
+                if (lane == 0) S.cand_col[ncand] = id;
+                ncand++;
+                if (ncand >= maxsearch) { if (lane == 0) S.ncand = ncand; __syncwarp(); return; }
+            } else { level = lev - 1; base = id * 32; break; }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ */
 /* Markowitz search, markowitz.rs:34-193 (search_rows == 0 path)       */
 /* ------------------------------------------------------------------ */
 template <int NT> __device__ void markowitz_search(Shm &S) {
@@ -106,7 +203,7 @@ template <int NT> __device__ void markowitz_search(Shm &S) {
     if (maxsearch > MAXCAND) maxsearch = MAXCAND;
 
     /* shrink the active-column list when more than half of it is dead */
-    if (S.ndead * 2 > S.nact && S.nact > 2 * NT) {
+    if (!S.use_tree && S.ndead * 2 > S.nact && S.nact > 2 * NT) {
         int *tmp = M.tmpi;
         int put = 0;
         for (int base = 0; base < S.nact; base += NT) {
@@ -127,6 +224,17 @@ template <int NT> __device__ void markowitz_search(Shm &S) {
     /* the first `maxsearch` live columns in ascending (count, stamp) order */
     int ncand = 0;
     u64 prev = 0; int have_prev = 0;
+    if (S.use_tree) {
+        if (wid == 0) {
+            /* frontier: 1 + maxsearch * levels rows of 32 (key, node) pairs in the (idle) pivot-step buffers */
+            u64 *fk = (u64 *)S.cval;
+            const int maxrows = 2 + maxsearch * (S.tree_levels + 1);
+            int *fi = (int *)(fk + maxrows * 32);
+            ctree_topk(S, maxsearch, fk, fi, fi + maxrows * 32);
+        }
+        bsync<NT>();
+        ncand = S.ncand;
+    } else
     while (ncand < maxsearch) {
         u64 k0 = KEY_INF, k1 = KEY_INF, k2 = KEY_INF;
         int j0 = -1, j1 = -1, j2 = -1;
@@ -1320,8 +1428,15 @@ template <int NT> __device__ void phase_bump(Shm &S) {
     const int m = M.m, tid = threadIdx.x;
     BLU_DYN_SMEM(dyn_);
     DenseSm dsm; dense_view(dsm, dyn_, S.kd, S.kw);
-    if (tid == 0) { S.lput = M.l_begin_p[S.rank]; S.uput = M.u_begin[S.rank]; }
+    if (tid == 0) {
+        S.lput = M.l_begin_p[S.rank]; S.uput = M.u_begin[S.rank];
+        int ms = M.prm.maxsearch < 1 ? 1 : M.prm.maxsearch, lv = 0;
+        for (int n = m; n > 32 && lv < 7; lv++) n = (n + 31) / 32;
+        const int rows = 2 + ms * (lv + 1);
+        S.use_tree = S.nact > M.tree_min && ms <= TREE_MAX_SEARCH && M.prm.search_rows == 0 && S.dyn_bytes >= rows * (32 * 12 + 4);
+    }
     bsync<NT>();
+    if (S.use_tree) ctree_build<NT>(S);
     while (S.rank + S.rankdef < m) {
         i64 t0 = clock64();
         if (!S.dense && S.kd > 0 && m - S.rank <= S.kd && m - S.rank >= DENSE_MIN_ROWS &&
@@ -1333,7 +1448,7 @@ template <int NT> __device__ void phase_bump(Shm &S) {
                 return;
             }
             dense_enter_d<NT>(S);
-            if (tid == 0) S.t_phase[13] += clock64() - t0;
+            if (tid == 0) { S.t_phase[13] += clock64() - t0; S.use_tree = 0; }      /* at most dense_k columns are left: the scan is cheap */
             if (S.status != BLU_OK) return;
             t0 = clock64();
         }
@@ -1346,6 +1461,7 @@ template <int NT> __device__ void phase_bump(Shm &S) {
             bsync<NT>();
             if (tid == 0) { M.ckey[pc] = KEY_INF; if (S.dense) dsm.skeyc[S.dpc] = KEY_INF; S.ndead++; S.rankdef++; }
             bsync<NT>();
+            if (S.use_tree) ctree_update<NT>(S, (const int *)0, 0, pc);
             continue;
         }
         const int rank = S.rank;
@@ -1401,6 +1517,12 @@ template <int NT> __device__ void phase_bump(Shm &S) {
         post_remove_cols<NT>(S, rank);
         if (tid == 0) S.t_phase[10] += clock64() - t0;
         if (S.status != BLU_OK) return;
+        if (S.use_tree) {
+            /* the keys that changed belong to the columns of the pivot row, whose (unlinked) line still sits in W */
+            t0 = clock64();
+            ctree_update<NT>(S, M.w_idx + M.lbeg[m + pr], nz_row, -1);
+            if (tid == 0) S.t_phase[3] += clock64() - t0;
+        }
     }
 }
 

@@ -215,6 +215,8 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     d.prm.nzbias = 1; d.prm.maxsearch = 3; d.prm.pad = 4; d.prm.stretch = 0.3;
     d.prm.compress_thres = 0.5; d.prm.sparse_thres = 0.05; d.prm.search_rows = 0;
     d.gwork_warps = 32;
+    d.tree_min = 4096;
+    if (const char *e = getenv("BLU_B200_TREE_MIN")) d.tree_min = atoi(e);      /* tuning / test knob, same as BLU_P_TREE_MIN */
     const size_t n = (size_t)nmat, M = (size_t)m;
     int st = BLU_OK;
 #define A(p, cnt) if (st == BLU_OK) st = dalloc(o, &(p), (cnt))
@@ -222,7 +224,7 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     A(d.pinv, n * M); A(d.qinv, n * M); A(d.prank, n * M); A(d.qrank, n * M);
     A(d.colpiv, n * M); A(d.rowpiv, n * M);
     A(d.lbeg, n * 2 * M); A(d.lend, n * 2 * M); A(d.lcap, n * 2 * M);
-    A(d.ckey, n * M); A(d.rkey, n * M);
+    A(d.ckey, n * M); A(d.rkey, n * M); A(d.ctree, n * (M / 31 + 72));
     A(d.l_begin_p, n * (M + 1)); A(d.u_begin, n * (M + 1)); A(d.l_begin, n * (M + 1));
     A(d.lt_begin, n * (M + 1)); A(d.lt_begin_p, n * (M + 1)); A(d.p, n * (M + 1));
     A(d.r_begin, n * (M + 1)); A(d.eta_row, n * (M + 1));
@@ -813,6 +815,7 @@ extern "C" int blu_set_param(blu_t *o, int what, double v) {
         break;
     }
     case BLU_P_SPLIT_MIN: o->split_min = (int)v; break;
+    case BLU_P_TREE_MIN: o->d.tree_min = (int)v; break;
     case BLU_P_L_MEM: case BLU_P_U_MEM: case BLU_P_W_MEM: {
         int64_t n = (int64_t)v;
         if (n < 1) return BLU_ERROR_INVALID_ARGUMENT;
@@ -852,6 +855,7 @@ extern "C" double blu_get_param(const blu_t *o, int what) {
     case BLU_P_DENSE_K: return o->d.dense_k;
     case BLU_P_TAIL_THREADS: return o->tail_threads;
     case BLU_P_SPLIT_MIN: return o->split_min;
+    case BLU_P_TREE_MIN: return o->d.tree_min;
     default: return 0.0;
     }
 }

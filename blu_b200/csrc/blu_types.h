@@ -101,6 +101,7 @@ struct BluDev {
     int *w_idx; double *w_val;
     int *lbeg, *lend, *lcap;    /* 2m each */
     blu_u64 *ckey, *rkey;       /* m each */
+    blu_u64 *ctree;             /* m/31 + 72 per basis: min-tree (fanout 32) over ckey for the Markowitz search of large bumps */
     int *l_begin_p, *u_begin;   /* m+1 each */
     int *l_begin, *lt_begin, *lt_begin_p, *p, *r_begin, *eta_row; /* m+1 each */
     int *len_uc;                  /* m: entries of the U column of pivot k */
@@ -124,6 +125,7 @@ struct BluDev {
     /* dense tail (blu_factor_dense.cuh): the last dense_k x dense_k active submatrix as a row-major value
      * array, per-entry storage-order keys, and row/column presence bitmaps.  dense_k = 0: disabled. */
     int dense_k;
+    int tree_min;               /* bumps with more columns than this search through the min-tree (ctree) */
     double *dn_val;             /* dense_k^2 per basis */
     BluKey2 *dn_key;            /* dense_k^2 per basis: (position key in its column, position key in its row) */
     unsigned *dn_rbits, *dn_cbits; /* dense_k * dense_k/32 each per basis */

@@ -20,7 +20,11 @@
  * vectors; D5 64-bit cancellation mask; D6 markowitz loop advance; D7 sentinel
  * refresh after reallocation; D9 get_factors before factorize -> INVALID_CALL;
  * D12 signed arithmetic in update() compression tests; D13 BLU::solve_for_update
- * computes no solution when want_solution == 0 (blu.rs:268-283 always passes Some(lhs)).  D8 (search_rows
+ * computes no solution when want_solution == 0 (blu.rs:268-283 always passes Some(lhs)); D14 bfs_path's
+ * `for front in 0..tail` (update.rs:68) fixes the range at entry although `tail` grows inside the loop, so the
+ * reference's augmenting-path search never leaves j0 -- the oracle uses BASICLU's dynamic bound.  Every repair
+ * sits behind a compile-time flag BLO_REPAIR_Dn (blo_int.h, default 1; 0 = the Rust source's behaviour, with
+ * a named trap where that is a panic or an endless loop).  D8 (search_rows
  * default 0) is REPRODUCED.  D11 (release-mode file_diff asserts in
  * setup_bump) is behind the run-time flag `check_file_diff` (default on, as
  * in the reference).

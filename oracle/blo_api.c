@@ -100,12 +100,17 @@ int blo_solve_for_update(blo *o, lint nzrhs, const lint *irhs, const double *xrh
          * want_solution == 0 the solution is still scattered into lhs while nzlhs is not
          * recorded and lu_clear_lhs (blu.rs:380-395) later clears the wrong entries.
          * BASICLU semantics: no solution unless it was asked for. */
+#if BLO_REPAIR_D13
         if (want_solution) {
             st = blo_lu_solve_for_update(&o->lu, nzrhs, irhs, xrhs, &nzlhs, o->ilhs, o->lhs, trans);
             o->nzlhs = nzlhs;
         } else {
             st = blo_lu_solve_for_update(&o->lu, nzrhs, irhs, xrhs, NULL, NULL, NULL, trans);
         }
+#else
+        st = blo_lu_solve_for_update(&o->lu, nzrhs, irhs, xrhs, &nzlhs, o->ilhs, o->lhs, trans);   /* blu.rs:268-283 as written */
+        if (want_solution) o->nzlhs = nzlhs;
+#endif
         if (st != BLO_REALLOCATE) break;
         realloc_obj(o);
     }
@@ -127,7 +132,10 @@ int blo_update(blo *o, double xtbl) {
 int blo_lu_get_factors(blo_lu *lu, lint *rowperm, lint *colperm,
                        lint *l_colptr, lint *l_rowidx, double *l_value_,
                        lint *u_colptr, lint *u_rowidx, double *u_value_) {
-    if (lu->nupdate != 0) return BLO_ERROR_INVALID_CALL; /* D9: also covers "never factorized" */
+#if !BLO_REPAIR_D9
+    if (lu->nupdate < 0) BLO_DEFECT_TRAP("D9", "get_factors.rs:59 unwraps nupdate == None (panic)");
+#endif
+    if (lu->nupdate != 0) return BLO_ERROR_INVALID_CALL; /* D9 repaired: also covers "never factorized" */
     const lint m = lu->m;
     if (rowperm) memcpy(rowperm, lu->pivotrow, (size_t)m * sizeof(lint));
     if (colperm) memcpy(colperm, lu->pivotcol, (size_t)m * sizeof(lint));

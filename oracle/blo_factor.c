@@ -344,6 +344,9 @@ int blo_markowitz(blo_lu *lu) {
             assert(w_end[j] - w_begin[j] == nz);
             double cmx = colmax[j];
             assert(cmx >= 0.0);
+#if !BLO_REPAIR_D6
+            if (cmx == 0.0 || cmx < abstol) BLO_DEFECT_TRAP("D6", "markowitz.rs:90-92 continues without advancing j (endless loop)");
+#endif
             if (cmx == 0.0 || cmx < abstol) continue; /* D6 repaired: advance j.  Reached when a column keeps entries but its pivot-row entry was dropped from U, so pivot.rs:96-106 never emptied it */
             double tol = fmax(abstol, reltol * cmx);
             for (lint pos = w_begin[j]; pos < w_end[j]; pos++) {
@@ -776,9 +779,11 @@ int blo_lu_factorize(blo_lu *lu, const lint *b_begin, const lint *b_end,
         blo_lu_reset(lu);
         lu->task = BLO_TASK_SINGLETONS;
     }
+#if BLO_REPAIR_D7
     /* D7 repair: what BASICLU's lu_load does on every entry */
     lu->addmem_l = lu->addmem_u = lu->addmem_w = 0;
     if (lu->task != BLO_TASK_NONE) lu->w_end[2 * lu->m] = lu->w_mem;
+#endif
 
     switch (lu->task) {
     case BLO_TASK_SINGLETONS:

@@ -3,6 +3,8 @@
 #define BLO_INT_H
 
 #include "blo.h"
+#include <stdio.h>
+#include <stdlib.h>
 #include <assert.h>
 #include <math.h>
 #include <stdlib.h>
@@ -72,5 +74,46 @@ int blo_k_solve_for_update(blo_lu *lu, lint nrhs, const lint *irhs, const double
 int blo_k_update(blo_lu *lu, double xtbl);
 
 void blo_trace_push(blo_lu *lu, lint row, lint col, double pivot, int kind, lint nz_row, lint nz_col);
+
+
+/* ---- repairs of the Rust port's defects ------------------------------------------
+ * Every repair is behind a named compile-time flag, default ON (= BASICLU semantics, what the device path
+ * implements).  Building with -DBLO_REPAIR_Dn=0 restores what the Rust source does at that place; where that
+ * is a panic or an endless loop the oracle stops with a message naming the defect (BLO_DEFECT_TRAP) instead
+ * of corrupting memory or hanging.  `make repairs-off-check` compiles every such variant. */
+#ifndef BLO_REPAIR_D1   /* lu.rs:184-193: eta_row aliases r_begin */
+#define BLO_REPAIR_D1 1
+#endif
+#ifndef BLO_REPAIR_D2   /* update.rs:422-423, 877-878: vec![0; ipivot] instead of [ipivot] */
+#define BLO_REPAIR_D2 1
+#endif
+#ifndef BLO_REPAIR_D3   /* update.rs:634-643: reach vectors one element short */
+#define BLO_REPAIR_D3 1
+#endif
+#ifndef BLO_REPAIR_D4   /* update.rs:797 vs 176-192: permute() handed nswap entries, reads nswap+1 */
+#define BLO_REPAIR_D4 1
+#endif
+#ifndef BLO_REPAIR_D5   /* pivot.rs:645-664, 750: 32-bit cancellation mask round-tripped through f64 */
+#define BLO_REPAIR_D5 1
+#endif
+#ifndef BLO_REPAIR_D6   /* markowitz.rs:90-92: `continue` without advancing j */
+#define BLO_REPAIR_D6 1
+#endif
+#ifndef BLO_REPAIR_D7   /* blu.rs:345-377, lu.rs:308-314: sentinel / addmem not refreshed after reallocation */
+#define BLO_REPAIR_D7 1
+#endif
+#ifndef BLO_REPAIR_D9   /* get_factors.rs:59: unwrap() on None instead of ErrorInvalidCall */
+#define BLO_REPAIR_D9 1
+#endif
+#ifndef BLO_REPAIR_D12  /* update.rs:917, 925: usize subtraction wraps */
+#define BLO_REPAIR_D12 1
+#endif
+#ifndef BLO_REPAIR_D13  /* blu.rs:268-283: solve_for_update scatters a solution nobody asked for */
+#define BLO_REPAIR_D13 1
+#endif
+#ifndef BLO_REPAIR_D14  /* update.rs:68: `for front in 0..tail` fixes the range at entry, the BFS never leaves j0 */
+#define BLO_REPAIR_D14 1
+#endif
+#define BLO_DEFECT_TRAP(name, what) do { fprintf(stderr, "blo oracle: reference defect %s reproduced: %s\n", name, what); abort(); } while (0)
 
 #endif

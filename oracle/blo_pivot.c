@@ -285,7 +285,12 @@ static int pivot_small(blo_lu *lu) {
                 put++;
                 if (x > cmx) cmx = x;
             } else {
+#if BLO_REPAIR_D5
                 mask |= (uint64_t)1 << (pos - 1); /* cancellation in row w_index[cbeg+pos] */
+#else
+                if (pos - 1 >= 31) BLO_DEFECT_TRAP("D5", "pivot.rs:659 shifts an i32 mask by >= 31 (debug: panic; release: wrong row pattern)");
+                mask |= (uint64_t)1 << (pos - 1);
+#endif
             }
             work[pos] = 0.0;
         }

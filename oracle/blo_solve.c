@@ -399,7 +399,11 @@ int blo_k_solve_for_update(blo_lu *lu, lint nrhs, const lint *irhs, const double
             work[j] = 0.0;
         }
         lu->r_begin[nforrest + 1] = put;
+#if BLO_REPAIR_D1
         lu->eta_row[nforrest] = ipivot; /* D1 repaired: own array */
+#else
+        lu->r_begin[nforrest] = ipivot; /* lu.rs:184-193 as written: eta_row! expands to the r_begin storage */
+#endif
         lu->btran_for_update = jpivot;
 
         if (!want_solution) { solve_done(lu, tic, l_flops, u_flops, r_flops); return BLO_OK; }
@@ -484,7 +488,9 @@ int blo_lu_solve_for_update(blo_lu *lu, lint nzrhs, const lint *irhs, const doub
         for (lint n = 0; n < nzrhs && ok; n++) ok = ok && irhs[n] >= 0 && irhs[n] < lu->m;
     }
     if (!ok) return BLO_ERROR_INVALID_ARGUMENT;
+#if BLO_REPAIR_D7
     /* D7 repair (lu_load semantics) */
     lu->addmem_l = lu->addmem_u = lu->addmem_w = 0;
+#endif
     return blo_k_solve_for_update(lu, nzrhs, irhs, xrhs, p_nzlhs, ilhs, lhs, trans);
 }

@@ -22,7 +22,15 @@ static lint bfs_path(lint m, lint j0, const lint *begin, const lint *end, const 
     lint j = -1, tail = 1, top = m;
     int found = 0;
     queue[0] = j0;
+    /* D14: update.rs:68 reads `for front in 0..tail` with `tail` grown inside the loop; a Rust range is
+     * evaluated once, so the reference's search never expands beyond j0 and the assert at update.rs:687
+     * fires whenever the path has more than one edge.  Repaired: BASICLU's dynamic bound. */
+#if BLO_REPAIR_D14
     for (lint front = 0; front < tail && !found; front++) {
+#else
+    const lint tail_at_entry = tail;
+    for (lint front = 0; front < tail_at_entry && !found; front++) {
+#endif
         j = queue[front];
         for (lint pos = begin[j]; pos < end[j]; pos++) {
             lint k = index[pos];
@@ -188,6 +196,10 @@ int blo_k_update(blo_lu *lu, double xtbl) {
     const lint ipivot = pmap[jpivot];
     const double oldpiv = lu->col_pivot[jpivot];
     lint ipivot_vec = ipivot, jpivot_vec = jpivot; /* D2 repaired: one-element reach */
+#if !BLO_REPAIR_D2
+    ipivot_vec = 0; jpivot_vec = 0;      /* update.rs:422-423: vec![0; ipivot] -- zeros (and a panic when the length is 0) */
+    if (ipivot == 0 || jpivot == 0) BLO_DEFECT_TRAP("D2", "update.rs:877-878 indexes an empty vec![0; 0] (panic)");
+#endif
     double tic = blo_now();
     assert(nforrest < m);
 
@@ -291,6 +303,9 @@ int blo_k_update(blo_lu *lu, double xtbl) {
         if (istriangular) {
             lu->min_pivot = fmin(lu->min_pivot, fabs(newpiv));
             lu->max_pivot = fmax(lu->max_pivot, fabs(newpiv));
+#if !BLO_REPAIR_D3
+            BLO_DEFECT_TRAP("D3", "update.rs:634-643 indexes reach vectors of nreach-1 elements at nreach-1 (panic)");
+#endif
             nreach = nz_roweta + 1; /* D3 repaired: nreach elements */
             row_reach = iwork1;
             col_reach = iwork2;
@@ -337,6 +352,9 @@ int blo_k_update(blo_lu *lu, double xtbl) {
         }
         if (istriangular) {
             lint nswap = m - top - 1;
+#if !BLO_REPAIR_D4
+            BLO_DEFECT_TRAP("D4", "update.rs:797 hands permute() a slice of nswap entries, it reads jlist[nswap] (panic)");
+#endif
             permute(lu, path + top, nswap); /* D4 repaired: nswap+1 entries visible */
             u_nz--;
             assert(reach[rtop] == jpivot);
@@ -399,13 +417,21 @@ int blo_k_update(blo_lu *lu, double xtbl) {
 
     /* compress U and W when enough was wasted, update.rs:915-937 (D12: signed) */
     lint used = u_begin[m];
+#if BLO_REPAIR_D12
     if (used - u_nz - m > (lint)(lu->compress_thres * (double)used)) {
+#else
+    if ((uint64_t)(used - u_nz - m) > (uint64_t)(lu->compress_thres * (double)used)) {      /* usize arithmetic wraps (release build) */
+#endif
         nz = compress_packed(m, u_begin, u_index, u_value);
         assert(nz == u_nz);
     }
     used = w_begin[m];
     lint need = u_nz + (lint)(stretch * (double)u_nz) + m * pad;
+#if BLO_REPAIR_D12
     if (used - need > (lint)(lu->compress_thres * (double)used)) {
+#else
+    if ((uint64_t)(used - need) > (uint64_t)(lu->compress_thres * (double)used)) {
+#endif
         nz = blo_file_compress(m, w_begin, w_end, w_flink, w_index, w_value, stretch, pad);
         assert(nz == u_nz);
     }
@@ -427,8 +453,10 @@ int blo_k_update(blo_lu *lu, double xtbl) {
 int blo_lu_update(blo_lu *lu, double xtbl) {
     if (lu->nupdate < 0 || lu->ftran_for_update < 0 || lu->btran_for_update < 0)
         return BLO_ERROR_INVALID_CALL;
+#if BLO_REPAIR_D7
     /* D7 repair (lu_load semantics): refresh the file-size sentinel of the m-line file */
     lu->addmem_l = lu->addmem_u = lu->addmem_w = 0;
     lu->w_end[lu->m] = lu->w_mem;
+#endif
     return blo_k_update(lu, xtbl);
 }

@@ -152,6 +152,46 @@ def c4(args):
     return [rec]
 
 
+def c4full(args):
+    """configs[3] at full size: 10^6 rows (ladder network, gen.config4_ladder), factorize + 1,000 Gilbert-Peierls
+    solves with 0.1 %-dense right-hand sides."""
+    cp, ri, v = gen.config4_ladder()
+    m = len(cp) - 1
+    g = BLU(m, len(v)); g.threads_per_basis = 1024
+    o = Oracle(m, 40 * len(v)); o.set_param("check_file_diff", 0)
+    sg, tg = wall(lambda: g.factorize(cp[:-1], cp[1:], ri, v))
+    so, to = wall(lambda: o.factorize(cp[:-1], cp[1:], ri, v))
+    byt = factor_bytes(g, m)
+    rec = {"config": f"configs[3] FULL SIZE: circuit-like ladder network, m={m}, nnz={len(v)}", "m": m, "nnz": int(len(v)),
+           "gpu": {"factorize_ms_wall": 1e3 * tg, "status": sg, "nrealloc": g.info("nrealloc"), "threads_per_basis": 1024,
+                   "search_kcycles": g.info("t_phase3") / 1e3, "total_kcycles": g.info("t_phase11") / 1e3},
+           "cpu_oracle_1thread": {"factorize_ms": 1e3 * to, "status": so},
+           "stats": {k: g.info(k) for k in ("rank", "bump_size", "bump_nz", "l_nz", "u_nz", "factor_flops", "nsearch_pivot", "ngarbage", "nexpand")},
+           "roofline": {"bound": "latency (one basis = one CTA)", "algorithmic_bytes": byt, "achieved_gbs": byt / tg / 1e9, "peak_gbs": HBM_PEAK, "frac": byt / tg / 1e9 / HBM_PEAK},
+           "parity": {"status_equal": sg == so, "factors_bit_identical": same_factors(g, o),
+                      "stats_equal": all(g.info(k) == o.info(k) for k in ("rank", "l_nz", "u_nz", "factor_flops", "nsearch_pivot"))}}
+    nrhs, nz, chunk = args.nrhs or 1000, m // 1000, 50
+    rl = [gen.sparse_rhs_np(6000 + r, m, nz) for r in range(nrhs)]
+    tsm, same, checked, nzl = 0.0, True, 0, 0
+    tco = 0.0
+    for c0 in range(0, nrhs, chunk):
+        (ssm, outm, statm), dt = wall(lambda: g.solve_sparse_multi(rl[c0:c0 + chunk], "N"))
+        tsm += dt
+        same = same and ssm == 0
+        nzl += sum(len(x[0]) for x in outm)
+        for r in (c0, c0 + chunk - 1)[:1 if c0 else 2]:      # bit-exact comparison of a sample against the oracle
+            _, dt = wall(lambda: o.solve_sparse(nz, rl[r][0], rl[r][1], "N")); tco += dt
+            n_ = o.nzlhs
+            same = same and len(outm[r - c0][0]) == n_ and np.array_equal(outm[r - c0][0], o.ilhs[:n_]) and np.array_equal(outm[r - c0][1], o.lhs[o.ilhs[:n_]])
+            checked += 1
+    rec["solve_sparse_multi"] = {"nrhs": nrhs, "nzrhs": nz, "avg_nzlhs": nzl / nrhs, "gpu_ms_total": 1e3 * tsm, "gpu_ms_per_rhs": 1e3 * tsm / nrhs,
+                                 "cpu_oracle_ms_per_rhs": 1e3 * tco / max(checked, 1), "compared_with_oracle": checked,
+                                 "bit_identical_pattern_order_and_values": bool(same)}
+    _, dt = wall(lambda: g.solve_sparse(nz, rl[0][0], rl[0][1], "N"))
+    rec["solve_sparse_single_call_ms"] = 1e3 * dt
+    return [rec]
+
+
 def c5(args):
     m, bump, nupd = (100000, 2000, 500) if not args.quick else (20000, 1000, 60)
     cp, ri, v = gen.config3(m, bump, seed=7001)
@@ -223,7 +263,7 @@ def main():
     ap.add_argument("which", nargs="*", default=["c1", "c3", "c4", "c5"])
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    fns = dict(c1=c1, c3=c3, c4=c4, c5=c5)
+    fns = dict(c1=c1, c3=c3, c4=c4, c4full=c4full, c5=c5)
     with open(args.out, "a") as f:
         for w in args.which:
             t = time.time()

@@ -3,7 +3,7 @@ import numpy as np
 from oracle_lib import Oracle
 
 STATS = ["rank", "bump_size", "bump_nz", "matrix_nz", "l_nz", "u_nz", "factor_flops", "nsearch_pivot",
-         "min_pivot", "max_pivot", "nelim_div",
+         "min_pivot", "max_pivot", "nelim_div", "elim_bytes",      # elim_bytes: the numerator of bench.py's roofline
          # the tail of factorize (factorize.rs:121-147): condest x2, residual_test, matrix_norm
          "condest_l", "condest_u", "norm_l", "norm_u", "normest_l_inv", "normest_u_inv", "onenorm", "infnorm",
          "residual_test", "update_cost"]

@@ -424,3 +424,28 @@ def test_emu_batch_replay_after_private_stores(emu):
     for k, o in enumerate(oracles):
         _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "T")
         assert np.array_equal(x[k], xo)
+
+
+@pytest.mark.parametrize("m,seed,nslack,dens,nt,kd,ms", [(300, 5, 60, 3.0, 128, 0, 3), (400, 6, 80, 3.0, 256, 64, 4), (1200, 7, 100, 2.0, 128, 32, 1)])
+def test_emu_tree_search(emu, m, seed, nslack, dens, nt, kd, ms):
+    """Markowitz candidates through the min-tree over the column keys (blu_factor_bump.cuh ctree_*), forced on
+    for small bumps with tree_min: same pivots, same nsearch_pivot as the bucket walk of markowitz.rs:80-123."""
+    cp, ri, v = gen.basis(seed, m, nslack, dens)
+    o = oracle_for(m, len(v), 100)
+    o.set_param("maxsearch", ms)
+    assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+    g = BLU(m, len(v), lib=emu)
+    g.threads_per_basis = nt; g.dense_k = kd; g.maxsearch = ms; g.tree_min = 16
+    assert g.factorize(cp[:-1], cp[1:], ri, v) == 0
+    assert_factor_parity(g, o)
+
+
+def test_emu_tree_search_structures(emu):
+    """... with rank deficiency and emptied columns (the tree is repaired after remove_col, pivot.rs:1333-1381)."""
+    from parity import structured_case
+    os.environ["BLU_B200_TREE_MIN"] = "8"; os.environ["BLU_B200_DENSE_K"] = "32"
+    try:
+        for seed, m in [(9000, 120), (9005, 90), (9006, 150), (9003, 130)]:
+            structured_case(lambda mm, nnz: BLU(mm, nnz, lib=emu), m, seed, nupd=2)
+    finally:
+        del os.environ["BLU_B200_TREE_MIN"]; del os.environ["BLU_B200_DENSE_K"]

@@ -368,13 +368,14 @@ def _residual(cp, ri, v, m, x, b, trans="N"):
 
 
 def test_config2_full_batch_properties():
-    """configs[1] at full size: 4,096 bases of 2,000^2 through blu_batch_factorize (pipelined upload) +
-    blu_batch_solve_dense.  Every basis must come back OK with full rank and a small residual; a sample
-    is compared with the oracle bit for bit."""
+    """configs[1] at full size: 4,096 bases of 2,000^2 through blu_batch_factorize (pipelined upload, head /
+    tail / build launches, default store sizes with per-basis Reallocate) + blu_batch_solve_dense.  Every basis
+    must come back OK with full rank and a small residual; 64 of them are compared with the oracle bit for bit
+    (factors, counters, solution)."""
+    from parity import STATS
     nmat, m = 4096, 2000
     bb, be, bi, bx, rhs = gen.batch(nmat, m, 700, 5.0, 2000, 3000)
     b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()))
-    b.l_mem = 100000; b.u_mem = 100000; b.w_mem = 900000
     st, status = b.factorize(bb, be, bi, bx)
     assert st == 0 and (status == 0).all()
     st, x, sst = b.solve_dense(rhs, "N")
@@ -386,7 +387,7 @@ def test_config2_full_batch_properties():
         worst = max(worst, _residual(cp, bi[lo:hi], bx[lo:hi], m, x[k], rhs[k * m:(k + 1) * m]))
         assert b.info(k, "rank") == m and b.info(k, "residual_test") < 1e-10
     assert worst < 1e-10, worst
-    for k in (0, 2047, 4095):
+    for k in list(range(0, nmat, 65)) + [4095]:      # 64 + 1 bases
         cp, ri, v = gen.basis(2000 + k, m, 700, 5.0)
         o = oracle_for(m, len(v))
         assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
@@ -394,6 +395,8 @@ def test_config2_full_batch_properties():
         _, fg = b.get_factors(k)
         for key in fo:
             assert np.array_equal(fo[key], fg[key]), (k, key)
+        for name in STATS:
+            assert o.info(name) == b.info(k, name), (k, name)
         _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
         assert np.array_equal(x[k], xo)
 
@@ -572,3 +575,58 @@ def test_dense_tail_structures():
             structured_case(lambda mm, nnz: BLU(mm, nnz), m, seed, nupd=4)
     finally:
         del os.environ["BLU_B200_DENSE_K"]
+
+
+def test_config4_full_size():
+    """configs[3] at FULL size: 10^6 rows (gen.config4_ladder: the circuit-like ladder network; the square grid
+    is beyond any CPU oracle), Markowitz candidates through the min-tree (10^6 active columns).
+    Factors, permutations and counters equal the oracle's bit for bit; of the 1,000 Gilbert-Peierls solves with
+    0.1 %-dense right-hand sides a first block runs through blu_solve_sparse_multi and is compared with the
+    oracle (pattern ORDER and values), plus one plain solve_sparse call."""
+    cp, ri, v = gen.config4_ladder()
+    m = len(cp) - 1
+    assert m == 1000000
+    g = BLU(m, len(v))
+    g.threads_per_basis = 1024
+    o = Oracle(m, 40 * len(v))
+    o.set_param("check_file_diff", 0)
+    assert g.factorize(cp[:-1], cp[1:], ri, v) == o.factorize(cp[:-1], cp[1:], ri, v) == 0
+    assert g.info("bump_size") == m and g.info("rank") == m
+    assert_factor_parity(g, o)
+    nz = m // 1000
+    rl = [gen.sparse_rhs_np(6000 + r, m, nz) for r in range(24)]
+    for tr in "NT":
+        st, out, stat = g.solve_sparse_multi(rl, tr)
+        assert st == 0 and (stat == 0).all()
+        for r in (0, 7, 23):
+            assert o.solve_sparse(nz, rl[r][0], rl[r][1], tr) == 0
+            n = o.nzlhs
+            assert len(out[r][0]) == n and np.array_equal(out[r][0], o.ilhs[:n]), (tr, r)
+            assert np.array_equal(out[r][1], o.lhs[o.ilhs[:n]]), (tr, r)
+    assert g.solve_sparse(nz, rl[1][0], rl[1][1], "N") == o.solve_sparse(nz, rl[1][0], rl[1][1], "N") == 0
+    n = o.nzlhs
+    assert g.nzlhs == n and np.array_equal(g.ilhs[:n], o.ilhs[:n]) and np.array_equal(g.lhs, o.lhs)
+
+
+def test_config5_replay_100k():
+    """configs[4]: a 100,000-row basis (gen.config3 structure, bump 2,000), 60 column replacements through
+    solve_for_update 'N'+'T' and update (Forrest-Tomlin and permutation updates), everything observable
+    bit-identical to the oracle; then the refactorization of the final basis."""
+    from parity import replay_updates
+    m, bump, nupd = 100000, 2000, 60
+    cp, ri, v = gen.config3(m, bump, seed=7001)
+    pool = gen.column_pool(7002, m, nupd)
+    g = BLU(m, len(v))
+    g.threads_per_basis = 1024
+    o = Oracle(m, 40 * len(v) + 8 * bump * bump)
+    o.set_param("check_file_diff", 0)
+    assert g.factorize(cp[:-1], cp[1:], ri, v) == o.factorize(cp[:-1], cp[1:], ri, v) == 0
+    assert_factor_parity(g, o)
+    kinds = replay_updates(g, o, m, pool, nupd, check_dense=False)
+    assert "ft" in kinds
+    assert g.info("nupdate") == o.info("nupdate") >= 50
+    b = gen.rhs(7003, m)
+    for tr in "NT":
+        _, xo = o.solve_dense(b, tr)
+        sg, xg = g.solve_dense(b, tr)
+        assert sg == 0 and np.array_equal(xg, xo), tr

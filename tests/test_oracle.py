@@ -190,3 +190,55 @@ def test_batch_driver_matches_single_instances():
         o.factorize(cp[:-1], cp[1:], ri, v)
         _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
         assert np.array_equal(x[k], xo)
+
+
+def _ref_case(seed):
+    """One random or structured matrix + one random setting of the tunables that steer pivot choice."""
+    import scipy.sparse as sp
+    from parity import structured_matrix
+    rng = np.random.default_rng(seed)
+    m = int(rng.integers(6, 70))
+    kind = seed % 9
+    if kind < 6:
+        cp, ri, v = structured_matrix(kind, m, rng)
+    else:
+        dens = [0.08, 0.2, 0.5][kind - 6]
+        A = sp.random(m, m, density=dens, format="csc", random_state=rng, data_rvs=lambda n: rng.uniform(-1, 1, n)) + sp.diags(rng.uniform(0.5, 2, m))
+        A = sp.csc_matrix(A); A.sort_indices()
+        cp, ri, v = A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.astype(np.float64)
+    prm = dict(abstol=[1e-14, 1e-8, 1e-3][int(rng.integers(3))], reltol=[0.1, 0.01, 0.5, 1.0][int(rng.integers(4))],
+               droptol=[1e-20, 1e-12, 1e-2][int(rng.integers(3))], maxsearch=int(rng.integers(1, 6)),
+               search_rows=int(rng.integers(2)), nzbias=[1, -1][int(rng.integers(2))])
+    return m, cp, ri, v, prm
+
+
+def test_second_restatement_agrees_on_pivot_sequences():
+    """oracle/blo_ref_pivots.py is a second reading of singletons.rs / setup_bump.rs / markowitz.rs / pivot.rs
+    with different data structures.  On >= 1000 random and structured matrices (exact cancellation, rank
+    deficiency, dense blocks, bad scaling; search_rows 0 and 1; maxsearch 1..5; several tolerances) it must
+    choose the same pivots in the same order as the C oracle -- a shared misreading of tie-breaking or
+    bucket order would show here."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from blo_ref_pivots import RefLU
+    ncase, checked, outside = 1100, 0, 0
+    for seed in range(20000, 20000 + ncase):
+        m, cp, ri, v, prm = _ref_case(seed)
+        try:
+            ref = RefLU(m, cp, ri, v, **prm).factorize()
+        except AssertionError:
+            outside += 1          # no eligible pivot: factorize_bump.rs:22 asserts, the C oracle aborts there too
+            continue
+        o = Oracle(m, 200 * len(v) + 2000)
+        for k, x in prm.items():
+            o.set_param(k, x)
+        st = o.factorize(cp[:-1], cp[1:], ri, v)
+        assert st in (0, 2), (seed, st)
+        _, f = o.get_factors()
+        rows, cols = ref.permutations()
+        assert int(o.info("rank")) == len(ref.pivots), (seed, prm)
+        assert list(f["rowperm"]) == rows, (seed, prm)
+        assert list(f["colperm"]) == cols, (seed, prm)
+        assert int(o.info("nsearch_pivot")) == ref.nsearch, (seed, prm)
+        checked += 1
+    assert checked >= 1000, (checked, outside)
