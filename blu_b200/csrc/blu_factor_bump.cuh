@@ -353,6 +353,142 @@ template <int NT> __device__ void markowitz_search(Shm &S) {
 }
 
 /* ------------------------------------------------------------------ */
+/* Markowitz search with search_rows != 0, markowitz.rs:34-219          */
+/* Columns and rows are visited in the reference's order -- count by    */
+/* count, the columns of a count before its rows, FIFO inside a bucket  */
+/* (ascending key) -- and every early exit (markowitz.rs:109, 171) and  */
+/* the parking of rows whose cheap entries are all unstable (:178-179,  */
+/* bucket m+1: key count m+1 until an update re-stamps the row,         */
+/* pivot.rs:387-397) is reproduced.  The walk is sequential by nature   */
+/* (each item is judged against the best cost so far), so one item at a */
+/* time: the block finds the next column / row by key, warp 0 judges it.*/
+/* ------------------------------------------------------------------ */
+template <int NT> __device__ void markowitz_search_rows(Shm &S) {
+    Mat &M = S.M;
+    const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double abstol = M.prm.abstol, reltol = M.prm.reltol;
+    int maxsearch = M.prm.maxsearch;
+    if (maxsearch < 1) maxsearch = 1;
+    u64 prevc = 0, prevr = 0; int havec = 0, haver = 0;
+    if (tid == 0) { S.pivot_row = -1; S.pivot_col = -1; S.cand_mc[0] = (i64)m * (i64)m; S.ncand = 0; S.flag_a = 0; }
+    bsync<NT>();
+    for (;;) {
+        /* next column and next row in bucket order */
+        u64 kc = KEY_INF, kr = KEY_INF; int jc = -1, ir = -1;
+        for (int t = tid; t < S.nact; t += NT) {
+            const int j = M.acols[t];
+            const u64 k = M.ckey[j];
+            if (k >= KEY_PARK || (havec && k <= prevc)) continue;
+            if (k < kc) { kc = k; jc = j; }
+        }
+        for (int i = tid; i < m; i += NT) {
+            const u64 k = M.rkey[i];
+            if (k == KEY_INF || key_cnt(k) > m || key_cnt(k) == 0 || (haver && k <= prevr)) continue;      /* gone, parked in bucket m+1, or empty (the walk starts at count 1, markowitz.rs:80) */
+            if (k < kr) { kr = k; ir = i; }
+        }
+        const u64 bc = block_min64<NT>(kc, S.kscr);
+        const u64 br = block_min64<NT>(kr, S.kscr);
+        if (bc == KEY_INF && br == KEY_INF) break;
+        if (kc == bc && bc != KEY_INF) S.iscr[38] = jc;
+        if (kr == br && br != KEY_INF) S.iscr[39] = ir;
+        bsync<NT>();
+        const bool take_col = bc != KEY_INF && (br == KEY_INF || key_cnt(bc) <= key_cnt(br));
+        if (take_col && key_cnt(bc) == 0 && !havec && !haver) {      /* markowitz.rs:73-78: bucket 0 is looked at first (a local test: tid 0 writes S.pivot_col below) */
+            if (tid == 0) { S.pivot_col = S.iscr[38]; S.pivot_row = -1; }
+            bsync<NT>();
+            return;
+        }
+        if (wid == 0) {
+            i64 mc64 = S.cand_mc[0];
+            int nsearch = S.ncand, stop = 0;
+            if (take_col) {
+                const int j = S.iscr[38];
+                const i64 nz1 = key_cnt(bc);
+                const double cmx = M.colpiv[j];
+                const int beg = M.lbeg[j], end = M.lend[j];
+                const double tol = fmax(abstol, reltol * cmx);
+                const i64 thr = (nz1 - 1) * (nz1 - 1);
+                /* markowitz.rs:94-112: strict improvements in storage order; the first improving entry within
+                 * the early-exit bound ends the search */
+                u64 cmin = KEY_INF; int cminpos = -1;
+                for (int base = beg; base < end && !stop; base += 32) {
+                    const int pos = base + lane;
+                    i64 mc = -1; int i = -1;
+                    if (pos < end) {
+                        const double x = fabs(M.w_val[pos]);
+                        if (!(x == 0.0 || x < tol)) { i = M.w_idx[pos]; mc = (nz1 - 1) * (i64)(M.lend[m + i] - M.lbeg[m + i] - 1); }
+                    }
+                    const unsigned hit = __ballot_sync(FULLMASK, mc >= 0 && mc < mc64 && mc <= thr);
+                    if (hit) {
+                        const int l = __ffs((int)hit) - 1;
+                        /* entries before it in this chunk may improve without ending the search, but the exit entry wins */
+                        const int ii = __shfl_sync(FULLMASK, i, l);
+                        const i64 mcl = __shfl_sync(FULLMASK, mc, l);
+                        if (lane == 0) { S.pivot_row = ii; S.pivot_col = j; S.cand_mc[0] = mcl; }
+                        stop = 1;
+                        break;
+                    }
+                    const u64 key = mc >= 0 ? (((u64)mc << 32) | (u64)(unsigned)(pos - beg)) : KEY_INF;
+                    const u64 wmin = warp_min64(key);
+                    if (wmin < cmin) { cmin = wmin; cminpos = beg + (int)(wmin & 0xffffffffu); }
+                }
+                if (!stop) {
+                    if (cmin != KEY_INF && (i64)(cmin >> 32) < mc64) {
+                        if (lane == 0) { S.pivot_row = M.w_idx[cminpos]; S.pivot_col = j; S.cand_mc[0] = (i64)(cmin >> 32); }
+                    }
+                    nsearch++;
+                    if (nsearch >= maxsearch) stop = 1;
+                }
+            } else {
+                const int i = S.iscr[39];
+                const i64 nz1 = key_cnt(br);
+                const int rb = M.lbeg[m + i], re = M.lend[m + i];
+                int cheap = 0, found = 0;
+                for (int rpos = rb; rpos < re && !stop; rpos++) {      /* markowitz.rs:142-176 */
+                    const int j = M.w_idx[rpos];
+                    const int cb = M.lbeg[j], ce = M.lend[j];
+                    const i64 mc = (nz1 - 1) * (i64)(ce - cb - 1);
+                    if (mc >= mc64) continue;
+                    cheap = 1;
+                    const double cmx = M.colpiv[j];
+                    if (cmx == 0.0 || cmx < abstol) continue;
+                    double x = 0.0;
+                    for (int base = cb; base < ce; base += 32) {
+                        const int pos = base + lane;
+                        const int h = pos < ce && M.w_idx[pos] == i;
+                        const unsigned hm = __ballot_sync(FULLMASK, h);
+                        if (hm) { const double v = h ? M.w_val[pos] : 0.0; x = fabs(__shfl_sync(FULLMASK, v, __ffs((int)hm) - 1)); break; }
+                    }
+                    if (x >= abstol && x >= reltol * cmx) {
+                        found = 1;
+                        mc64 = mc;
+                        if (lane == 0) { S.pivot_row = i; S.pivot_col = j; S.cand_mc[0] = mc; }
+                        if (mc64 <= nz1 * (nz1 - 1)) stop = 1;
+                    }
+                }
+                if (!stop) {
+                    if (cheap && !found) {
+                        if (lane == 0) { M.rkey[i] = mkkey(m + 1, S.rstamp); S.rstamp++; }      /* parked, markowitz.rs:178-179 */
+                    } else {
+                        nsearch++;
+                        if (nsearch >= maxsearch) stop = 1;
+                    }
+                }
+            }
+            if (lane == 0) { S.ncand = nsearch; S.flag_a = stop; }
+        }
+        bsync<NT>();
+        if (S.flag_a) break;
+        if (take_col) { prevc = bc; havec = 1; } else { prevr = br; haver = 1; }
+    }
+    if (tid == 0) {
+        BLU_CHECK(S, S.pivot_col >= 0);
+        S.nsearch += S.ncand;      /* (flag_a is lowered by the next user after a barrier of its own, not here: other threads may still be reading it) */
+    }
+    bsync<NT>();
+}
+
+/* ------------------------------------------------------------------ */
 /* helpers shared by the elimination variants                          */
 /* ------------------------------------------------------------------ */
 
@@ -1452,7 +1588,7 @@ template <int NT> __device__ void phase_bump(Shm &S) {
             if (S.status != BLU_OK) return;
             t0 = clock64();
         }
-        if (S.dense) dense_search_d<NT>(S); else markowitz_search<NT>(S);
+        if (S.dense) dense_search_d<NT>(S); else if (M.prm.search_rows != 0) markowitz_search_rows<NT>(S); else markowitz_search<NT>(S);
         if (tid == 0) { if (S.dense) S.t_phase[13] += clock64() - t0; else S.t_phase[3] += clock64() - t0; }
         if (S.status != BLU_OK) return;
         const int pc = S.pivot_col, pr = S.pivot_row;

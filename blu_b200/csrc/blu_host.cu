@@ -793,11 +793,7 @@ extern "C" int blu_set_param(blu_t *o, int what, double v) {
     case BLU_P_STRETCH: p.stretch = v; break;
     case BLU_P_COMPRESS_THRES: p.compress_thres = v; break;
     case BLU_P_SPARSE_THRES: p.sparse_thres = v; break;
-    case BLU_P_SEARCH_ROWS:
-        /* markowitz.rs:125-189 (row search) is not on the device; the reference's default is 0 (D8).
-         * Refuse loudly rather than factorize with a different pivot rule than the caller asked for. */
-        if ((int)v != 0) { fprintf(stderr, "blu_b200: search_rows != 0 is not supported by the device path\n"); return BLU_ERROR_INVALID_ARGUMENT; }
-        p.search_rows = 0; break;
+    case BLU_P_SEARCH_ROWS: p.search_rows = (int)v != 0; break;      /* markowitz.rs:125-189 (markowitz_search_rows); the crate's default is 0 (D8) */
     case BLU_P_REALLOC_FACTOR: o->realloc_factor = v; break;
     case BLU_P_NORMS: o->norms = v != 0.0; break;
     case BLU_P_DENSE_K: {

@@ -217,6 +217,7 @@ TUNABLES = dict(            # the `pub` tunables of LU (lu.rs:10-66), values on 
     stretch=[0.1, 0.3, 1.0],
     compress_thres=[0.05, 0.5, 1.0],
     sparse_thres=[0.0, 0.05, 0.5, 1.0],
+    search_rows=[0, 0, 1],      # markowitz.rs:125-189; the crate's default is 0 (D8)
 )
 
 

@@ -449,3 +449,26 @@ def test_emu_tree_search_structures(emu):
             structured_case(lambda mm, nnz: BLU(mm, nnz, lib=emu), m, seed, nupd=2)
     finally:
         del os.environ["BLU_B200_TREE_MIN"]; del os.environ["BLU_B200_DENSE_K"]
+
+
+@pytest.mark.parametrize("seed", [100, 101, 104, 107, 110, 113, 117, 131])
+def test_emu_row_search(emu, seed):
+    """search_rows != 0 (markowitz.rs:125-189 on the device: markowitz_search_rows): columns and rows visited
+    count by count in bucket order, both early exits, rows parked in bucket m+1 until re-stamped."""
+    from parity import structured_matrix
+    rng = np.random.default_rng(seed)
+    m = int(rng.integers(20, 160))
+    if seed % 3 == 0:
+        cp, ri, v = gen.basis(seed, m, m // 4, 3.0 + seed % 4)
+    else:
+        cp, ri, v = structured_matrix(seed % 6, m, rng)
+    ms = int(rng.integers(1, 6)); reltol = [0.1, 0.5, 1.0, 0.01][seed % 4]
+    o = oracle_for(m, len(v), 400)
+    for k, x in (("search_rows", 1), ("maxsearch", ms), ("reltol", reltol)):
+        o.set_param(k, x)
+    so = o.factorize(cp[:-1], cp[1:], ri, v)
+    g = BLU(m, len(v), lib=emu)
+    g.threads_per_basis = [32, 64, 128][seed % 3]; g.search_rows = 1; g.maxsearch = ms; g.reltol = reltol
+    assert g.factorize(cp[:-1], cp[1:], ri, v) == so
+    if so in (0, 2):
+        assert_factor_parity(g, o)

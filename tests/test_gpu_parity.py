@@ -10,6 +10,7 @@ import scipy.sparse as sp
 
 from blu_b200 import BLU, BLUBatch, gen
 from parity import oracle_for, assert_factor_parity, assert_backward_error, structured_case
+from oracle_lib import Oracle
 
 pytestmark = pytest.mark.gpu
 
