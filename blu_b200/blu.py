@@ -91,6 +91,10 @@ def load_library(path=None):
     L.blu_batch_synchronize.argtypes = [vp]
     L.blu_batch_last_kernel_ms.argtypes = [vp, ctypes.c_int]; L.blu_batch_last_kernel_ms.restype = ctypes.c_double
     L.blu_batch_launch_count.argtypes = [vp]; L.blu_batch_launch_count.restype = ctypes.c_int64
+    L.blu_multi_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, i32p, ctypes.c_int]
+    L.blu_multi_destroy.argtypes = [vp]
+    L.blu_multi_factorize_solve.argtypes = [vp, i64p, i64p, i64p, f64p, ctypes.c_int64, f64p, f64p, ctypes.c_char, i32p]
+    L.blu_multi_part.argtypes = [vp, ctypes.c_int, i64p, i64p]; L.blu_multi_part.restype = vp
     L.blu_version.restype = ctypes.c_char_p
     if path == library_path():
         _LIB = L
@@ -370,3 +374,51 @@ class BLUBatch(_Base):
 
     def synchronize(self):
         return self._L.blu_batch_synchronize(self._h)
+
+
+class BLUMulti:
+    """One batch of independent bases spread over several GPUs of this process (blu_multi_*: contiguous
+    ranges per device, one host thread and stream each, no collective -- SURVEY.md 8e)."""
+
+    def __init__(self, nmat, m, bnz_cap, devices, lib=None):
+        self._L = lib or load_library()
+        self.nmat, self.m = int(nmat), int(m)
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        h = ctypes.c_void_p()
+        st = self._L.blu_multi_create(ctypes.byref(h), self.nmat, self.m, int(bnz_cap), dev.ctypes.data_as(i32p), len(dev))
+        if st != 0:
+            raise RuntimeError(f"blu_multi_create failed with status {st} (no CUDA device? there is no CPU path)")
+        self._h = h
+        self.ndev = len(dev)
+
+    def factorize_solve(self, b_begin, b_end, b_i, b_x, rhs=None, trans="N"):
+        bb, be, bi, bx = _i64(b_begin), _i64(b_end), _i64(b_i), _f64(b_x)
+        status = np.zeros(self.nmat, dtype=np.int32)
+        r = _f64(rhs).reshape(-1) if rhs is not None else None
+        x = np.zeros(self.nmat * self.m) if rhs is not None else None
+        st = self._L.blu_multi_factorize_solve(self._h, _pi(bb), _pi(be), _pi(bi), _pf(bx), len(bi), _pf(r), _pf(x), _ch(trans), status.ctypes.data_as(i32p))
+        return st, (x.reshape(self.nmat, self.m) if x is not None else None), status
+
+    def part(self, d):
+        """(batch handle usable with blu_batch_get_info / get_factors, first basis, number of bases) of device slot d"""
+        first, count = ctypes.c_int64(), ctypes.c_int64()
+        h = self._L.blu_multi_part(self._h, int(d), ctypes.byref(first), ctypes.byref(count))
+        return h, first.value, count.value
+
+    def info(self, k, name):
+        for d in range(self.ndev):
+            h, first, count = self.part(d)
+            if first <= k < first + count:
+                return self._L.blu_batch_get_info(h, int(k - first), I[name])
+        raise IndexError(k)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.blu_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -18,6 +18,9 @@
 #include <vector>
 #include <algorithm>
 #include <time.h>
+#ifndef BLU_EMU
+#include <thread>
+#endif
 
 #define PADDING 160 /* slack entries after the L/U/W stores: warp-wide terminator scans read up to 96 entries ahead */
 
@@ -1360,4 +1363,81 @@ extern "C" int blu_batch_update(blu_batch_t *o, const double *xtbl, int *status)
     }
     o->info_dirty = 1;
     return worst;
+}
+
+/* ------------------------------------------------------------------ */
+/* one batch over several GPUs of one process                          */
+/* ------------------------------------------------------------------ */
+struct blu_multi {
+    int ndev; int64_t nmat, m;
+    std::vector<blu_b200 *> part;
+    std::vector<int64_t> first, count;
+};
+
+extern "C" int blu_multi_create(blu_multi_t **out, int64_t nmat, int64_t m, int64_t bnz_cap, const int *devices, int ndev) {
+    if (!out || !devices || ndev < 1 || nmat < ndev || m < 1) return BLU_ERROR_INVALID_ARGUMENT;
+    blu_multi *mb = new blu_multi();
+    mb->ndev = ndev; mb->nmat = nmat; mb->m = m;
+    const int64_t base = nmat / ndev, extra = nmat % ndev;      /* the split of blu_b200/shard.py */
+    int st = BLU_OK;
+    for (int d = 0; d < ndev && st == BLU_OK; d++) {
+        const int64_t lo = d * base + std::min<int64_t>(d, extra), n = base + (d < extra ? 1 : 0);
+        blu_b200 *p = nullptr;
+        st = create_common(&p, n, m, bnz_cap, devices[d], 0);
+        if (st == BLU_OK) { mb->part.push_back(p); mb->first.push_back(lo); mb->count.push_back(n); }
+    }
+    if (st != BLU_OK) { for (auto *p : mb->part) destroy_common(p); delete mb; return st; }
+    *out = mb;
+    return BLU_OK;
+}
+extern "C" void blu_multi_destroy(blu_multi_t *mb) {
+    if (!mb) return;
+    for (auto *p : mb->part) destroy_common(p);
+    delete mb;
+}
+extern "C" blu_batch_t *blu_multi_part(blu_multi_t *mb, int d, int64_t *first, int64_t *count) {
+    if (!mb || d < 0 || d >= mb->ndev) return nullptr;
+    if (first) *first = mb->first[(size_t)d];
+    if (count) *count = mb->count[(size_t)d];
+    return mb->part[(size_t)d];
+}
+
+/* the work of one device: its range of bases, pointers rebased to the part of b_i / b_x the range uses */
+static int multi_run_part(blu_multi *mb, int d, const int64_t *b_begin, const int64_t *b_end, const int64_t *b_i, const double *b_x,
+                          int64_t bnz_total, const double *rhs, double *lhs, char trans, int *status) {
+    const int64_t lo = mb->first[(size_t)d], n = mb->count[(size_t)d], m = mb->m;
+    const size_t cols = (size_t)(n * m);
+    const int64_t *bb = b_begin + lo * m, *be = b_end + lo * m;
+    int64_t pmin = bnz_total, pmax = 0;
+    for (size_t q = 0; q < cols; q++) { if (be[q] > bb[q]) { pmin = std::min(pmin, bb[q]); pmax = std::max(pmax, be[q]); } }
+    if (pmax <= pmin) { pmin = 0; pmax = 0; }
+    bool inside = pmin >= 0 && pmax <= bnz_total;
+    if (!inside) { pmin = 0; pmax = bnz_total; }      /* out-of-range pointers: let the kernel report them per basis */
+    std::vector<int64_t> rb(cols), re(cols);
+    for (size_t q = 0; q < cols; q++) { rb[q] = bb[q] - pmin; re[q] = be[q] - pmin; }
+    std::vector<int> st((size_t)n, 0);
+    int rc = blu_batch_factorize(mb->part[(size_t)d], rb.data(), re.data(), b_i ? b_i + pmin : nullptr, b_x ? b_x + pmin : nullptr, pmax - pmin, st.data());
+    if (rc == BLU_OK && rhs && lhs) {
+        std::vector<int> ss((size_t)n, 0);
+        rc = blu_batch_solve_dense(mb->part[(size_t)d], rhs + lo * m, lhs + lo * m, trans, ss.data());
+        for (int64_t k = 0; k < n; k++) if (ss[(size_t)k] != BLU_OK && (st[(size_t)k] == BLU_OK || st[(size_t)k] == BLU_WARNING_SINGULAR_MATRIX)) st[(size_t)k] = ss[(size_t)k];
+    }
+    if (status) for (int64_t k = 0; k < n; k++) status[lo + k] = st[(size_t)k];
+    return rc;
+}
+
+extern "C" int blu_multi_factorize_solve(blu_multi_t *mb, const int64_t *b_begin, const int64_t *b_end, const int64_t *b_i,
+                                         const double *b_x, int64_t bnz_total, const double *rhs, double *lhs, char trans, int *status) {
+    if (!mb || !b_begin || !b_end || bnz_total < 0 || (rhs && !lhs)) return BLU_ERROR_INVALID_ARGUMENT;
+    std::vector<int> rc((size_t)mb->ndev, BLU_OK);
+#ifndef BLU_EMU
+    std::vector<std::thread> th;
+    for (int d = 0; d < mb->ndev; d++)
+        th.emplace_back([&, d]() { rc[(size_t)d] = multi_run_part(mb, d, b_begin, b_end, b_i, b_x, bnz_total, rhs, lhs, trans, status); });
+    for (auto &t : th) t.join();
+#else
+    for (int d = 0; d < mb->ndev; d++) rc[(size_t)d] = multi_run_part(mb, d, b_begin, b_end, b_i, b_x, bnz_total, rhs, lhs, trans, status);
+#endif
+    for (int d = 0; d < mb->ndev; d++) if (rc[(size_t)d] != BLU_OK) return rc[(size_t)d];
+    return BLU_OK;
 }

@@ -168,6 +168,22 @@ double blu_batch_last_kernel_ms(blu_batch_t *b, int which /*0 factorize (all ker
 /* number of kernels this library launched since creation */
 int64_t blu_batch_launch_count(blu_batch_t *b);
 
+/* ------------------------------------------------------------------ */
+/* one batch over several GPUs of this process ("a device list")  */
+/* Bases are split into contiguous ranges, one per device (sizes differ by at most   */
+/* one); every device has its own blu_batch_t, host thread and stream; there is no   */
+/* collective -- the results land in the caller's arrays at the bases' own offsets.  */
+/* ------------------------------------------------------------------ */
+typedef struct blu_multi blu_multi_t;
+int blu_multi_create(blu_multi_t **out, int64_t nmat, int64_t m, int64_t bnz_cap, const int *devices, int ndev);
+void blu_multi_destroy(blu_multi_t *mb);
+/* factorize every basis and (if rhs and lhs are given) solve with it; layout as blu_batch_factorize /
+ * blu_batch_solve_dense.  status[k]: per-basis code of the factorization, or of the solve if that failed. */
+int blu_multi_factorize_solve(blu_multi_t *mb, const int64_t *b_begin, const int64_t *b_end, const int64_t *b_i,
+                              const double *b_x, int64_t bnz_total, const double *rhs, double *lhs, char trans, int *status);
+/* the batch object of device slot d and the range of bases it owns (for the getters / further calls) */
+blu_batch_t *blu_multi_part(blu_multi_t *mb, int d, int64_t *first, int64_t *count);
+
 const char *blu_version(void);
 
 #ifdef __cplusplus

@@ -47,3 +47,17 @@ def test_product_does_not_reference_oracle():
                 s = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in s.lower() or f in ("gen.py", "blugen.c", "Makefile", "blu_types.h"), f
                 assert "libblo" not in s and "blo_" not in s, f
+
+
+def test_c_program_links_and_fails_loudly(tmp_path):
+    """tests/abi/abi_check.c: plain C99 against include/blu_b200.h and libblu_b200.so.  Without a GPU the first
+    call answers BLU_ERROR_CUDA; with one the program solves the reference's 10 x 10 example."""
+    import subprocess
+    lib = blu_b200.library_path()
+    exe = str(tmp_path / "abi_check")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "abi", "abi_check.c"),
+                           "-L", os.path.dirname(lib), "-lblu_b200", "-Wl,-rpath," + os.path.dirname(lib), "-lm", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "sm_100a" in out.stdout
+    assert ("BLU_ERROR_CUDA" in out.stdout) or ("solution 0.1..1.0 recovered" in out.stdout)

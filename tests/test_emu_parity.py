@@ -472,3 +472,23 @@ def test_emu_row_search(emu, seed):
     assert g.factorize(cp[:-1], cp[1:], ri, v) == so
     if so in (0, 2):
         assert_factor_parity(g, o)
+
+
+def test_emu_multi_device_entry(emu):
+    """blu_multi_*: one batch split into contiguous ranges over a device list (two device slots here, both the
+    emulator); results land at the bases' own offsets and equal the oracle."""
+    from blu_b200 import BLUMulti
+    nmat, m = 5, 70
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 20, 3.5, 9300, 9350)
+    mb = BLUMulti(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()), [0, 0], lib=emu)
+    assert [mb.part(d)[1:] for d in range(2)] == [(0, 3), (3, 2)]
+    st, x, status = mb.factorize_solve(bb, be, bi, bx, rhs, "N")
+    assert st == 0 and (status == 0).all()
+    for k in range(nmat):
+        cp, ri, v = gen.basis(9300 + k, m, 20, 3.5)
+        o = oracle_for(m, len(v))
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
+        assert np.array_equal(x[k], xo), k
+        assert mb.info(k, "rank") == o.info("rank") and mb.info(k, "l_nz") == o.info("l_nz")
+    mb.close()

@@ -631,3 +631,24 @@ def test_config5_replay_100k():
         _, xo = o.solve_dense(b, tr)
         sg, xg = g.solve_dense(b, tr)
         assert sg == 0 and np.array_equal(xg, xo), tr
+
+
+def test_multi_device_batch():
+    """blu_multi_*: one batch over every GPU of the box from ONE process (device list, a host thread and a stream
+    per GPU, no collective).  With a single GPU the list names it twice -- two streams on one device."""
+    import torch
+    from blu_b200 import BLUMulti
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    nmat, m = 64, 400
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 120, 4.0, 9800, 9900)
+    mb = BLUMulti(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()), devices)
+    st, x, status = mb.factorize_solve(bb, be, bi, bx, rhs, "N")
+    assert st == 0 and (status == 0).all()
+    for k in range(0, nmat, 7):
+        cp, ri, v = gen.basis(9800 + k, m, 120, 4.0)
+        o = oracle_for(m, len(v))
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
+        assert np.array_equal(x[k], xo), k
+    mb.close()
