@@ -40,7 +40,7 @@ _INFO_NAMES = ["m", "rank", "bump_size", "bump_nz", "matrix_nz", "l_nz", "u_nz",
                "u_flops", "r_flops", "condest_l", "condest_u", "norm_l", "norm_u", "normest_l_inv",
                "normest_u_inv", "onenorm", "infnorm", "residual_test", "pivot_error", "update_cost",
                "time_factorize", "time_solve", "time_update", "elim_bytes", "nelim_div", "pivotlen",
-               "rankdef", "internal_error", "status", "nrealloc", "elim_bytes_head", "nruns"]
+               "rankdef", "internal_error", "status", "nrealloc", "elim_bytes_head", "nruns", "addmem_l", "addmem_u", "addmem_w"]
 I = {n: 100 + k for k, n in enumerate(_INFO_NAMES)}
 I.update({f"t_phase{q}": 200 + q for q in range(16)})
 I.update({f"n_kind{q}": 220 + q for q in range(8)})
@@ -68,6 +68,7 @@ def load_library(path=None):
     L.blu_get_info.argtypes = [vp, ctypes.c_int]; L.blu_get_info.restype = ctypes.c_double
     L.blu_factorize.argtypes = [vp, i64p, i64p, i64p, f64p]
     L.blu_get_factors.argtypes = [vp, i64p, i64p, i64p, i64p, f64p, i64p, i64p, f64p]
+    L.blu_factorize_c0ntinue.argtypes = [vp, i64p, i64p, i64p, f64p, ctypes.c_int]
     L.blu_solve_dense.argtypes = [vp, f64p, f64p, ctypes.c_char]
     L.blu_solve_dense_multi.argtypes = [vp, ctypes.c_int64, f64p, f64p, ctypes.c_char]
     L.blu_solve_sparse_multi.argtypes = [vp, ctypes.c_int64, i64p, i64p, f64p, i64p, i64p, f64p, i32p, ctypes.c_char]
@@ -175,6 +176,13 @@ class BLU(_Base):
         if len(bb) < self.m or len(be) < self.m:
             raise IndexError("b_begin/b_end shorter than m")
         return self._L.blu_factorize(self._h, _pi(bb), _pi(be), _pi(bi), _pf(bx))
+
+    def factorize_c0ntinue(self, b_begin, b_end, b_i, b_x, c0ntinue):
+        """factorize() of the crate's free-function surface (lib.rs:11-19, factorize.rs:34): Reallocate escapes
+        (status 1, `addmem_l/u/w` say how much is missing); grow `l_mem`/`u_mem`/`w_mem` and call again with
+        c0ntinue=True."""
+        bb, be, bi, bx = _i64(b_begin), _i64(b_end), _i64(b_i), _f64(b_x)
+        return self._L.blu_factorize_c0ntinue(self._h, _pi(bb), _pi(be), _pi(bi), _pf(bx), 1 if c0ntinue else 0)
 
     # blu.rs:139
     def get_factors(self, want_l=True, want_u=True):

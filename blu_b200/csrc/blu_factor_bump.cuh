@@ -589,57 +589,128 @@ __device__ __forceinline__ void finish_step(Shm &S, int rank, int lput, int uput
 
 /* ------------------------------------------------------------------ */
 /* pivot_any (pivot.rs:114-458) and pivot_small (pivot.rs:460-833)     */
+/* One body, two homes for the per-step state.                          */
+/*  FAST (m <= SMARK_MAX and pivot column and row fit the cache): the    */
+/*    pivot column and row, the line headers (begin, end, capacity) of   */
+/*    every line the step touches and the row/column marks are staged in */
+/*    shared memory by ONE parallel pass over the pivot column and row   */
+/*    (the pass that also bounds the growth, pivot.rs:156-208), so a     */
+/*    column update is  load line -> compute -> store  instead of        */
+/*    header -> line -> mark lookup -> compute -> store; the line two    */
+/*    ahead of each warp is pulled into L2 meanwhile.                    */
+/*  general: marks and headers in global memory, the pivot column / row  */
+/*    cached in shared memory when they fit, lines of any length.        */
+/* Arithmetic and storage order are identical in both.                   */
 /* ------------------------------------------------------------------ */
-template <int NT> __device__ void pivot_general(Shm &S, const bool small) {
+template <int NT, bool FAST> __device__ void pivot_general_t(Shm &S, const bool small) {
     Mat &M = S.M;
     const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = NT / 32;
     const int pc = S.pivot_col, pr = S.pivot_row, rank = S.rank;
     const double droptol = M.prm.droptol, abstol = M.prm.abstol;
-    int cbeg = M.lbeg[pc], cend = M.lend[pc];
-    int rbeg = M.lbeg[m + pr], rend = M.lend[m + pr];
-    const int cnz1 = cend - cbeg - 1, rnz1 = rend - rbeg - 1;
+    int cbeg = M.lbeg[pc], rbeg = M.lbeg[m + pr];
+    const int cnz1 = M.lend[pc] - cbeg - 1, rnz1 = M.lend[m + pr] - rbeg - 1;
+    const int *cidx, *ridx; const double *cval; double *work;
+    double pivot;
 
-    /* prologue, pivot.rs:142-208: find the pivot in its column and row, bound the growth */
-    i64 grow = 0; int wc = -1, wr = -1;
-    for (int pos = cbeg + tid; pos < cend; pos += NT) {
-        int i = M.w_idx[pos];
-        if (i == pr) wc = pos;
-        else { int nz = M.lend[m + i] - M.lbeg[m + i]; grow += nz + rnz1 + slack_of(M.prm, nz + rnz1); }
+    if (FAST) {
+        /* one pass: stage column, row and headers; bound the growth; find the pivot */
+        i64 grow = 0;
+        for (int p = tid; p <= cnz1; p += NT) {
+            const int i = M.w_idx[cbeg + p];
+            S.cidx[p] = i; S.cval[p] = M.w_val[cbeg + p];
+            if (i == pr) S.wc = p;
+            else {
+                const int b = M.lbeg[m + i], e = M.lend[m + i];
+                S.rhb[p] = b; S.rhe[p] = e; S.rhc[p] = M.lcap[m + i];
+                const int nz = e - b;
+                grow += nz + rnz1 + slack_of(M.prm, nz + rnz1);
+            }
+        }
+        for (int k = tid; k <= rnz1; k += NT) {
+            const int j = M.w_idx[rbeg + k];
+            S.ridx[k] = j;
+            if (j == pc) S.wr = k;
+            else {
+                const int b = M.lbeg[j], e = M.lend[j];
+                S.chb[k] = b; S.che[k] = e; S.chc[k] = M.lcap[j];
+                const int nz = e - b;
+                grow += nz + cnz1 + slack_of(M.prm, nz + cnz1);
+            }
+        }
+        grow = block_sum64<NT>(grow, S.kscr);
+        const int wc = S.wc, wr = S.wr;
+        if (wc < 0 || wr < 0) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
+        /* (block_sum64 ended with a barrier: the staged arrays are complete and visible) */
+        if (tid == 0) {
+            /* pivot to the front of its column and row (pivot.rs:142-154), headers travel along */
+            int ti = S.cidx[0]; S.cidx[0] = S.cidx[wc]; S.cidx[wc] = ti;
+            double tv = S.cval[0]; S.cval[0] = S.cval[wc]; S.cval[wc] = tv;
+            S.rhb[wc] = S.rhb[0]; S.rhe[wc] = S.rhe[0]; S.rhc[wc] = S.rhc[0];
+            ti = S.ridx[0]; S.ridx[0] = S.ridx[wr]; S.ridx[wr] = ti;
+            S.chb[wr] = S.chb[0]; S.che[wr] = S.che[0]; S.chc[wr] = S.chc[0];
+            S.flag_a = 0; S.flag_b = 0;
+        }
+        bsync<NT>();
+        {
+            const int ng0 = S.ngarbage;
+            if (!w_reserve<NT>(S, grow)) return;
+            if (S.ngarbage != ng0) {      /* the lines moved: reload the headers */
+                for (int p = 1 + tid; p <= cnz1; p += NT) { const int i = S.cidx[p]; S.rhb[p] = M.lbeg[m + i]; S.rhe[p] = M.lend[m + i]; S.rhc[p] = M.lcap[m + i]; }
+                for (int k = 1 + tid; k <= rnz1; k += NT) { const int j = S.ridx[k]; S.chb[k] = M.lbeg[j]; S.che[k] = M.lend[j]; S.chc[k] = M.lcap[j]; }
+            }
+        }
+        pivot = S.cval[0];
+        cidx = S.cidx; ridx = S.ridx; cval = S.cval;
+        for (int p = 1 + tid; p <= cnz1; p += NT) S.rm[cidx[p]] = (unsigned short)p;
+        for (int k = tid; k <= rnz1; k += NT) S.cm[ridx[k]] = 1;
+        work = S.work + (size_t)wid * S.cap;
+        for (int p = lane; p <= cnz1; p += 32) work[p] = 0.0;
+        bsync<NT>();
+    } else {
+        /* prologue, pivot.rs:142-208: find the pivot in its column and row, bound the growth */
+        int cend = M.lend[pc], rend = M.lend[m + pr];
+        i64 grow = 0; int wc = -1, wr = -1;
+        for (int pos = cbeg + tid; pos < cend; pos += NT) {
+            int i = M.w_idx[pos];
+            if (i == pr) wc = pos;
+            else { int nz = M.lend[m + i] - M.lbeg[m + i]; grow += nz + rnz1 + slack_of(M.prm, nz + rnz1); }
+        }
+        for (int pos = rbeg + tid; pos < rend; pos += NT) {
+            int j = M.w_idx[pos];
+            if (j == pc) wr = pos;
+            else { int nz = M.lend[j] - M.lbeg[j]; grow += nz + cnz1 + slack_of(M.prm, nz + cnz1); }
+        }
+        grow = block_sum64<NT>(grow, S.kscr);
+        wc = block_max<NT>(wc, S.iscr);
+        wr = block_max<NT>(wr, S.iscr);
+        if (wc < 0 || wr < 0) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
+        if (tid == 0) {
+            int ti = M.w_idx[cbeg]; M.w_idx[cbeg] = M.w_idx[wc]; M.w_idx[wc] = ti;
+            double tv = M.w_val[cbeg]; M.w_val[cbeg] = M.w_val[wc]; M.w_val[wc] = tv;
+            ti = M.w_idx[rbeg]; M.w_idx[rbeg] = M.w_idx[wr]; M.w_idx[wr] = ti;
+        }
+        bsync<NT>();
+        if (!w_reserve<NT>(S, grow)) return;
+        cbeg = M.lbeg[pc]; rbeg = M.lbeg[m + pr];
+        pivot = M.w_val[cbeg];
+        /* stage the pivot column / row in shared memory when they fit */
+        const bool ccached = cnz1 + 1 <= S.cap, rcached = rnz1 + 1 <= S.cap;
+        cidx = ccached ? S.cidx : M.w_idx + cbeg;
+        cval = ccached ? S.cval : M.w_val + cbeg;
+        ridx = rcached ? S.ridx : M.w_idx + rbeg;
+        if (ccached) for (int p = tid; p <= cnz1; p += NT) { S.cidx[p] = M.w_idx[cbeg + p]; S.cval[p] = M.w_val[cbeg + p]; }
+        if (rcached) for (int k = tid; k <= rnz1; k += NT) S.ridx[k] = M.w_idx[rbeg + k];
+        for (int p = 1 + tid; p <= cnz1; p += NT) M.rowmark[M.w_idx[cbeg + p]] = p;
+        for (int k = tid; k <= rnz1; k += NT) M.colmark[M.w_idx[rbeg + k]] = 1;
+        work = ccached ? S.work + (size_t)wid * S.cap : M.gwork + (size_t)wid * m;
+        if (ccached) for (int p = lane; p <= cnz1; p += 32) work[p] = 0.0;
+        if (tid == 0) { S.flag_a = 0; S.flag_b = 0; }
+        bsync<NT>();
     }
-    for (int pos = rbeg + tid; pos < rend; pos += NT) {
-        int j = M.w_idx[pos];
-        if (j == pc) wr = pos;
-        else { int nz = M.lend[j] - M.lbeg[j]; grow += nz + cnz1 + slack_of(M.prm, nz + cnz1); }
-    }
-    grow = block_sum64<NT>(grow, S.kscr);
-    wc = block_max<NT>(wc, S.iscr);
-    wr = block_max<NT>(wr, S.iscr);
-    if (wc < 0 || wr < 0) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
-    if (tid == 0) {
-        int ti = M.w_idx[cbeg]; M.w_idx[cbeg] = M.w_idx[wc]; M.w_idx[wc] = ti;
-        double tv = M.w_val[cbeg]; M.w_val[cbeg] = M.w_val[wc]; M.w_val[wc] = tv;
-        ti = M.w_idx[rbeg]; M.w_idx[rbeg] = M.w_idx[wr]; M.w_idx[wr] = ti;
-    }
-    bsync<NT>();
-    if (!w_reserve<NT>(S, grow)) return;
-    cbeg = M.lbeg[pc]; cend = M.lend[pc];
-    rbeg = M.lbeg[m + pr]; rend = M.lend[m + pr];
-    const double pivot = M.w_val[cbeg];
-
-    /* stage the pivot column / row in shared memory when they fit */
-    const bool ccached = cnz1 + 1 <= S.cap, rcached = rnz1 + 1 <= S.cap;
-    const int *cidx = ccached ? S.cidx : M.w_idx + cbeg;
-    const double *cval = ccached ? S.cval : M.w_val + cbeg;
-    const int *ridx = rcached ? S.ridx : M.w_idx + rbeg;
-    if (ccached) for (int p = tid; p <= cnz1; p += NT) { S.cidx[p] = M.w_idx[cbeg + p]; S.cval[p] = M.w_val[cbeg + p]; }
-    if (rcached) for (int k = tid; k <= rnz1; k += NT) S.ridx[k] = M.w_idx[rbeg + k];
-    for (int p = 1 + tid; p <= cnz1; p += NT) M.rowmark[M.w_idx[cbeg + p]] = p;
-    for (int k = tid; k <= rnz1; k += NT) M.colmark[M.w_idx[rbeg + k]] = 1;
-    double *work = ccached ? S.work + (size_t)wid * S.cap : M.gwork + (size_t)wid * m;
-    if (ccached) for (int p = lane; p <= cnz1; p += 32) work[p] = 0.0;
-    if (tid == 0) { S.flag_a = 0; S.flag_b = 0; }
-    bsync<NT>();
+    /* where a row / column mark and a line header come from */
+    auto rowmark_of = [&](int i) -> int { return FAST ? (int)S.rm[i] : M.rowmark[i]; };
+    auto colmark_of = [&](int j) -> int { return FAST ? (int)S.cm[j] : M.colmark[j]; };
 
     const int ubase = M.u_begin[rank];
     const i64 cbase = S.cstamp, rbase = S.rstamp;
@@ -647,8 +718,13 @@ template <int NT> __device__ void pivot_general(Shm &S, const bool small) {
 
     /* column file update, pivot.rs:219-331 / 569-693: one warp per column of the pivot row */
     for (int k = 1 + wid; k <= rnz1; k += NW) {
+        if (FAST && k + PF_DIST * NW <= rnz1) {      /* a later line of this warp: start pulling it in now */
+            const int nb = S.chb[k + PF_DIST * NW], nn = S.che[k + PF_DIST * NW] - nb;
+            warp_prefetch_l2(M.w_idx + nb, nn * 4);
+            warp_prefetch_l2(M.w_val + nb, nn * 8);
+        }
         const int j = ridx[k];
-        int beg = M.lbeg[j], end = M.lend[j], cap = M.lcap[j];
+        int beg = FAST ? S.chb[k] : M.lbeg[j], end = FAST ? S.che[k] : M.lend[j], cap = FAST ? S.chc[k] : M.lcap[j];
         const int oldnz = end - beg;
         int put, where = -1;
         double cmx = 0.0, xrj;
@@ -665,7 +741,7 @@ template <int NT> __device__ void pivot_general(Shm &S, const bool small) {
                 ev[e] = valid ? M.w_val[pos] : 0.0;
             }
             #pragma unroll
-            for (int e = 0; e < REGE; e++) emk[e] = ei[e] >= 0 ? M.rowmark[ei[e]] : -1;
+            for (int e = 0; e < REGE; e++) emk[e] = (e * 32 < oldnz && ei[e] >= 0) ? rowmark_of(ei[e]) : -1;
             int tcount = 0; double myx = 0.0; int mine = 0;
             #pragma unroll
             for (int e = 0; e < REGE; e++) {
@@ -706,340 +782,13 @@ template <int NT> __device__ void pivot_general(Shm &S, const bool small) {
             beg = dstb; put = dstb + nT - 1;
             __syncwarp();
         } else {
-        put = beg;
-        for (int base = beg; base < end; base += 32) {
-            int pos = base + lane;
-            int valid = pos < end;
-            int i = valid ? M.w_idx[pos] : 0;
-            double x = valid ? M.w_val[pos] : 0.0;
-            int mk = valid ? M.rowmark[i] : 0;
-            int isT = valid && mk == 0;
-            if (valid && mk > 0) work[mk] = x;
-            unsigned tm = __ballot_sync(FULLMASK, isT);
-            int dst = put + __popc(tm & lanemask_lt());
-            if (isT) { if (i == pr) where = dst; else { double a = fabs(x); if (a > cmx) cmx = a; } }
-            __syncwarp();
-            if (isT) { M.w_idx[dst] = i; M.w_val[dst] = x; }
-            put += __popc(tm);
-        }
-        where = warp_max(where);
-        __syncwarp();
-        if (where < 0) { if (lane == 0) BLU_CHECK(S, 0); continue; }
-        xrj = M.w_val[where];
-        __syncwarp();
-        if (lane == 0 && where != beg) { M.w_idx[where] = M.w_idx[beg]; M.w_val[where] = M.w_val[beg]; }
-        __syncwarp();
-        nT = put - beg;
-        beg += 1;                            /* the pivot-row entry leaves the line */
-        if (cap - put < cnz1) {              /* move the line to the end of the file */
-            int nz = put - beg;
-            int room = cnz1 + slack_of(M.prm, nT + cnz1);
-            int np = 0;
-            if (lane == 0) { np = atomicAdd(&S.w_used, nz + room); atomicAdd(&S.nexpand, 1); }
-            np = __shfl_sync(FULLMASK, np, 0);
-            for (int t = lane; t < nz; t += 32) { M.w_idx[np + t] = M.w_idx[beg + t]; M.w_val[np + t] = M.w_val[beg + t]; }
-            beg = np; put = np + nz; cap = np + nz + room;
-            __syncwarp();
-        }
-        }
-        const double a = __ddiv_rn(xrj, pivot);
-        u64 cmask = 0;
-        for (int base = 1; base <= cnz1; base += 32) {
-            int p = base + lane;
-            int valid = p <= cnz1;
-            double x = 0.0;
-            if (valid) { x = __dsub_rn(work[p], __dmul_rn(a, cval[p])); work[p] = 0.0; }
-            if (!small) {
-                if (valid) {
-                    M.w_idx[put + p - 1] = cidx[p]; M.w_val[put + p - 1] = x;
-                    double ax = fabs(x); if (ax > cmx) cmx = ax;
-                }
-            } else {
-                int keep = valid && fabs(x) > droptol;
-                unsigned km = __ballot_sync(FULLMASK, keep);
-                unsigned dm = __ballot_sync(FULLMASK, valid && !keep);
-                if (keep) {
-                    int d = put + __popc(km & lanemask_lt());
-                    M.w_idx[d] = cidx[p]; M.w_val[d] = x;
-                    double ax = fabs(x); if (ax > cmx) cmx = ax;
-                }
-                cmask |= (u64)dm << (base - 1);
-                put += __popc(km);
-            }
-        }
-        if (!small) put += cnz1;
-        cmx = warp_maxd(cmx);
-        if (lane == 0) {
-            M.lbeg[j] = beg; M.lend[j] = put; M.lcap[j] = cap;
-            M.colpiv[j] = cmx;
-            M.ckey[j] = mkckey(put - beg, cbase + k, cmx, abstol);
-            if (small) M.cancelled[k - 1] = cmask;
-            if (fabs(xrj) > droptol) { M.u_idx[ubase + k - 1] = j; M.u_val[ubase + k - 1] = xrj; }
-            else { M.u_idx[ubase + k - 1] = -2; M.u_val[ubase + k - 1] = 0.0; S.flag_a = 1; }
-            if (cmx == 0.0 || cmx < abstol) S.need_remove = 1;
-            acc_bytes += 12.0 * (oldnz + put - beg);
-        }
-        __syncwarp();
-    }
-    if (small) bsync<NT>();      /* the row update needs every column's cancellation mask */
-
-    /* row file update, pivot.rs:335-401 / 697-774: one warp per row of the pivot column */
-    for (int p = 1 + wid; p <= cnz1; p += NW) {
-        const int i = cidx[p];
-        const int line = m + i;
-        int beg = M.lbeg[line], end = M.lend[line], cap = M.lcap[line];
-        const int oldnz = end - beg;
-        int put;
-        if (oldnz <= 32 * REGE) {
-            int rj[REGE], roff[REGE];
-            #pragma unroll
-            for (int e = 0; e < REGE; e++) {
-                int pos = beg + e * 32 + lane;
-                rj[e] = pos < end ? M.w_idx[pos] : -1;
-            }
-            #pragma unroll
-            for (int e = 0; e < REGE; e++) roff[e] = (rj[e] >= 0 && M.colmark[rj[e]] == 0) ? 0 : -1;
-            int kcount = 0;
-            #pragma unroll
-            for (int e = 0; e < REGE; e++) {
-                if (e * 32 < oldnz) {
-                    unsigned km = __ballot_sync(FULLMASK, roff[e] == 0);
-                    if (roff[e] == 0) roff[e] = kcount + __popc(km & lanemask_lt());
-                    kcount += __popc(km);
-                }
-            }
-            int dstb = beg;
-            if (cap - (beg + kcount) < rnz1) {
-                int room = rnz1 + slack_of(M.prm, kcount + rnz1);
-                int np = 0;
-                if (lane == 0) { np = atomicAdd(&S.w_used, kcount + room); atomicAdd(&S.nexpand, 1); }
-                np = __shfl_sync(FULLMASK, np, 0);
-                dstb = np; cap = np + kcount + room;
-            }
-            #pragma unroll
-            for (int e = 0; e < REGE; e++) if (roff[e] >= 0) M.w_idx[dstb + roff[e]] = rj[e];
-            beg = dstb; put = dstb + kcount;
-            __syncwarp();
-        } else {
-        put = beg;
-        for (int base = beg; base < end; base += 32) {
-            int pos = base + lane;
-            int valid = pos < end;
-            int j = valid ? M.w_idx[pos] : 0;
-            int keep = valid && M.colmark[j] == 0;
-            unsigned km = __ballot_sync(FULLMASK, keep);
-            __syncwarp();
-            if (keep) M.w_idx[put + __popc(km & lanemask_lt())] = j;
-            put += __popc(km);
-        }
-        __syncwarp();
-        if (cap - put < rnz1) {
-            int nz = put - beg;
-            int room = rnz1 + slack_of(M.prm, nz + rnz1);
-            int np = 0;
-            if (lane == 0) { np = atomicAdd(&S.w_used, nz + room); atomicAdd(&S.nexpand, 1); }
-            np = __shfl_sync(FULLMASK, np, 0);
-            for (int t = lane; t < nz; t += 32) M.w_idx[np + t] = M.w_idx[beg + t];
-            beg = np; put = np + nz; cap = np + nz + room;
-            __syncwarp();
-        }
-        }
-        if (!small) {
-            for (int k = 1 + lane; k <= rnz1; k += 32) M.w_idx[put + k - 1] = ridx[k];
-            put += rnz1;
-        } else {
-            for (int base = 1; base <= rnz1; base += 32) {
-                int k = base + lane;
-                int keep = k <= rnz1 && ((M.cancelled[k - 1] >> (p - 1)) & 1ull) == 0;
-                unsigned km = __ballot_sync(FULLMASK, keep);
-                if (keep) M.w_idx[put + __popc(km & lanemask_lt())] = ridx[k];
-                put += __popc(km);
-            }
-        }
-        if (lane == 0) {
-            M.lbeg[line] = beg; M.lend[line] = put; M.lcap[line] = cap;
-            M.rkey[i] = mkkey(put - beg, rbase + p);
-            acc_bytes += 4.0 * (oldnz + put - beg);
-        }
-        __syncwarp();
-    }
-
-    /* L column, pivot.rs:403-415 (tentative slots, squeezed if something was dropped) */
-    const int lbase = M.l_begin_p[rank];
-    for (int p = 1 + tid; p <= cnz1; p += NT) {
-        double x = __ddiv_rn(cval[p], pivot);
-        if (fabs(x) > droptol) { M.l_idx[lbase + p - 1] = cidx[p]; M.l_val[lbase + p - 1] = x; }
-        else { M.l_idx[lbase + p - 1] = -2; M.l_val[lbase + p - 1] = 0.0; S.flag_b = 1; }
-    }
-    if (acc_bytes != 0.0) atomicAdd(&S.elim_bytes, acc_bytes);
-    bsync<NT>();
-    /* clear marks */
-    for (int p = 1 + tid; p <= cnz1; p += NT) M.rowmark[cidx[p]] = 0;
-    for (int k = tid; k <= rnz1; k += NT) M.colmark[ridx[k]] = 0;
-    if (wid == 0) {
-        int ln = cnz1, un = rnz1;
-        if (S.flag_b) ln = warp_squeeze(M.l_idx, M.l_val, lbase, cnz1);
-        if (S.flag_a) un = warp_squeeze(M.u_idx, M.u_val, ubase, rnz1);
-        if (lane == 0) {
-            M.l_idx[lbase + ln] = -1;
-            finish_step(S, rank, lbase + ln + 1, ubase + un, pivot, cnz1 + 1, rnz1 + 1);
-            S.cstamp = cbase + rnz1 + 1;
-            S.rstamp = rbase + cnz1 + 1;
-        }
-    }
-    bsync<NT>();
-}
-
-
-/* ------------------------------------------------------------------ */
-/* pivot_any / pivot_small, shared-memory variant.                     */
-/* Same arithmetic and same storage order as pivot_general; what        */
-/* changes is where the per-step state lives: the pivot column and row, */
-/* the line headers (begin,end,capacity) of every line the step touches */
-/* and the row/column marks are staged in shared memory by ONE parallel */
-/* pass over the pivot column and row (the pass that also bounds the    */
-/* growth, pivot.rs:156-208), so a column update is                     */
-/*   load line -> compute -> store                                      */
-/* instead of header -> line -> mark lookup -> compute -> store.        */
-/* Used when m <= SMARK_MAX and pivot column and row fit the cache.     */
-/* ------------------------------------------------------------------ */
-template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
-    Mat &M = S.M;
-    const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr int NW = NT / 32;
-    const int pc = S.pivot_col, pr = S.pivot_row, rank = S.rank;
-    const double droptol = M.prm.droptol, abstol = M.prm.abstol;
-    const int cbeg = M.lbeg[pc], rbeg = M.lbeg[m + pr];
-    const int cnz1 = M.lend[pc] - cbeg - 1, rnz1 = M.lend[m + pr] - rbeg - 1;
-
-    /* one pass: stage column, row and headers; bound the growth; find the pivot */
-    i64 grow = 0;
-    for (int p = tid; p <= cnz1; p += NT) {
-        const int i = M.w_idx[cbeg + p];
-        S.cidx[p] = i; S.cval[p] = M.w_val[cbeg + p];
-        if (i == pr) S.wc = p;
-        else {
-            const int b = M.lbeg[m + i], e = M.lend[m + i];
-            S.rhb[p] = b; S.rhe[p] = e; S.rhc[p] = M.lcap[m + i];
-            const int nz = e - b;
-            grow += nz + rnz1 + slack_of(M.prm, nz + rnz1);
-        }
-    }
-    for (int k = tid; k <= rnz1; k += NT) {
-        const int j = M.w_idx[rbeg + k];
-        S.ridx[k] = j;
-        if (j == pc) S.wr = k;
-        else {
-            const int b = M.lbeg[j], e = M.lend[j];
-            S.chb[k] = b; S.che[k] = e; S.chc[k] = M.lcap[j];
-            const int nz = e - b;
-            grow += nz + cnz1 + slack_of(M.prm, nz + cnz1);
-        }
-    }
-    grow = block_sum64<NT>(grow, S.kscr);
-    const int wc = S.wc, wr = S.wr;
-    if (wc < 0 || wr < 0) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
-    /* (block_sum64 ended with a barrier: the staged arrays are complete and visible) */
-    if (tid == 0) {
-        /* pivot to the front of its column and row (pivot.rs:142-154), headers travel along */
-        int ti = S.cidx[0]; S.cidx[0] = S.cidx[wc]; S.cidx[wc] = ti;
-        double tv = S.cval[0]; S.cval[0] = S.cval[wc]; S.cval[wc] = tv;
-        S.rhb[wc] = S.rhb[0]; S.rhe[wc] = S.rhe[0]; S.rhc[wc] = S.rhc[0];
-        ti = S.ridx[0]; S.ridx[0] = S.ridx[wr]; S.ridx[wr] = ti;
-        S.chb[wr] = S.chb[0]; S.che[wr] = S.che[0]; S.chc[wr] = S.chc[0];
-        S.flag_a = 0; S.flag_b = 0;
-    }
-    bsync<NT>();
-    {
-        const int ng0 = S.ngarbage;
-        if (!w_reserve<NT>(S, grow)) return;
-        if (S.ngarbage != ng0) {      /* the lines moved: reload the headers */
-            for (int p = 1 + tid; p <= cnz1; p += NT) { const int i = S.cidx[p]; S.rhb[p] = M.lbeg[m + i]; S.rhe[p] = M.lend[m + i]; S.rhc[p] = M.lcap[m + i]; }
-            for (int k = 1 + tid; k <= rnz1; k += NT) { const int j = S.ridx[k]; S.chb[k] = M.lbeg[j]; S.che[k] = M.lend[j]; S.chc[k] = M.lcap[j]; }
-        }
-    }
-    const double pivot = S.cval[0];
-    const int *cidx = S.cidx, *ridx = S.ridx;
-    const double *cval = S.cval;
-    for (int p = 1 + tid; p <= cnz1; p += NT) S.rm[cidx[p]] = (unsigned short)p;
-    for (int k = tid; k <= rnz1; k += NT) S.cm[ridx[k]] = 1;
-    double *work = S.work + (size_t)wid * S.cap;
-    for (int p = lane; p <= cnz1; p += 32) work[p] = 0.0;
-    bsync<NT>();
-
-    const int ubase = M.u_begin[rank];
-    const i64 cbase = S.cstamp, rbase = S.rstamp;
-    double acc_bytes = 0.0;
-
-    /* column file update, pivot.rs:219-331 / 569-693: one warp per column of the pivot row */
-    for (int k = 1 + wid; k <= rnz1; k += NW) {
-        if (k + PF_DIST * NW <= rnz1) {      /* a later line of this warp: start pulling it in now */
-            const int nb = S.chb[k + PF_DIST * NW], nn = S.che[k + PF_DIST * NW] - nb;
-            warp_prefetch_l2(M.w_idx + nb, nn * 4);
-            warp_prefetch_l2(M.w_val + nb, nn * 8);
-        }
-        const int j = ridx[k];
-        int beg = S.chb[k], end = S.che[k], cap = S.chc[k];
-        const int oldnz = end - beg;
-        int put, where = -1;
-        double cmx = 0.0, xrj;
-        int nT;
-        if (oldnz <= 32 * REGE) {
-            int ei[REGE], emk[REGE], toff[REGE]; double ev[REGE];
-            #pragma unroll
-            for (int e = 0; e < REGE; e++) {
-                int pos = beg + e * 32 + lane;
-                bool valid = pos < end;
-                ei[e] = valid ? M.w_idx[pos] : -1;
-                ev[e] = valid ? M.w_val[pos] : 0.0;
-            }
-            int tcount = 0; double myx = 0.0; int mine = 0;
-            #pragma unroll
-            for (int e = 0; e < REGE; e++) {
-                if (e * 32 < oldnz) {
-                    emk[e] = ei[e] >= 0 ? (int)S.rm[ei[e]] : -1;
-                    int isT = emk[e] == 0;
-                    unsigned tm = __ballot_sync(FULLMASK, isT);
-                    toff[e] = tcount + __popc(tm & lanemask_lt());
-                    if (isT) { if (ei[e] == pr) { where = toff[e]; myx = ev[e]; mine = 1; } else { double a = fabs(ev[e]); if (a > cmx) cmx = a; } }
-                    if (emk[e] > 0) work[emk[e]] = ev[e];
-                    tcount += __popc(tm);
-                } else { toff[e] = 0; emk[e] = -1; }
-            }
-            unsigned hm = __ballot_sync(FULLMASK, mine);
-            if (hm == 0) { if (lane == 0) BLU_CHECK(S, 0); continue; }
-            const int hl = __ffs((int)hm) - 1;
-            where = __shfl_sync(FULLMASK, where, hl);
-            xrj = __shfl_sync(FULLMASK, myx, hl);
-            nT = tcount;
-            int dstb = beg + 1;
-            if (cap - (beg + nT) < cnz1) {      /* the line moves to the end of the file */
-                int room = cnz1 + slack_of(M.prm, nT + cnz1);
-                int np = 0;
-                if (lane == 0) { np = atomicAdd(&S.w_used, nT - 1 + room); atomicAdd(&S.nexpand, 1); }
-                np = __shfl_sync(FULLMASK, np, 0);
-                dstb = np; cap = np + nT - 1 + room;
-            }
-            #pragma unroll
-            for (int e = 0; e < REGE; e++) {
-                if (emk[e] == 0) {
-                    int t = toff[e];
-                    if (t != where) {
-                        int slot = t == 0 ? where - 1 : t - 1;
-                        M.w_idx[dstb + slot] = ei[e]; M.w_val[dstb + slot] = ev[e];
-                    }
-                }
-            }
-            beg = dstb; put = dstb + nT - 1;
-            __syncwarp();
-        } else {
             put = beg;
             for (int base = beg; base < end; base += 32) {
                 int pos = base + lane;
                 int valid = pos < end;
                 int i = valid ? M.w_idx[pos] : 0;
                 double x = valid ? M.w_val[pos] : 0.0;
-                int mk = valid ? (int)S.rm[i] : 0;
+                int mk = valid ? rowmark_of(i) : 0;
                 int isT = valid && mk == 0;
                 if (valid && mk > 0) work[mk] = x;
                 unsigned tm = __ballot_sync(FULLMASK, isT);
@@ -1057,8 +806,8 @@ template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
             if (lane == 0 && where != beg) { M.w_idx[where] = M.w_idx[beg]; M.w_val[where] = M.w_val[beg]; }
             __syncwarp();
             nT = put - beg;
-            beg += 1;
-            if (cap - put < cnz1) {
+            beg += 1;                            /* the pivot-row entry leaves the line */
+            if (cap - put < cnz1) {              /* move the line to the end of the file */
                 int nz = put - beg;
                 int room = cnz1 + slack_of(M.prm, nT + cnz1);
                 int np = 0;
@@ -1112,10 +861,10 @@ template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
 
     /* row file update, pivot.rs:335-401 / 697-774: one warp per row of the pivot column */
     for (int p = 1 + wid; p <= cnz1; p += NW) {
-        if (p + PF_DIST * NW <= cnz1) warp_prefetch_l2(M.w_idx + S.rhb[p + PF_DIST * NW], (S.rhe[p + PF_DIST * NW] - S.rhb[p + PF_DIST * NW]) * 4);
+        if (FAST && p + PF_DIST * NW <= cnz1) warp_prefetch_l2(M.w_idx + S.rhb[p + PF_DIST * NW], (S.rhe[p + PF_DIST * NW] - S.rhb[p + PF_DIST * NW]) * 4);
         const int i = cidx[p];
         const int line = m + i;
-        int beg = S.rhb[p], end = S.rhe[p], cap = S.rhc[p];
+        int beg = FAST ? S.rhb[p] : M.lbeg[line], end = FAST ? S.rhe[p] : M.lend[line], cap = FAST ? S.rhc[p] : M.lcap[line];
         const int oldnz = end - beg;
         int put;
         if (oldnz <= 32 * REGE) {
@@ -1130,7 +879,7 @@ template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
             for (int e = 0; e < REGE; e++) {
                 roff[e] = -1;
                 if (e * 32 < oldnz) {
-                    int keep = rj[e] >= 0 && S.cm[rj[e]] == 0;
+                    int keep = rj[e] >= 0 && colmark_of(rj[e]) == 0;
                     unsigned km = __ballot_sync(FULLMASK, keep);
                     if (keep) roff[e] = kcount + __popc(km & lanemask_lt());
                     kcount += __popc(km);
@@ -1154,7 +903,7 @@ template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
                 int pos = base + lane;
                 int valid = pos < end;
                 int j = valid ? M.w_idx[pos] : 0;
-                int keep = valid && S.cm[j] == 0;
+                int keep = valid && colmark_of(j) == 0;
                 unsigned km = __ballot_sync(FULLMASK, keep);
                 __syncwarp();
                 if (keep) M.w_idx[put + __popc(km & lanemask_lt())] = j;
@@ -1202,8 +951,13 @@ template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
     if (acc_bytes != 0.0) atomicAdd(&S.elim_bytes, acc_bytes);
     bsync<NT>();
     /* clear marks */
-    for (int p = 1 + tid; p <= cnz1; p += NT) S.rm[cidx[p]] = 0;
-    for (int k = tid; k <= rnz1; k += NT) S.cm[ridx[k]] = 0;
+    if (FAST) {
+        for (int p = 1 + tid; p <= cnz1; p += NT) S.rm[cidx[p]] = 0;
+        for (int k = tid; k <= rnz1; k += NT) S.cm[ridx[k]] = 0;
+    } else {
+        for (int p = 1 + tid; p <= cnz1; p += NT) M.rowmark[cidx[p]] = 0;
+        for (int k = tid; k <= rnz1; k += NT) M.colmark[ridx[k]] = 0;
+    }
     if (wid == 0) {
         int ln = cnz1, un = rnz1;
         if (S.flag_b) ln = warp_squeeze(M.l_idx, M.l_val, lbase, cnz1);
@@ -1213,11 +967,13 @@ template <int NT> __device__ void pivot_general_fast(Shm &S, const bool small) {
             finish_step(S, rank, lbase + ln + 1, ubase + un, pivot, cnz1 + 1, rnz1 + 1);
             S.cstamp = cbase + rnz1 + 1;
             S.rstamp = rbase + cnz1 + 1;
-            S.wc = -1; S.wr = -1;
+            if (FAST) { S.wc = -1; S.wr = -1; }
         }
     }
     bsync<NT>();
 }
+template <int NT> __device__ __forceinline__ void pivot_general(Shm &S, const bool small) { pivot_general_t<NT, false>(S, small); }
+template <int NT> __device__ __forceinline__ void pivot_general_fast(Shm &S, const bool small) { pivot_general_t<NT, true>(S, small); }
 
 /* ------------------------------------------------------------------ */
 /* pivot_singleton_row, pivot.rs:835-926                               */

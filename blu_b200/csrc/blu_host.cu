@@ -45,6 +45,7 @@ struct blu_b200 {
     double last_ms[2], last_part_ms[3]; int parts_timed;
     int64_t launches;
     int nrealloc;
+    int escape_realloc, task_pending;   /* blu_factorize_c0ntinue: Reallocate is handed to the caller; a Reallocate is pending */
     /* device staging for B, rhs, lhs, status */
     int64_t *db_begin, *db_end, *db_i; double *db_x; int64_t b_cap;
     double *d_rhs, *d_lhs; int *d_status;
@@ -198,7 +199,7 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     o->split_min = o->num_sms;
     if (const char *e = getenv("BLU_B200_CAP")) { int c = atoi(e); if (c >= 64 && c <= 4096) o->cap = c & ~31; }   /* tuning knob: entries of the shared-memory line caches */
     o->launches = 0; o->nrealloc = 0; o->last_ms[0] = o->last_ms[1] = 0.0; o->last_part_ms[0] = o->last_part_ms[1] = o->last_part_ms[2] = 0.0;
-    o->d_slot = nullptr; o->have_overrides = 0;
+    o->d_slot = nullptr; o->have_overrides = 0; o->escape_realloc = 0; o->task_pending = 0;
     o->have_b = 0; o->info_dirty = 0; o->norms = 1; o->last_norms_ms = 0.0;
     o->have_pipe = 0; o->d_chunk_end = nullptr; o->h_chunk_end = nullptr;
     o->dm_rhs = o->dm_lhs = o->dm_work = nullptr; o->dm_status = nullptr; o->multi_cap = 0;
@@ -443,7 +444,7 @@ static int ensure_info(blu_b200 *o) {
 }
 
 /* factorize what is resident in db_*; loops on Reallocate like blu.rs:95-118 */
-static int factorize_resident(blu_b200 *o, int hungry_known = 0) {
+static int factorize_resident(blu_b200 *o, int hungry_known = 0, int escape_realloc = 0) {
     CK(cudaSetDevice(o->device));
     BluDev &d = o->d;
     d.b_begin = (const blu_i64 *)o->db_begin; d.b_end = (const blu_i64 *)o->db_end;
@@ -493,6 +494,7 @@ static int factorize_resident(blu_b200 *o, int hungry_known = 0) {
             o->last_ms[0] = total_ms;
             return BLU_OK;
         }
+        if (escape_realloc) { o->last_ms[0] = total_ms; return BLU_REALLOCATE; }      /* the free-function surface: the caller grows the stores (lib.rs:11-19) */
         /* lu_realloc_obj, blu.rs:345-377 */
         if (!o->single) {
             if ((st = grow_hungry_slots(o)) != BLU_OK) return st;
@@ -764,6 +766,9 @@ static double info_value(blu_b200 *o, const BluInfo &I, int what) {
     case BLU_I_STATUS: return I.status;
     case BLU_I_NREALLOC: return o->nrealloc;
     case BLU_I_NRUNS: return I.nruns;
+    case BLU_I_ADDMEM_L: return (double)I.addmem_l;
+    case BLU_I_ADDMEM_U: return (double)I.addmem_u;
+    case BLU_I_ADDMEM_W: return (double)I.addmem_w;
     case BLU_I_ELIM_BYTES_HEAD: return I.elim_bytes_head;
     default:
         if (what >= BLU_I_T_PHASE0 && what < BLU_I_T_PHASE0 + 16) return (double)I.t_phase[what - BLU_I_T_PHASE0];
@@ -935,10 +940,26 @@ extern "C" int blu_factorize(blu_t *o, const int64_t *b_begin, const int64_t *b_
     }
     int st = blu_batch_upload(o, o->hb_begin.data(), o->hb_end.data(), o->hb_i.data(), o->hb_x.data(), nnz, nullptr);
     if (st != BLU_OK) return st;
-    st = factorize_resident(o);
+    st = factorize_resident(o, 0, o->escape_realloc);
     o->time_factorize += 1e-3 * o->last_ms[0];
     if (st != BLU_OK) return st;
     return o->hinfo[0].status;
+}
+
+/* factorize() of the crate's free-function surface (lib.rs:11-19 -> factorize.rs:34-119): Reallocate ESCAPES.
+ * The caller reads BLU_I_ADDMEM_L/U/W, grows the stores (blu_set_param BLU_P_L_MEM / U_MEM / W_MEM, the role of
+ * lu_realloc_obj) and calls again with c0ntinue != 0.  c0ntinue without a pending Reallocate is
+ * ErrorInvalidCall (factorize.rs:102-105).  The reference resumes at the phase that ran out of memory; the device
+ * starts the factorization over with the larger stores -- same factors, same return codes. */
+extern "C" int blu_factorize_c0ntinue(blu_t *o, const int64_t *b_begin, const int64_t *b_end, const int64_t *b_i, const double *b_x, int c0ntinue) {
+    if (!o || !b_begin || !b_end) return BLU_ERROR_INVALID_ARGUMENT;
+    if (o->d.nmat != 1) return BLU_ERROR_INVALID_CALL;
+    if (c0ntinue && !o->task_pending) return BLU_ERROR_INVALID_CALL;
+    o->escape_realloc = 1;
+    int st = blu_factorize(o, b_begin, b_end, b_i, b_x);
+    o->escape_realloc = 0;
+    o->task_pending = st == BLU_REALLOCATE;
+    return st;
 }
 
 extern "C" int blu_get_factors(blu_t *o, int64_t *rowperm, int64_t *colperm,

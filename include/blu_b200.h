@@ -61,6 +61,7 @@ enum {
     BLU_I_PIVOTLEN, BLU_I_RANKDEF, BLU_I_INTERNAL_ERROR, BLU_I_STATUS, BLU_I_NREALLOC,
     BLU_I_ELIM_BYTES_HEAD,              /* part of BLU_I_ELIM_BYTES done by the head launch of a split batch factorization */
     BLU_I_NRUNS,                        /* factorization passes started on this basis since creation (a Reallocate re-run counts) */
+    BLU_I_ADDMEM_L, BLU_I_ADDMEM_U, BLU_I_ADDMEM_W, /* lu.rs:308-314: entries missing in L / U / W when the last call answered Reallocate */
     BLU_I_T_PHASE0 = 200, /* +0..15: SM cycles per phase of the factorization kernel (diagnostic) */
     BLU_I_N_KIND0 = 220,  /* +0..4: pivots taken by singleton-row / singleton-col / doubleton / small / any; +5: of those, steps taken in the dense tail; +6: entries into it */
     BLU_I_NORMS_CYC0 = 230 /* +0..3: SM cycles of condest(L), condest(U), residual forward, residual transposed (diagnostic) */
@@ -85,6 +86,13 @@ double blu_get_info(blu_t *o, int what);
  * b_i/b_x[b_begin[j] .. b_end[j]); pass (colptr, colptr+1) for CSC. */
 int blu_factorize(blu_t *o, const int64_t *b_begin, const int64_t *b_end,
                   const int64_t *b_i, const double *b_x);
+
+/* factorize() of the crate's FREE-FUNCTION surface (lib.rs:11-19, factorize.rs:34-119), where Reallocate escapes:
+ * returns BLU_REALLOCATE with BLU_I_ADDMEM_L/U/W set; the caller grows the stores (blu_set_param with
+ * BLU_P_L_MEM / BLU_P_U_MEM / BLU_P_W_MEM -- lu_realloc_obj, blu.rs:345-377) and calls again with c0ntinue != 0.
+ * c0ntinue != 0 without a pending Reallocate: BLU_ERROR_INVALID_CALL (factorize.rs:102-105). */
+int blu_factorize_c0ntinue(blu_t *o, const int64_t *b_begin, const int64_t *b_end,
+                           const int64_t *b_i, const double *b_x, int c0ntinue);
 
 /* BLU::get_factors, blu.rs:139-160 -> get_factors.rs:48.  Every output may be NULL. */
 int blu_get_factors(blu_t *o, int64_t *rowperm, int64_t *colperm,

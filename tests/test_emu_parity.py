@@ -492,3 +492,30 @@ def test_emu_multi_device_entry(emu):
         assert np.array_equal(x[k], xo), k
         assert mb.info(k, "rank") == o.info("rank") and mb.info(k, "l_nz") == o.info("l_nz")
     mb.close()
+
+
+def test_emu_factorize_c0ntinue(emu):
+    """The free-function protocol (lib.rs:11-19, factorize.rs:34-119, blu.rs:345-377 done by the caller):
+    Reallocate escapes with addmem_*, the caller grows the stores and calls again with c0ntinue; c0ntinue
+    without a pending Reallocate is ErrorInvalidCall (factorize.rs:102-105)."""
+    m = 110
+    cp, ri, v = gen.basis(77, m, 20, 5.0)
+    o = oracle_for(m, len(v), 400)
+    assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+    g = BLU(m, len(v), lib=emu)
+    g.threads_per_basis = 64
+    assert g.factorize_c0ntinue(cp[:-1], cp[1:], ri, v, True) == -2
+    g.l_mem = len(v); g.u_mem = len(v); g.w_mem = len(v)
+    st, rounds = g.factorize_c0ntinue(cp[:-1], cp[1:], ri, v, False), 0
+    while st == 1:
+        rounds += 1
+        assert rounds < 30
+        add = [g.info(n) for n in ("addmem_l", "addmem_u", "addmem_w")]
+        assert max(add) > 0
+        for name, a in zip(("l_mem", "u_mem", "w_mem"), add):
+            if a > 0:
+                setattr(g, name, int(1.5 * (g.get_param(name) + a)) + 1)      # lu_realloc_obj, blu.rs:345-377
+        st = g.factorize_c0ntinue(cp[:-1], cp[1:], ri, v, True)
+    assert st == 0 and rounds >= 1
+    assert_factor_parity(g, o, check_stats=False)
+    assert g.factorize_c0ntinue(cp[:-1], cp[1:], ri, v, True) == -2      # nothing pending any more
