@@ -140,6 +140,7 @@ struct Shm {
     int mode, suspend;        /* BLU_MODE_*; 1 = park for the tail kernel, 2 = park for the build kernel */
     int dv_smem;              /* the launch has room for the dense values and bitmaps in shared memory */
     int use_tree, tree_levels, tree_off[8], tree_n[8];   /* min-tree over the column keys (markowitz_search of large bumps) */
+    u64 mbar; unsigned mbar_phase;   /* completion barrier of the bulk copies (dense_pivot) and its current phase */
     int lput, uput;           /* fill pointers of L and U (= l_begin_p[rank], u_begin[rank]) */
     int dpcand;               /* stash row of the pivot column's keys (-1: none) */
 };
@@ -325,6 +326,29 @@ __device__ __forceinline__ void lane_prefetch(const void *p) {
     (void)p;
 #endif
 }
+
+/* ---- bulk asynchronous copy global -> shared (the TMA engine's 1-D form, cp.async.bulk, completion on an mbarrier):
+ * one thread starts the copy of a contiguous, 16-byte aligned segment and the block goes on with other work; whoever
+ * needs the data waits for the barrier's phase.  SASS: UBLKCP + SYNCS.  (The emulator copies in place.) ---- */
+#ifndef BLU_EMU
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *sdst, const void *gsrc, unsigned bytes, u64 *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#else
+static inline void mbar_init(u64 *, unsigned) {}
+static inline void bulk_copy_g2s(void *sdst, const void *gsrc, unsigned bytes, u64 *) { memcpy(sdst, gsrc, bytes); }
+static inline void mbar_wait(u64 *, unsigned) {}
+#endif
 
 /* record the first failed device-side invariant (kept live like the reference's assert!s) */
 #define BLU_CHECK(S, cond) do { if (!(cond)) { if ((S).M.info->internal_error == 0) (S).M.info->internal_error = __LINE__; (S).status = BLU_ERROR_INTERNAL; } } while (0)

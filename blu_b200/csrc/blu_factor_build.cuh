@@ -304,6 +304,8 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
     BLU_DYN_SMEM(dyn);
     __shared__ Shm S;
     const int tid = threadIdx.x;
+    if (tid == 0) { mbar_init(&S.mbar, 1); S.mbar_phase = 0; }
+    bsync<NT>();
     for (int s = D.slot0 + blockIdx.x; s < D.slot0 + D.nslot; s += gridDim.x) {
         const bool fresh = mode == BLU_MODE_WHOLE || mode == BLU_MODE_HEAD;
         if (!fresh && D.info[s].status != (mode == BLU_MODE_TAIL ? BLU_SUSPENDED_TAIL : BLU_SUSPENDED_BUILD)) continue;

@@ -30,7 +30,7 @@
 /* ------------------------------------------------------------------ */
 /* garbage collection (role of file.rs:92 file_compress)               */
 /* ------------------------------------------------------------------ */
-template <int NT> __device__ void w_compact(Shm &S) {
+template <int NT> __device__ __noinline__ void w_compact(Shm &S) {
     Mat &M = S.M;
     const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = NT / 32;
@@ -107,7 +107,7 @@ template <int NT> __device__ bool w_reserve(Shm &S, i64 grow) {
 /* ------------------------------------------------------------------ */
 __device__ __forceinline__ const u64 *ctree_level(const Shm &S, int l) { return l == 0 ? S.M.ckey : S.M.ctree + S.tree_off[l]; }
 
-template <int NT> __device__ void ctree_build(Shm &S) {
+template <int NT> __device__ __noinline__ void ctree_build(Shm &S) {
     Mat &M = S.M;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = NT / 32;
@@ -132,7 +132,7 @@ template <int NT> __device__ void ctree_build(Shm &S) {
 }
 
 /* the keys of columns cols[0..ncols) (and of column `extra` if >= 0) changed: repair their ancestors */
-template <int NT> __device__ void ctree_update(Shm &S, const int *cols, int ncols, int extra) {
+template <int NT> __device__ __noinline__ void ctree_update(Shm &S, const int *cols, int ncols, int extra) {
     Mat &M = S.M;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = NT / 32;
@@ -363,7 +363,7 @@ template <int NT> __device__ void markowitz_search(Shm &S) {
 /* (each item is judged against the best cost so far), so one item at a */
 /* time: the block finds the next column / row by key, warp 0 judges it.*/
 /* ------------------------------------------------------------------ */
-template <int NT> __device__ void markowitz_search_rows(Shm &S) {
+template <int NT> __device__ __noinline__ void markowitz_search_rows(Shm &S) {
     Mat &M = S.M;
     const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double abstol = M.prm.abstol, reltol = M.prm.reltol;
@@ -972,7 +972,7 @@ template <int NT, bool FAST> __device__ void pivot_general_t(Shm &S, const bool 
     }
     bsync<NT>();
 }
-template <int NT> __device__ __forceinline__ void pivot_general(Shm &S, const bool small) { pivot_general_t<NT, false>(S, small); }
+template <int NT> __device__ __noinline__ void pivot_general(Shm &S, const bool small) { pivot_general_t<NT, false>(S, small); }      /* (the rare variant: kept out of line so that it does not weigh on the register allocation of the hot loop) */
 template <int NT> __device__ __forceinline__ void pivot_general_fast(Shm &S, const bool small) { pivot_general_t<NT, true>(S, small); }
 
 /* ------------------------------------------------------------------ */

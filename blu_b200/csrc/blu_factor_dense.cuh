@@ -47,6 +47,7 @@ struct DenseSm {
     unsigned *keyc, *keyr; /* sort keys of the pivot column / row */
     u64 *sdrop;            /* pivot_small: cancellation mask per column of the pivot row (overlays keyc|keyr) */
     unsigned *candk;       /* key stash of the search candidates */
+    BluKey2 *rowk;         /* the pivot row's keys, fetched by one bulk copy (16-byte aligned: kd is a multiple of 32) */
     unsigned *cmask, *rmask, *rfull;
     unsigned short *clist, *rlist, *posr, *rnz, *cnz, *tmps, *tmpr;
     unsigned *rb_s, *cb_s; double *dv_s;   /* resident bitmaps and values (RES only) */
@@ -61,6 +62,7 @@ __device__ __forceinline__ void dense_view(DenseSm &d, unsigned char *dyn, int K
     d.dcol = p4; p4 += KD;
     d.keyc = (unsigned *)p4; d.sdrop = (u64 *)p4; p4 += KD;
     d.keyr = (unsigned *)p4; p4 += KD;
+    d.rowk = (BluKey2 *)p4; p4 += KD;
     d.candk = (unsigned *)p4; p4 += DENSE_STASH * KD;
     d.cmask = (unsigned *)p4; p4 += KW;
     d.rmask = (unsigned *)p4; p4 += KW;
@@ -309,7 +311,13 @@ template <int NT, bool RES> __device__ __noinline__ void dense_search(Shm &S) {
         if (cc < DENSE_STASH) {
             /* all key loads of the column in flight together; the pivot step reuses them */
             unsigned *stash = d.candk + cc * KD;
-            for (int t = lane; t < nr; t += 32) stash[t] = bit_test(cb, t) ? dkey[(size_t)t * KD + c].c : 0xffffffffu;
+            {   /* kd <= 256: at most eight rows per lane, their key loads issued back to back (one round trip) */
+                unsigned kq[8];
+                #pragma unroll
+                for (int u = 0; u < 8; u++) { const int t = lane + 32 * u; kq[u] = (t < nr && bit_test(cb, t)) ? dkey[(size_t)t * KD + c].c : 0xffffffffu; }
+                #pragma unroll
+                for (int u = 0; u < 8; u++) { const int t = lane + 32 * u; if (t < nr) stash[t] = kq[u]; }
+            }
             __syncwarp();
             for (int t = lane; t < nr; t += 32) {
                 const unsigned kq = stash[t];
@@ -369,6 +377,10 @@ template <int NT, bool RES, bool SMALL> __device__ __noinline__ void dense_pivot
     const int cnz1 = n - 1, rnz1 = k - 1;
 
     i64 tq = clock64();
+    /* the keys of the pivot row are one contiguous segment of kd * 4 bytes in HBM/L2: one thread hands the copy
+     * to the bulk-copy engine (cp.async.bulk + mbarrier) and the block gathers the pivot column meanwhile */
+    const unsigned phase = S.mbar_phase;
+    if (tid == 0) bulk_copy_g2s(d.rowk, dkey + (size_t)tp * KD, (unsigned)(KD * sizeof(BluKey2)), &S.mbar);
     /* 1. the pivot column and the pivot row with their storage-order keys */
     {
         const int sc = S.dpcand;
@@ -379,8 +391,12 @@ template <int NT, bool RES, bool SMALL> __device__ __noinline__ void dense_pivot
                 d.keyc[e] = sc >= 0 ? d.candk[sc * KD + t] : dkey[(size_t)t * KD + cp].c;
             }
     }
+#ifdef BLU_EMU
+    bsync<NT>();      /* (the emulator's copy ran on thread 0) */
+#endif
+    mbar_wait(&S.mbar, phase);
     for (int c = tid; c < nc; c += NT)
-        if (bit_test(rbp, c)) { const int e = bits_rank(rbp, c); d.tmpr[e] = (unsigned short)c; d.keyr[e] = dkey[(size_t)tp * KD + c].r; }
+        if (bit_test(rbp, c)) { const int e = bits_rank(rbp, c); d.tmpr[e] = (unsigned short)c; d.keyr[e] = d.rowk[c].r; }
     for (int w = tid; w < KW; w += NT) {
         d.cmask[w] = cbp[w] & ~(w == (tp >> 5) ? 1u << (tp & 31) : 0u);
         d.rfull[w] = rbp[w];
@@ -429,6 +445,12 @@ template <int NT, bool RES, bool SMALL> __device__ __noinline__ void dense_pivot
         const int c = d.rlist[kk];
         const unsigned *cb = cbm + c * KW;
         double cmx = 0.0; unsigned kmin = 0xffffffffu; int tmin = -1;
+        {   /* a column whose only entry outside the pivot column is the pivot-row entry (the usual case once the
+             * tail is full) has nothing to exchange and no maximum to seed: no key is needed */
+            int others = 0;
+            for (int w = 0; w < KW; w++) others += __popc(cb[w] & ~d.cmask[w]);
+            if (others == 1) { d.scm[c] = 0; continue; }
+        }
         const unsigned short kpr = dkey[(size_t)tp * KD + c].c;
         /* the keys live in HBM/L2: fetch them eight at a time so that one round trip serves eight entries */
         int w = 0; unsigned tb = cb[0] & ~d.cmask[0];
@@ -585,6 +607,7 @@ template <int NT, bool RES, bool SMALL> __device__ __noinline__ void dense_pivot
             d.skeyc[cp] = KEY_INF; d.cnz[cp] = 0; d.rnz[tp] = 0;
             S.n_kind[5]++;
             S.n_kind[7] += clock64() - tq;
+            S.mbar_phase = phase ^ 1u;
         }
     }
     bsync<NT>();

@@ -26,7 +26,10 @@ for nt, kd, tail in [(a, b_, c) for a in nts for b_ in kds for c in (tails if b_
         b.threads_per_basis = nt
         b.dense_k = kd
         b.tail_threads = tail
-        b.l_mem = 100000; b.u_mem = 100000; b.w_mem = 900000
+        if os.environ.get("SWEEP_W_MEM"):
+            b.w_mem = int(os.environ["SWEEP_W_MEM"])
+        elif not os.environ.get("SWEEP_DEFAULT_MEM"):
+            b.l_mem = 100000; b.u_mem = 100000; b.w_mem = 900000
         assert b.upload(bb, be, bi, bx, rhs) == 0
         ms = []
         for it in range(3):
@@ -36,7 +39,8 @@ for nt, kd, tail in [(a, b_, c) for a in nts for b_ in kds for c in (tails if b_
         ph = np.array([[b.info(k, f"t_phase{q}") for q in range(16)] for k in sample]).mean(0)
         kinds = np.array([[b.info(k, f"n_kind{q}") for q in range(8)] for k in sample]).mean(0)
         bad = sum(int(b.info(k, "status")) != 0 for k in sample)
-        print(f"nt {nt} dense_k {kd} tail {tail}: k_factorize {min(ms):.1f} ms (runs {[round(x, 1) for x in ms]}), norms {b.last_kernel_ms(2):.1f} ms, bad {bad}", flush=True)
+        gc = np.mean([b.info(k, "ngarbage") for k in sample]); nre = int(b.info(0, "nrealloc"))
+        print(f"nt {nt} dense_k {kd} tail {tail}: k_factorize {min(ms):.1f} ms (runs {[round(x, 1) for x in ms]}), norms {b.last_kernel_ms(2):.1f} ms, bad {bad}, head/tail/build {b.last_kernel_ms(3):.1f}/{b.last_kernel_ms(4):.1f}/{b.last_kernel_ms(5):.1f} ms, w_mem {int(b.get_param('w_mem'))} gc/basis {gc:.2f} realloc rounds {nre}", flush=True)
         print("   kcycles/basis: " + " ".join(f"{n}={v / 1e3:.0f}" for n, v in zip(names, ph)), flush=True)
         print("   pivots/basis: srow %.1f scol %.1f dbl %.1f small %.1f any %.1f | dense steps %.1f entries %.2f d_finish kcycles %.0f" % tuple(list(kinds[:7]) + [kinds[7] / 1e3]), flush=True)
         b.close()
