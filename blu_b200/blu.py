@@ -87,6 +87,10 @@ def load_library(path=None):
     L.blu_batch_factorize_resident.argtypes = [vp]
     L.blu_batch_solve_dense_resident.argtypes = [vp, ctypes.c_char]
     L.blu_batch_download.argtypes = [vp, f64p, i32p]
+    L.blu_batch_factorize_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int64]
+    L.blu_batch_solve_dense_dev.argtypes = [vp, vp, vp, ctypes.c_char, vp]
+    L.blu_batch_graph_capture.argtypes = [vp, ctypes.c_char]
+    L.blu_batch_graph_launch.argtypes = [vp]
     L.blu_batch_stream.argtypes = [vp]; L.blu_batch_stream.restype = vp
     L.blu_batch_set_stream.argtypes = [vp, vp]
     L.blu_batch_synchronize.argtypes = [vp]
@@ -361,6 +365,19 @@ class BLUBatch(_Base):
 
     def factorize_resident(self):
         return self._L.blu_batch_factorize_resident(self._h)
+
+    def factorize_dev(self, d_b_begin, d_b_end, d_b_i, d_b_x, bnz_total):
+        """B in caller-owned device memory (raw device pointers as ints, e.g. torch.Tensor.data_ptr())."""
+        return self._L.blu_batch_factorize_dev(self._h, d_b_begin, d_b_end, d_b_i, d_b_x, int(bnz_total))
+
+    def solve_dense_dev(self, d_rhs, d_lhs, trans="N", d_status=None):
+        return self._L.blu_batch_solve_dense_dev(self._h, d_rhs, d_lhs, _ch(trans), d_status)
+
+    def graph_capture(self, trans="N"):
+        return self._L.blu_batch_graph_capture(self._h, _ch(trans))
+
+    def graph_launch(self):
+        return self._L.blu_batch_graph_launch(self._h)
 
     def solve_dense_resident(self, trans="N"):
         return self._L.blu_batch_solve_dense_resident(self._h, _ch(trans))

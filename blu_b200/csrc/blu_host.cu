@@ -65,6 +65,8 @@ struct blu_b200 {
     std::vector<BluInfo> hinfo;
     std::vector<int64_t> hb_begin, hb_end, hb_i; std::vector<double> hb_x; /* compact staging (object API) */
     int have_b;                 /* B resident on device (for re-runs) */
+    int b_external;             /* B lives in the caller's device buffers (blu_batch_factorize_dev) */
+    cudaGraph_t graph; cudaGraphExec_t graph_exec; int have_graph; char graph_trans;   /* blu_batch_graph_* */
     double time_factorize, time_solve, time_update;
 };
 
@@ -200,6 +202,7 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     if (const char *e = getenv("BLU_B200_CAP")) { int c = atoi(e); if (c >= 64 && c <= 4096) o->cap = c & ~31; }   /* tuning knob: entries of the shared-memory line caches */
     o->launches = 0; o->nrealloc = 0; o->last_ms[0] = o->last_ms[1] = 0.0; o->last_part_ms[0] = o->last_part_ms[1] = o->last_part_ms[2] = 0.0;
     o->d_slot = nullptr; o->have_overrides = 0; o->escape_realloc = 0; o->task_pending = 0;
+    o->b_external = 0; o->have_graph = 0;
     o->have_b = 0; o->info_dirty = 0; o->norms = 1; o->last_norms_ms = 0.0;
     o->have_pipe = 0; o->d_chunk_end = nullptr; o->h_chunk_end = nullptr;
     o->dm_rhs = o->dm_lhs = o->dm_work = nullptr; o->dm_status = nullptr; o->multi_cap = 0;
@@ -304,6 +307,9 @@ static void destroy_common(blu_b200 *o) {
         cudaStreamDestroy(o->copy_stream);
         cudaFreeHost(o->h_chunk_end);
     }
+#ifndef BLU_EMU
+    if (o->have_graph) { cudaGraphExecDestroy(o->graph_exec); cudaGraphDestroy(o->graph); }
+#endif
     if (o->own_stream) cudaStreamDestroy(o->stream);
     delete o;
 }
@@ -447,8 +453,10 @@ static int ensure_info(blu_b200 *o) {
 static int factorize_resident(blu_b200 *o, int hungry_known = 0, int escape_realloc = 0) {
     CK(cudaSetDevice(o->device));
     BluDev &d = o->d;
-    d.b_begin = (const blu_i64 *)o->db_begin; d.b_end = (const blu_i64 *)o->db_end;
-    d.b_i = (const blu_i64 *)o->db_i; d.b_x = o->db_x;
+    if (!o->b_external) {
+        d.b_begin = (const blu_i64 *)o->db_begin; d.b_end = (const blu_i64 *)o->db_end;
+        d.b_i = (const blu_i64 *)o->db_i; d.b_x = o->db_x;
+    }
     double total_ms = 0.0;
     if (hungry_known && !o->single) {      /* a pipelined first pass already ran: hinfo says who wants more memory */
         int st = grow_hungry_slots(o);
@@ -534,7 +542,7 @@ extern "C" int blu_batch_upload(blu_batch_t *o, const int64_t *b_begin, const in
             CK(cudaMemcpyAsync(o->db_i, b_i, (size_t)bnz_total * sizeof(int64_t), cudaMemcpyHostToDevice, o->stream));
             CK(cudaMemcpyAsync(o->db_x, b_x, (size_t)bnz_total * sizeof(double), cudaMemcpyHostToDevice, o->stream));
         }
-        o->have_b = 1;
+        o->have_b = 1; o->b_external = 0;
         o->d.b_total = bnz_total;
     }
     if (rhs) CK(cudaMemcpyAsync(o->d_rhs, rhs, n * m * sizeof(double), cudaMemcpyHostToDevice, o->stream));
@@ -559,6 +567,74 @@ static int solve_dense_resident(blu_b200 *o, char trans) {
 extern "C" int blu_batch_solve_dense_resident(blu_batch_t *o, char trans) {
     if (!o) return BLU_ERROR_INVALID_ARGUMENT;
     return solve_dense_resident(o, trans);
+}
+
+/* SURVEY.md 8(f) N4 -- caller-owned DEVICE buffers: nothing is staged or copied, everything is queued on the
+ * batch's stream.  B must stay valid and unchanged until the next factorization of this batch. */
+extern "C" int blu_batch_factorize_dev(blu_batch_t *o, const int64_t *d_b_begin, const int64_t *d_b_end,
+                                       const int64_t *d_b_i, const double *d_b_x, int64_t bnz_total) {
+    if (!o || !d_b_begin || !d_b_end || bnz_total < 0 || (bnz_total > 0 && (!d_b_i || !d_b_x))) return BLU_ERROR_INVALID_ARGUMENT;
+    BluDev &d = o->d;
+    d.b_begin = (const blu_i64 *)d_b_begin; d.b_end = (const blu_i64 *)d_b_end;
+    d.b_i = (const blu_i64 *)d_b_i; d.b_x = d_b_x; d.b_total = bnz_total;
+    o->b_external = 1; o->have_b = 1;
+    return factorize_resident(o);
+}
+extern "C" int blu_batch_solve_dense_dev(blu_batch_t *o, const double *d_rhs, double *d_lhs, char trans, int *d_status) {
+    if (!o || !d_rhs || !d_lhs) return BLU_ERROR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(o->device));
+    timer_start(o);
+    BLU_LAUNCH(k_solve_dense, o->d.nmat, 32, 0, o->stream, o->d, d_rhs, d_lhs, trans, d_status ? d_status : o->d_status, (double *)nullptr, 0);
+    o->launches++;
+    CK(cudaGetLastError());
+    timer_stop(o, 1);
+    return BLU_OK;
+}
+
+/* The steady-state step of a resident batch -- the factorization launches, condest/residual_test and solve_dense
+ * -- captured once into a CUDA graph and replayed with one launch call.  A replay in which some basis answers
+ * Reallocate falls back to the classic path (grow that basis, re-run it) before the solve is repeated. */
+extern "C" int blu_batch_graph_capture(blu_batch_t *o, char trans) {
+    if (!o || !o->have_b) return BLU_ERROR_INVALID_CALL;
+    CK(cudaSetDevice(o->device));
+#ifndef BLU_EMU
+    if (o->have_graph) { cudaGraphExecDestroy(o->graph_exec); cudaGraphDestroy(o->graph); o->have_graph = 0; }
+    BluDev &d = o->d;
+    if (!o->b_external) { d.b_begin = (const blu_i64 *)o->db_begin; d.b_end = (const blu_i64 *)o->db_end; d.b_i = (const blu_i64 *)o->db_i; d.b_x = o->db_x; }
+    CK(cudaStreamSynchronize(o->stream));
+    cudaStream_t cap = nullptr;      /* (a stream of its own: launch_factorize records timing events only on o->stream) */
+    CK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    CK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    int st = launch_factorize(o, cap, 0, d.nmat);
+    if (st == BLU_OK && o->norms) { BLU_LAUNCH(k_factor_norms, d.nmat, 128, 0, cap, d); o->launches++; }
+    if (st == BLU_OK) { BLU_LAUNCH(k_solve_dense, d.nmat, 32, 0, cap, d, (const double *)o->d_rhs, o->d_lhs, trans, o->d_status, (double *)nullptr, 0); o->launches++; }
+    cudaError_t e = cudaStreamEndCapture(cap, &o->graph);
+    cudaStreamDestroy(cap);
+    if (st != BLU_OK) return st;
+    CK(e);
+    CK(cudaGraphInstantiate(&o->graph_exec, o->graph, 0));
+#endif
+    o->have_graph = 1; o->graph_trans = trans;
+    return BLU_OK;
+}
+extern "C" int blu_batch_graph_launch(blu_batch_t *o) {
+    if (!o || !o->have_graph) return BLU_ERROR_INVALID_CALL;
+    CK(cudaSetDevice(o->device));
+#ifndef BLU_EMU
+    timer_start(o);
+    CK(cudaGraphLaunch(o->graph_exec, o->stream));
+    timer_stop(o, 0);
+    int st = fetch_info(o);
+    if (st != BLU_OK) return st;
+    bool hungry = false;
+    for (auto &I : o->hinfo) hungry = hungry || I.status == BLU_REALLOCATE;
+    if (!hungry) return BLU_OK;
+    if ((st = factorize_resident(o, 1)) != BLU_OK) return st;      /* blu.rs:95-118 for the bases that asked */
+    return solve_dense_resident(o, o->graph_trans);
+#else
+    int st = factorize_resident(o);
+    return st != BLU_OK ? st : solve_dense_resident(o, o->graph_trans);
+#endif
 }
 
 extern "C" int blu_batch_download(blu_batch_t *o, double *lhs, int *status) {
@@ -627,7 +703,7 @@ static int factorize_pipelined(blu_b200 *o, const int64_t *b_begin, const int64_
         }
         CK(cudaEventRecord(o->ev_up[p], cs));
     }
-    o->have_b = 1;
+    o->have_b = 1; o->b_external = 0;
     d.b_total = bnz_total;
     CK(cudaEventSynchronize(o->ev_up[14]));        /* the chunk ranges are on the host now */
     d.b_begin = (const blu_i64 *)o->db_begin; d.b_end = (const blu_i64 *)o->db_end;

@@ -166,6 +166,17 @@ int blu_batch_upload(blu_batch_t *b, const int64_t *b_begin, const int64_t *b_en
 int blu_batch_factorize_resident(blu_batch_t *b);
 int blu_batch_solve_dense_resident(blu_batch_t *b, char trans);
 int blu_batch_download(blu_batch_t *b, double *lhs, int *status);
+/* SURVEY.md 8(f) N4.  Caller-owned DEVICE buffers (same layout as the host variants): no staging, no copies;
+ * B must stay valid and unchanged until the next factorization of the batch.  d_status (nmat ints on the device)
+ * may be NULL. */
+int blu_batch_factorize_dev(blu_batch_t *b, const int64_t *d_b_begin, const int64_t *d_b_end,
+                            const int64_t *d_b_i, const double *d_b_x, int64_t bnz_total);
+int blu_batch_solve_dense_dev(blu_batch_t *b, const double *d_rhs, double *d_lhs, char trans, int *d_status);
+/* The steady-state step of a resident batch (factorization launches + condest/residual_test + solve_dense of the
+ * uploaded rhs) captured into a CUDA graph once, then replayed with one launch per step; a basis that answers
+ * Reallocate during a replay is grown and re-run by the classic path before the call returns. */
+int blu_batch_graph_capture(blu_batch_t *b, char trans);
+int blu_batch_graph_launch(blu_batch_t *b);
 /* cudaStream_t the library launches on (so callers can bracket it with their own events),
  * and a way to make it use the caller's stream instead */
 void *blu_batch_stream(blu_batch_t *b);

@@ -42,6 +42,8 @@ extern emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
+typedef void *cudaGraph_t;
+typedef void *cudaGraphExec_t;
 #define cudaSuccess 0
 enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 

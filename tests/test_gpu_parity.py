@@ -652,3 +652,37 @@ def test_multi_device_batch():
         _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
         assert np.array_equal(x[k], xo), k
     mb.close()
+
+
+def test_device_pointer_entry_points_and_graph():
+    """B, rhs and lhs in caller-owned device memory (torch tensors here) through
+    blu_batch_factorize_dev / blu_batch_solve_dense_dev, and the steady-state step replayed as a CUDA graph
+    (blu_batch_graph_capture / _launch): both equal the host-pointer path bit for bit."""
+    import torch
+    nmat, m = 200, 500
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 150, 4.0, 9900, 9950)
+    b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()))
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all()
+    st, x_ref, _ = b.solve_dense(rhs, "N")
+    assert st == 0
+    dev = torch.device("cuda", 0)
+    tb, te, ti, tx, tr = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (bb, be, bi, bx, rhs)]
+    tl = torch.zeros(nmat * m, dtype=torch.float64, device=dev)
+    ts = torch.full((nmat,), -1, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    b2 = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()))
+    assert b2.factorize_dev(tb.data_ptr(), te.data_ptr(), ti.data_ptr(), tx.data_ptr(), len(bi)) == 0
+    assert b2.solve_dense_dev(tr.data_ptr(), tl.data_ptr(), "N", ts.data_ptr()) == 0
+    assert b2.synchronize() == 0
+    assert (ts.cpu().numpy() == 0).all()
+    assert np.array_equal(tl.cpu().numpy().reshape(nmat, m), x_ref)
+    for k in (0, 99, 199):
+        assert b2.info(k, "rank") == b.info(k, "rank") and b2.info(k, "residual_test") == b.info(k, "residual_test")
+    # graph replay of the resident step (B and rhs uploaded once)
+    assert b.upload(bb, be, bi, bx, rhs) == 0
+    assert b.graph_capture("N") == 0
+    for _ in range(3):
+        assert b.graph_launch() == 0
+    _, xg, sg = b.download()
+    assert (sg == 0).all() and np.array_equal(xg, x_ref)
