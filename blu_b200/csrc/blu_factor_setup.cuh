@@ -122,165 +122,212 @@ template <int NT> __device__ void phase_validate_transpose(Shm &S) {
     bsync<NT>();
 }
 
-/* singletons.rs:287-393 (columns) and 398-503 (rows).  The FIFO queue is processed
- * by warp 0 in the reference's order; the lanes share the scan of each pivot row /
- * column so one queue entry costs a handful of dependent loads instead of O(nz).
- * iset = iwork1[0..m), queue = iwork1[m..2m). */
-template <int NT> __device__ void singleton_cols(Shm &S) {
-    Mat &M = S.M;
-    const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    int *iset = M.iwork1, *queue = M.iwork1 + m;
-    const double abstol = M.prm.abstol;
-    int tail = 0;
-    for (int base = 0; base < m; base += NT) {
-        int j = base + tid;
-        int is1 = 0;
-        if (j < m && M.qinv[j] < 0) {
-            i64 bb = M.b_begin[j], be = M.b_end[j];
-            int x = 0;
-            for (i64 pos = bb; pos < be; pos++) x ^= (int)M.b_i[pos];
-            iset[j] = x;
-            M.qinv[j] = -(int)(be - bb) - 1;
-            is1 = (be - bb) == 1;
-        }
-        int tot, ex = block_excl_scan<NT>(is1, &tot, S.iscr);
-        if (is1) queue[tail + ex] = j;
-        tail += tot;
-    }
+/* ------------------------------------------------------------------ */
+/* singletons.rs:287-393 (columns) and 398-503 (rows): the peel as a      */
+/* LEVEL-SYNCHRONOUS frontier.  The reference pops a FIFO queue; a line  */
+/* enters the queue when its count drops to 1, so the queue is a         */
+/* sequence of levels (the singletons present at the start, then those   */
+/* created by processing the previous level) and the rank of a pivot is  */
+/* its position in that sequence.  One level is processed in parallel:    */
+/*  A. every queued line with count 1 finds its cross line and pivot; a  */
+/*     pivot of 0 or below abstol is passed over (singletons.rs:353-355,  */
+/*     463-465).  Two queued lines with the same cross line: the first    */
+/*     in queue order wins, the other becomes empty (its count drops to  */
+/*     0 when the winner is processed) -- atomicMin on the cross line.    */
+/*  B. winners take consecutive ranks in queue order (block scan); they   */
+/*     cannot disturb one another (a winner's only active entry is in    */
+/*     its own cross line), so each scans its cross line independently:   */
+/*     U row / L column entries in storage order at offsets from a scan   */
+/*     of the per-winner counts, iset ^= , count -= 1 by atomics.         */
+/*  C. a line whose count reaches 1 joins the next level.  Its place in   */
+/*     the queue is that of the decrement that made the count 1, i.e.     */
+/*     the LAST decrement it saw (a line that goes on to 0 is popped and  */
+/*     skipped, singletons.rs:337-339, so its place is irrelevant): the   */
+/*     key (rank of the winner << 32 | position in the winner's cross     */
+/*     line) is accumulated with atomicMax and the next level is sorted   */
+/*     by it (bitonic, in place).                                         */
+/* Scratch: iset = iwork1[0..m), queue = iwork1[m..2m); win = tmpi[0..m), */
+/* next = tmpi[m..2m), key = (u64*)(tmpi+2m)[m]; per queue entry: rank    */
+/* (pstack), cross line (acols), count / offset (prank); pivots and the   */
+/* sort buffers in gwork.                                              */
+/* ------------------------------------------------------------------ */
+
+/* ascending bitonic sort of (key, val) pairs, n padded to a power of two with KEY_INF; whole block */
+template <int NT> __device__ void block_sort_pairs(u64 *key, int *val, int n) {
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int t = n + (int)threadIdx.x; t < P; t += NT) { key[t] = KEY_INF; val[t] = -1; }
     bsync<NT>();
-    if (wid == 0) {
-        int rank = S.rank;
-        const int rk0 = rank;
-        int uput = M.u_begin[rank];
-        for (int front = 0; front < tail; front++) {
-            const int j = queue[front];
-            if (M.qinv[j] == -1) continue;          /* column became empty meanwhile */
-            const int i = iset[j];
-            const int rb = M.bt_ptr[i], re = M.bt_ptr[i + 1];
-            double piv = 0.0;
-            for (int base = rb; base < re; base += 32) {
-                int pos = base + lane;
-                int hit = pos < re && M.bt_idx[pos] == j;
-                unsigned hm = __ballot_sync(FULLMASK, hit);
-                if (hm) {
-                    double v = hit ? M.bt_val[pos] : 0.0;
-                    piv = __shfl_sync(FULLMASK, v, __ffs((int)hm) - 1);
-                    break;
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < P; t += NT) {
+                const int u = t ^ j;
+                if (u > t) {
+                    const bool up = (t & k) == 0;
+                    const u64 a = key[t], b = key[u];
+                    if ((a > b) == up) { key[t] = b; key[u] = a; const int x = val[t]; val[t] = val[u]; val[u] = x; }
                 }
             }
-            if (piv == 0.0 || fabs(piv) < abstol) continue; /* leave to the bump */
-            if (lane == 0) { M.qinv[j] = rank; M.pinv[i] = rank; }
-            __syncwarp();
-            for (int base = rb; base < re; base += 32) {
-                int pos = base + lane;
-                int j2 = -1; double v = 0.0; int act = 0;
-                if (pos < re) { j2 = M.bt_idx[pos]; v = M.bt_val[pos]; act = M.qinv[j2] < 0; }
-                unsigned am = __ballot_sync(FULLMASK, act);
-                int enq = 0;
-                if (act) {
-                    int dst = uput + __popc(am & lanemask_lt());
-                    M.u_idx[dst] = j2; M.u_val[dst] = v;
-                    iset[j2] ^= i;
-                    int q = M.qinv[j2] + 1;
-                    M.qinv[j2] = q;
-                    enq = q == -2;
-                }
-                unsigned em = __ballot_sync(FULLMASK, enq);
-                if (enq) queue[tail + __popc(em & lanemask_lt())] = j2;
-                uput += __popc(am);
-                tail += __popc(em);
-            }
-            if (lane == 0) { M.u_begin[rank + 1] = uput; M.colpiv[j] = piv; }
-            rank++;
-            __syncwarp();
+            bsync<NT>();
         }
-        /* empty L columns, singletons.rs:385-391 */
-        int lpos = M.l_begin_p[rk0];
-        for (int rk = rk0 + lane; rk < rank; rk += 32) {
-            M.l_idx[lpos + (rk - rk0)] = -1;
-            M.l_begin_p[rk + 1] = lpos + (rk - rk0) + 1;
-        }
-        if (lane == 0) S.rank = rank;
     }
-    bsync<NT>();
 }
 
-template <int NT> __device__ void singleton_rows(Shm &S) {
+/* COLS = true: singleton columns (cross line = the row-wise copy, U rows are produced);
+ * COLS = false: singleton rows (cross line = the column in the caller's storage, L columns are produced). */
+template <int NT, bool COLS> __device__ void singleton_peel(Shm &S) {
     Mat &M = S.M;
     const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
     int *iset = M.iwork1, *queue = M.iwork1 + m;
+    int *win = M.tmpi, *next = M.tmpi + m;
+    u64 *key = (u64 *)(M.tmpi + 2 * m);
+    int *qrank = M.pstack, *qcnt = M.acols, *qoff = M.prank;      /* per queue entry: rank or -1, cross line or -1, count then offset */
+    int *cnt_own = COLS ? M.qinv : M.pinv;      /* -(count) - 1 for active lines, rank >= 0 once pivotal */
+    int *cnt_cross = COLS ? M.pinv : M.qinv;
     const double abstol = M.prm.abstol;
-    int tail = 0;
+    u64 *skey = (u64 *)(M.gwork + m);      /* (slice 0 of gwork is the sparse solves' all-zero solution vector: left alone) */
+    int *sval = (int *)(skey + 2 * (size_t)m);
+    double *qpiv = (double *)(skey + 3 * (size_t)m);      /* (work0 / work1 stay untouched: the solves rely on work0 being zero) */
+
+    /* level 0: the lines with exactly one entry, ascending index (singletons.rs:316-329, 427-440) */
+    int ncur = 0;
     for (int base = 0; base < m; base += NT) {
-        int i = base + tid;
+        const int e = base + tid;
         int is1 = 0;
-        if (i < m && M.pinv[i] < 0) {
-            int rb = M.bt_ptr[i], re = M.bt_ptr[i + 1];
-            int x = 0;
-            for (int pos = rb; pos < re; pos++) x ^= M.bt_idx[pos];
-            iset[i] = x;
-            M.pinv[i] = -(re - rb) - 1;
-            is1 = (re - rb) == 1;
+        if (e < m) {
+            win[e] = 0x7fffffff; key[e] = 0;
+            if (cnt_own[e] < 0) {
+                int x = 0, n;
+                if (COLS) { const i64 bb = M.b_begin[e], be = M.b_end[e]; for (i64 pos = bb; pos < be; pos++) x ^= (int)M.b_i[pos]; n = (int)(be - bb); }
+                else { const int rb = M.bt_ptr[e], re = M.bt_ptr[e + 1]; for (int pos = rb; pos < re; pos++) x ^= M.bt_idx[pos]; n = re - rb; }
+                iset[e] = x;
+                cnt_own[e] = -n - 1;
+                is1 = n == 1;
+            }
         }
         int tot, ex = block_excl_scan<NT>(is1, &tot, S.iscr);
-        if (is1) queue[tail + ex] = i;
-        tail += tot;
+        if (is1) queue[ncur + ex] = e;
+        ncur += tot;
     }
     bsync<NT>();
-    if (wid == 0) {
-        int rank = S.rank;
-        const int rk0 = rank;
-        int lput = M.l_begin_p[rank];
-        for (int front = 0; front < tail; front++) {
-            const int i = queue[front];
-            if (M.pinv[i] == -1) continue;
-            const int j = iset[i];
-            const i64 cb = M.b_begin[j], ce = M.b_end[j];
-            double piv = 0.0;
-            for (i64 base = cb; base < ce; base += 32) {
-                i64 pos = base + lane;
-                int hit = pos < ce && (int)M.b_i[pos] == i;
-                unsigned hm = __ballot_sync(FULLMASK, hit);
-                if (hm) {
-                    double v = hit ? M.b_x[pos] : 0.0;
-                    piv = __shfl_sync(FULLMASK, v, __ffs((int)hm) - 1);
-                    break;
-                }
+    int rank = S.rank;
+    const int rk0 = rank;
+    int put = COLS ? M.u_begin[rank] : M.l_begin_p[rank];      /* fill pointer of U (columns pass) / L (rows pass) */
+
+    while (ncur > 0) {
+        /* A. pivots and winners */
+        for (int q = tid; q < ncur; q += NT) {
+            const int e = queue[q];
+            double piv = 0.0; int x = -1;
+            if (cnt_own[e] == -2) {      /* still exactly one entry */
+                x = iset[e];
+                if (COLS) { for (i64 pos = M.b_begin[e]; pos < M.b_end[e]; pos++) if ((int)M.b_i[pos] == x) { piv = M.b_x[pos]; break; } }
+                else { for (int pos = M.bt_ptr[e]; pos < M.bt_ptr[e + 1]; pos++) if (M.bt_idx[pos] == x) { piv = M.bt_val[pos]; break; } }
+                if (piv == 0.0 || fabs(piv) < abstol) x = -1;      /* left to the bump */
+                else atomicMin(&win[x], q);
             }
-            if (piv == 0.0 || fabs(piv) < abstol) continue;
-            if (lane == 0) { M.qinv[j] = rank; M.pinv[i] = rank; }
-            __syncwarp();
-            for (i64 base = cb; base < ce; base += 32) {
-                i64 pos = base + lane;
-                int i2 = -1; double v = 0.0; int act = 0;
-                if (pos < ce) { i2 = (int)M.b_i[pos]; v = M.b_x[pos]; act = M.pinv[i2] < 0; }
-                unsigned am = __ballot_sync(FULLMASK, act);
-                int enq = 0;
-                if (act) {
-                    int dst = lput + __popc(am & lanemask_lt());
-                    M.l_idx[dst] = i2; M.l_val[dst] = __ddiv_rn(v, piv);
-                    iset[i2] ^= j;
-                    int q = M.pinv[i2] + 1;
-                    M.pinv[i2] = q;
-                    enq = q == -2;
-                }
-                unsigned em = __ballot_sync(FULLMASK, enq);
-                if (enq) queue[tail + __popc(em & lanemask_lt())] = i2;
-                lput += __popc(am);
-                tail += __popc(em);
-            }
-            if (lane == 0) { M.l_idx[lput] = -1; M.l_begin_p[rank + 1] = lput + 1; M.colpiv[j] = piv; }
-            lput++;
-            rank++;
-            __syncwarp();
+            qcnt[q] = x; qpiv[q] = piv;
         }
-        /* empty U rows, singletons.rs:495-500 */
-        int upos = M.u_begin[rk0];
-        for (int rk = rk0 + lane; rk < rank; rk += 32) M.u_begin[rk + 1] = upos;
-        if (lane == 0) S.rank = rank;
+        bsync<NT>();
+        /* B1. ranks in queue order; mark the pivots */
+        int nwin = 0;
+        for (int base = 0; base < ncur; base += NT) {
+            const int q = base + tid;
+            const int x = q < ncur ? qcnt[q] : -1;
+            const int w = x >= 0 && win[x] == q;
+            int tot, ex = block_excl_scan<NT>(w, &tot, S.iscr);
+            if (q < ncur) {
+                qrank[q] = w ? rank + nwin + ex : -1;
+                if (w) { const int e = queue[q]; cnt_own[e] = rank + nwin + ex; cnt_cross[x] = rank + nwin + ex; M.colpiv[COLS ? e : x] = qpiv[q]; }
+            }
+            nwin += tot;
+        }
+        bsync<NT>();
+        /* B2. entries each winner will emit (active entries of its cross line; + the terminator of an L column) */
+        for (int q = wid; q < ncur; q += NW) {
+            if (qrank[q] < 0) { if (lane == 0) qoff[q] = 0; continue; }
+            const int x = qcnt[q];
+            int n = 0;
+            if (COLS) { for (int pos = M.bt_ptr[x] + lane; pos < M.bt_ptr[x + 1]; pos += 32) n += M.qinv[M.bt_idx[pos]] < 0; }
+            else { for (i64 pos = M.b_begin[x] + lane; pos < M.b_end[x]; pos += 32) n += M.pinv[(int)M.b_i[pos]] < 0; }
+            n = warp_sum(n);
+            if (lane == 0) qoff[q] = n + (COLS ? 0 : 1);
+        }
+        bsync<NT>();
+        int produced = 0;
+        for (int base = 0; base < ncur; base += NT) {
+            const int q = base + tid;
+            const int n = q < ncur ? qoff[q] : 0;
+            int tot, ex = block_excl_scan<NT>(n, &tot, S.iscr);
+            if (q < ncur && qrank[q] >= 0) {
+                const int off = put + produced + ex, rk = qrank[q];
+                qoff[q] = off;      /* where this winner writes */
+                if (COLS) M.u_begin[rk + 1] = off + n;
+                else { M.l_begin_p[rk + 1] = off + n; M.l_idx[off + n - 1] = -1; }
+            }
+            produced += tot;
+        }
+        bsync<NT>();
+        /* B3. scan the cross lines: emit, decrement, collect the next level */
+        if (tid == 0) S.ncand = 0;      /* entries of `next` */
+        bsync<NT>();
+        for (int q = wid; q < ncur; q += NW) {
+            const int rk = qrank[q];
+            if (rk < 0) continue;
+            const int x = qcnt[q];
+            const double piv = qpiv[q];
+            int off = qoff[q];
+            const i64 lb = COLS ? (i64)M.bt_ptr[x] : M.b_begin[x], le = COLS ? (i64)M.bt_ptr[x + 1] : M.b_end[x];
+            for (i64 base = lb; base < le; base += 32) {
+                const i64 pos = base + lane;
+                int o = -1; double v = 0.0; int act = 0;
+                if (pos < le) {
+                    if (COLS) { o = M.bt_idx[pos]; v = M.bt_val[pos]; act = M.qinv[o] < 0; }
+                    else { o = (int)M.b_i[pos]; v = M.b_x[pos]; act = M.pinv[o] < 0; }
+                }
+                const unsigned am = __ballot_sync(FULLMASK, act);
+                if (act) {
+                    const int dst = off + __popc(am & lanemask_lt());
+                    if (COLS) { M.u_idx[dst] = o; M.u_val[dst] = v; }
+                    else { M.l_idx[dst] = o; M.l_val[dst] = __ddiv_rn(v, piv); }
+                    atomicXor(&iset[o], x);
+                    atomicMax((unsigned long long *)&key[o], ((unsigned long long)(unsigned)rk << 32) | (unsigned long long)(unsigned)(pos - lb));
+                    const int old = atomicAdd(&cnt_own[o], 1);
+                    if (old == -3) next[atomicAdd(&S.ncand, 1)] = o;      /* count 2 -> 1: a new singleton */
+                }
+                off += __popc(am);
+            }
+        }
+        bsync<NT>();
+        /* restore the cross-line scratch of this level, advance */
+        for (int q = tid; q < ncur; q += NT) if (qcnt[q] >= 0) win[qcnt[q]] = 0x7fffffff;
+        const int nnext = S.ncand;
+        rank += nwin; put += produced;
+        bsync<NT>();
+        /* C. the next level in queue order */
+        for (int t = tid; t < nnext; t += NT) { skey[t] = key[next[t]]; sval[t] = next[t]; }
+        bsync<NT>();
+        if (nnext > 1) block_sort_pairs<NT>(skey, sval, nnext);
+        for (int t = tid; t < nnext; t += NT) queue[t] = sval[t];
+        ncur = nnext;
+        bsync<NT>();
     }
+    /* the lines of the other factor are empty for these pivots: singletons.rs:385-391 / 495-500 */
+    if (COLS) {
+        const int lpos = M.l_begin_p[rk0];
+        for (int rk = rk0 + tid; rk < rank; rk += NT) { M.l_idx[lpos + (rk - rk0)] = -1; M.l_begin_p[rk + 1] = lpos + (rk - rk0) + 1; }
+    } else {
+        const int upos = M.u_begin[rk0];
+        for (int rk = rk0 + tid; rk < rank; rk += NT) M.u_begin[rk + 1] = upos;
+    }
+    /* gwork is the per-warp scatter space of the pivot steps and must be all zero when they start */
+    for (size_t t = tid; t < 4 * (size_t)m; t += NT) M.gwork[m + t] = 0.0;
+    if (tid == 0) S.rank = rank;
     bsync<NT>();
 }
+template <int NT> __device__ void singleton_cols(Shm &S) { singleton_peel<NT, true>(S); }
+template <int NT> __device__ void singleton_rows(Shm &S) { singleton_peel<NT, false>(S); }
 
 /* singletons.rs:81-264 */
 template <int NT> __device__ void phase_singletons(Shm &S) {

@@ -149,6 +149,7 @@ template <typename T> inline T atomicSub(T *p, T v) { T o = *p; *p = o - v; retu
 template <typename T> inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <typename T> inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <typename T> inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
+template <typename T> inline T atomicXor(T *p, T v) { T o = *p; *p = o ^ v; return o; }
 template <typename T> inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
 template <typename T> inline T atomicAnd(T *p, T v) { T o = *p; *p = o & v; return o; }
 template <typename T> inline T atomicCAS(T *p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
