@@ -48,7 +48,7 @@ enum {
     BLU_P_NORMS,                        /* 1 (default): factorize also runs condest x2 + residual_test as factorize.rs:121-147 does; 0: skip them (their getters then read 0) */
     BLU_P_DENSE_K,                      /* order at which the active submatrix switches to the dense-tail representation (multiple of 32, <= 256; 0 = never; default: the largest order whose values fit in shared memory, 160 on B200).  Results do not depend on it. */
     BLU_P_TAIL_THREADS,                 /* CTA size of the dense-tail launch of a split batch factorization (default 512) */
-    BLU_P_SPLIT_MIN,                    /* batches of more bases than this run as three launches: sparse head, dense tail with one CTA per SM, build_factors (default: the SM count) */
+    BLU_P_SPLIT_MIN,                    /* batches of more bases than this run as three launches: sparse head, dense tail with one CTA per SM, build_factors (default 0: always, when the dense tail is shared-memory resident -- a single launch sized for 200+ KB of shared memory would leave the sparse head without L1) */
     BLU_P_TREE_MIN,                     /* bumps with more active columns than this find their Markowitz candidates through a min-tree over the column keys instead of a scan (default 4096; needs maxsearch <= 4) */
     BLU_I_M = 100, BLU_I_RANK, BLU_I_BUMP_SIZE, BLU_I_BUMP_NZ, BLU_I_MATRIX_NZ, BLU_I_L_NZ,
     BLU_I_U_NZ, BLU_I_R_NZ, BLU_I_NSEARCH_PIVOT, BLU_I_NEXPAND, BLU_I_NGARBAGE,
