@@ -1479,19 +1479,25 @@ extern "C" int blu_multi_create(blu_multi_t **out, int64_t nmat, int64_t m, int6
     mb->ndev = ndev; mb->nmat = nmat; mb->m = m;
     const int64_t base = nmat / ndev, extra = nmat % ndev;      /* the split of blu_b200/shard.py */
     int st = BLU_OK;
+    int caller_dev = 0;
+    cudaGetDevice(&caller_dev);      /* creating the parts selects their devices: hand the caller's back afterwards */
     for (int d = 0; d < ndev && st == BLU_OK; d++) {
         const int64_t lo = d * base + std::min<int64_t>(d, extra), n = base + (d < extra ? 1 : 0);
         blu_b200 *p = nullptr;
         st = create_common(&p, n, m, bnz_cap, devices[d], 0);
         if (st == BLU_OK) { mb->part.push_back(p); mb->first.push_back(lo); mb->count.push_back(n); }
     }
+    cudaSetDevice(caller_dev);
     if (st != BLU_OK) { for (auto *p : mb->part) destroy_common(p); delete mb; return st; }
     *out = mb;
     return BLU_OK;
 }
 extern "C" void blu_multi_destroy(blu_multi_t *mb) {
     if (!mb) return;
+    int caller_dev = 0;
+    cudaGetDevice(&caller_dev);
     for (auto *p : mb->part) destroy_common(p);
+    cudaSetDevice(caller_dev);
     delete mb;
 }
 extern "C" blu_batch_t *blu_multi_part(blu_multi_t *mb, int d, int64_t *first, int64_t *count) {
