@@ -142,7 +142,9 @@ struct Shm {
     int use_tree, tree_levels, tree_off[8], tree_n[8];   /* min-tree over the column keys (markowitz_search of large bumps) */
     u64 mbar; unsigned mbar_phase;   /* completion barrier of the bulk copies (dense_pivot) and its current phase */
     int lput, uput;           /* fill pointers of L and U (= l_begin_p[rank], u_begin[rank]) */
-    int dpcand;               /* stash row of the pivot column's keys (-1: none) */
+    int dpcand;               /* stash row of the pivot column's keys */
+    int cand_done;            /* candidate columns evaluated so far (the warp that finishes last makes the choice) */
+    int dgeneral;             /* the chosen pivot is a general dense step (pivot_any / pivot_small) */
 };
 
 template <int NT> __device__ __forceinline__ void bsync() {
@@ -341,6 +343,8 @@ __device__ __forceinline__ void bulk_copy_g2s(void *sdst, const void *gsrc, unsi
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+/* writes of the generic proxy (ordered before by a barrier) become visible to the bulk-copy engine */
+__device__ __forceinline__ void bulk_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
     asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
@@ -348,6 +352,7 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
 static inline void mbar_init(u64 *, unsigned) {}
 static inline void bulk_copy_g2s(void *sdst, const void *gsrc, unsigned bytes, u64 *) { memcpy(sdst, gsrc, bytes); }
 static inline void mbar_wait(u64 *, unsigned) {}
+static inline void bulk_fence() {}
 #endif
 
 /* record the first failed device-side invariant (kept live like the reference's assert!s) */

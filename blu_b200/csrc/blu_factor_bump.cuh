@@ -1309,17 +1309,11 @@ template <int NT> __device__ void pivot_doubleton_col(Shm &S) {
 /* dense-tail dispatch: RES (values in shared memory) is a launch property, uniform over the block */
 template <int NT> __device__ __forceinline__ void dense_enter_d(Shm &S) { if (S.dv_smem) dense_enter<NT, true>(S); else dense_enter<NT, false>(S); }
 template <int NT> __device__ __forceinline__ void dense_exit_d(Shm &S) { if (S.dv_smem) dense_exit<NT, true>(S); else dense_exit<NT, false>(S); }
-template <int NT> __device__ __forceinline__ void dense_search_d(Shm &S) { if (S.dv_smem) dense_search<NT, true>(S); else dense_search<NT, false>(S); }
-template <int NT> __device__ __forceinline__ void dense_pivot_d(Shm &S, bool small) {
-    if (S.dv_smem) { if (small) dense_pivot<NT, true, true>(S); else dense_pivot<NT, true, false>(S); }
-    else { if (small) dense_pivot<NT, false, true>(S); else dense_pivot<NT, false, false>(S); }
-}
+template <int NT> __device__ __forceinline__ int dense_run_d(Shm &S) { return S.dv_smem ? dense_run<NT, true>(S) : dense_run<NT, false>(S); }
 
 template <int NT> __device__ void phase_bump(Shm &S) {
     Mat &M = S.M;
     const int m = M.m, tid = threadIdx.x;
-    BLU_DYN_SMEM(dyn_);
-    DenseSm dsm; dense_view(dsm, dyn_, S.kd, S.kw);
     if (tid == 0) {
         S.lput = M.l_begin_p[S.rank]; S.uput = M.u_begin[S.rank];
         int ms = M.prm.maxsearch < 1 ? 1 : M.prm.maxsearch, lv = 0;
@@ -1344,21 +1338,42 @@ template <int NT> __device__ void phase_bump(Shm &S) {
             if (S.status != BLU_OK) return;
             t0 = clock64();
         }
-        if (S.dense) dense_search_d<NT>(S); else if (M.prm.search_rows != 0) markowitz_search_rows<NT>(S); else markowitz_search<NT>(S);
-        if (tid == 0) { if (S.dense) S.t_phase[13] += clock64() - t0; else S.t_phase[3] += clock64() - t0; }
-        if (S.status != BLU_OK) return;
-        const int pc = S.pivot_col, pr = S.pivot_row;
-        if (pr < 0) {
-            /* empty column: drop it, no pivot (factorize_bump.rs:23-31) */
-            bsync<NT>();
-            if (tid == 0) { M.ckey[pc] = KEY_INF; if (S.dense) dsm.skeyc[S.dpc] = KEY_INF; S.ndead++; S.rankdef++; }
-            bsync<NT>();
-            if (S.use_tree) ctree_update<NT>(S, (const int *)0, 0, pc);
-            continue;
+        if (S.dense) {
+            /* the dense pivot loop runs until the pivots are found or a step belongs to the sparse code */
+            const int code = dense_run_d<NT>(S);
+            if (S.status != BLU_OK) return;
+            if (code == DRUN_DONE) continue;
+            t0 = clock64();
+            dense_exit_d<NT>(S);
+            if (tid == 0) S.t_phase[13] += clock64() - t0;
+            if (S.status != BLU_OK) return;
+            if (code == DRUN_REMOVE) {      /* pivot.rs:96-106 works on the line file */
+                t0 = clock64();
+                post_remove_cols<NT>(S, S.rank - 1);
+                if (tid == 0) S.t_phase[10] += clock64() - t0;
+                if (S.status != BLU_OK) return;
+                continue;
+            }
+            /* DRUN_SPARSE_PIVOT: singleton row / column, doubleton column: the same pivot on the line file
+             * (the room in L and U was checked by dense_run) */
+        } else {
+            if (M.prm.search_rows != 0) markowitz_search_rows<NT>(S); else markowitz_search<NT>(S);
+            if (tid == 0) S.t_phase[3] += clock64() - t0;
+            if (S.status != BLU_OK) return;
+            if (S.pivot_row < 0) {
+                /* empty column: drop it, no pivot (factorize_bump.rs:23-31) */
+                const int pc0 = S.pivot_col;
+                bsync<NT>();
+                if (tid == 0) { M.ckey[pc0] = KEY_INF; S.ndead++; S.rankdef++; }
+                bsync<NT>();
+                if (S.use_tree) ctree_update<NT>(S, (const int *)0, 0, pc0);
+                continue;
+            }
         }
+        const int pc = S.pivot_col, pr = S.pivot_row;
         const int rank = S.rank;
-        const int nz_col = S.dense ? (int)dsm.cnz[S.dpc] : M.lend[pc] - M.lbeg[pc];
-        const int nz_row = S.dense ? (int)dsm.rnz[S.dpt] : M.lend[m + pr] - M.lbeg[m + pr];
+        const int nz_col = M.lend[pc] - M.lbeg[pc];
+        const int nz_row = M.lend[m + pr] - M.lbeg[m + pr];
         /* room in L and U, pivot.rs:69-81 (S.lput / S.uput mirror l_begin_p[rank] / u_begin[rank]) */
         {
             int room = M.l_mem - S.lput;
@@ -1369,30 +1384,6 @@ template <int NT> __device__ void phase_bump(Shm &S) {
             if (st != BLU_OK) { bsync<NT>(); if (tid == 0) S.status = st; bsync<NT>(); return; }
         }
         t0 = clock64();
-        if (S.dense) {
-            if (nz_row > 1 && nz_col > 2 && S.epoch < 255) {      /* (eight bits of epoch in the keys) */
-                const bool small = nz_col - 1 <= MAXROW_SMALL;
-                dense_pivot_d<NT>(S, small);
-                if (tid == 0) { S.t_phase[12] += clock64() - t0; S.n_kind[small ? 3 : 4]++; }
-                if (S.status != BLU_OK) return;
-                if (S.need_remove) {      /* pivot.rs:96-106 works on the line file */
-                    t0 = clock64();
-                    dense_exit_d<NT>(S);
-                    if (tid == 0) S.t_phase[13] += clock64() - t0;
-                    if (S.status != BLU_OK) return;
-                    t0 = clock64();
-                    post_remove_cols<NT>(S, rank);
-                    if (tid == 0) S.t_phase[10] += clock64() - t0;
-                    if (S.status != BLU_OK) return;
-                }
-                continue;
-            }
-            /* singleton row / column or doubleton column: back to the line file, same pivot */
-            dense_exit_d<NT>(S);
-            if (tid == 0) S.t_phase[13] += clock64() - t0;
-            if (S.status != BLU_OK) return;
-            t0 = clock64();
-        }
         int kind;
         if (nz_row == 1) { pivot_singleton_row<NT>(S); kind = 0; }
         else if (nz_col == 1) { pivot_singleton_col<NT>(S); kind = 1; }

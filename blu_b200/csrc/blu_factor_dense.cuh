@@ -123,6 +123,10 @@ template <int NT, bool RES> __device__ __noinline__ void dense_enter(Shm &S) {
     }
     if (nr > KD || nc > KD) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
     for (size_t q = tid; q < (size_t)nr * KD; q += NT) dv[q] = 0.0;
+    {   /* no entry: key 0xffff/0xffff (dense_step ranks the keys of a row without looking at the bitmaps) */
+        unsigned *k32 = (unsigned *)dkey;
+        for (size_t q = tid; q < (size_t)KD * KD; q += NT) k32[q] = 0xffffffffu;
+    }
     for (int q = tid; q < KD * KW; q += NT) { rbm[q] = 0; cbm[q] = 0; }
     for (int c = tid; c < KD; c += NT) { d.skeyc[c] = KEY_INF; d.cnz[c] = 0; d.rnz[c] = 0; }
     bsync<NT>();
@@ -248,199 +252,108 @@ template <int NT, bool RES> __device__ __noinline__ void dense_exit(Shm &S) {
 }
 
 /* ------------------------------------------------------------------ */
-/* markowitz.rs:34-123 on the dense arrays (search_rows == 0)          */
+/* the dense pivot loop: markowitz.rs:34-123 + pivot_any / pivot_small   */
 /* ------------------------------------------------------------------ */
-template <int NT, bool RES> __device__ __noinline__ void dense_search(Shm &S) {
-    Mat &M = S.M;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr int NW = NT / 32;
-    const int KD = S.kd, KW = S.kw, nr = S.nrs, nc = S.ncs;
-    DENSE_VIEW(RES);
-    int maxsearch = M.prm.maxsearch;
-    if (maxsearch < 1) maxsearch = 1;
-    if (maxsearch > MAXCAND) maxsearch = MAXCAND;
-    /* the first `maxsearch` live columns in ascending (count, stamp) order: one warp, no block barriers */
-    if (wid == 0) {
-        int ncand = 0;
-        u64 prev = 0; int have_prev = 0;
-        while (ncand < maxsearch) {
-            u64 k0 = KEY_INF, k1 = KEY_INF, k2 = KEY_INF;
-            int j0 = -1, j1 = -1, j2 = -1;
-            for (int c = lane; c < nc; c += 32) {
-                const u64 k = d.skeyc[c];
-                if (k >= KEY_PARK || (have_prev && k <= prev)) continue;
-                if (k < k2) {
-                    if (k < k1) {
-                        k2 = k1; j2 = j1;
-                        if (k < k0) { k1 = k0; j1 = j0; k0 = k; j0 = c; }
-                        else { k1 = k; j1 = c; }
-                    } else { k2 = k; j2 = c; }
-                }
-            }
-            int got = 0;
-            for (int r = 0; r < 3 && ncand < maxsearch; r++) {
-                const u64 best = warp_min64(k0);
-                if (best == KEY_INF) break;
-                if (k0 == best) {
-                    S.cand_col[ncand] = j0;
-                    k0 = k1; j0 = j1; k1 = k2; j1 = j2; k2 = KEY_INF; j2 = -1;
-                }
-                prev = best; have_prev = 1;
-                ncand++; got++;
-            }
-            if (got < 3) break;
-        }
-        if (lane == 0) S.ncand = ncand;
-    }
-    bsync<NT>();
-    const int ncand = S.ncand;
-    if (ncand == 0) { if (tid == 0) { BLU_CHECK(S, 0); } bsync<NT>(); return; }
-    if (key_cnt(d.skeyc[S.cand_col[0]]) == 0) {      /* markowitz.rs:73-78 */
-        if (tid == 0) { S.dpc = S.cand_col[0]; S.pivot_col = d.dcol[S.cand_col[0]]; S.pivot_row = -1; }
-        bsync<NT>();
-        return;
-    }
-    const double abstol = M.prm.abstol, reltol = M.prm.reltol;
-    for (int cc = wid; cc < ncand; cc += NW) {
-        const int c = S.cand_col[cc];
-        const i64 nz1 = d.cnz[c];
-        const double cmx = __longlong_as_double((long long)d.scm[c]);
-        const double tol = fmax(abstol, reltol * cmx);
-        const unsigned *cb = cbm + c * KW;
-        u64 best = KEY_INF; int bt = -1;
-        if (cc < DENSE_STASH) {
-            /* all key loads of the column in flight together; the pivot step reuses them */
-            unsigned *stash = d.candk + cc * KD;
-            {   /* kd <= 256: at most eight rows per lane, their key loads issued back to back (one round trip) */
-                unsigned kq[8];
-                #pragma unroll
-                for (int u = 0; u < 8; u++) { const int t = lane + 32 * u; kq[u] = (t < nr && bit_test(cb, t)) ? dkey[(size_t)t * KD + c].c : 0xffffffffu; }
-                #pragma unroll
-                for (int u = 0; u < 8; u++) { const int t = lane + 32 * u; if (t < nr) stash[t] = kq[u]; }
-            }
-            __syncwarp();
-            for (int t = lane; t < nr; t += 32) {
-                const unsigned kq = stash[t];
-                if (kq == 0xffffffffu) continue;
-                const double x = fabs(dv[(size_t)t * KD + c]);
-                if (x == 0.0 || x < tol) continue;
-                const u64 mc = (u64)((nz1 - 1) * (i64)(d.rnz[t] - 1));
-                const u64 key = (mc << 32) | (u64)kq;       /* ties: first in storage order, markowitz.rs:105 */
-                if (key < best) { best = key; bt = t; }
-            }
-        } else {
-            for (int t = lane; t < nr; t += 32) {
-                if (!bit_test(cb, t)) continue;
-                const size_t off = (size_t)t * KD + c;
-                const double x = fabs(dv[off]);
-                if (x == 0.0 || x < tol) continue;
-                const u64 mc = (u64)((nz1 - 1) * (i64)(d.rnz[t] - 1));
-                const u64 key = (mc << 32) | (u64)dkey[off].c;
-                if (key < best) { best = key; bt = t; }
-            }
-        }
-        const u64 wb = warp_min64(best);
-        const unsigned own = __ballot_sync(FULLMASK, best == wb && wb != KEY_INF);
-        int tt = -1;
-        if (own) tt = __shfl_sync(FULLMASK, bt, __ffs((int)own) - 1);
-        if (lane == 0) {
-            S.cand_mc[cc] = wb == KEY_INF ? -1 : (i64)(wb >> 32);
-            S.cand_row[cc] = tt;
-        }
-    }
-    bsync<NT>();
-    if (tid == 0) {
-        i64 mc64 = (i64)M.m * (i64)M.m;
-        int bt = -1, bc = -1, bcc = -1;
-        for (int cc = 0; cc < ncand; cc++)
-            if (S.cand_mc[cc] >= 0 && S.cand_mc[cc] < mc64) { mc64 = S.cand_mc[cc]; bt = S.cand_row[cc]; bc = S.cand_col[cc]; bcc = cc; }
-        BLU_CHECK(S, bc >= 0);
-        if (bc >= 0) { S.dpt = bt; S.dpc = bc; S.pivot_row = d.drow[bt]; S.pivot_col = d.dcol[bc]; S.dpcand = bcc < DENSE_STASH ? bcc : -1; }
-        S.nsearch += ncand;
-    }
-    bsync<NT>();
-}
+/* One elimination step on the dense arrays is five block barriers long:
+ *   A  warp 0 picks the candidate columns (the first `maxsearch` live columns in (count, stamp) order) while the
+ *      finisher warp still writes the previous step's L/U pointers                                   -- barrier 1
+ *   B  one warp per candidate column evaluates it (markowitz.rs:82-123) and leaves the column's storage-order keys
+ *      in shared memory; the warp that finishes last makes the choice, checks the room in L and U
+ *      (pivot.rs:69-81) and starts the bulk copy of the pivot row's keys                             -- barrier 2
+ *   C  one thread per entry of the pivot column and of the pivot row ranks its key by counting: this is the
+ *      storage order, with the pivot moved to the front (pivot.rs:142-154)                           -- barrier 3
+ *   D  one thread per column of the pivot row looks at the entries outside the pivot column (pivot.rs:231-262);
+ *   E  the rank-1 update (pivot.rs:285-304 / 638-662), a warp per 32 column slots                    -- barrier 4
+ *   F  counts, Markowitz keys, the U row and the L column (pivot.rs:306-328, 403-415)                -- barrier 5
+ * Invariant used by C: an entry that is not in the active submatrix carries the key 0xffff/0xffff in dn_key
+ * (dense_enter fills the array with it, a dropped entry and the entries of a pivot column get it in E), so that
+ * the keys of a row can be ranked as 32-bit words (.r in the upper half) without looking at the bitmaps. */
+#define DRUN_DONE 0          /* nothing left to do here: all pivots found, an error, or Reallocate (S.status) */
+#define DRUN_SPARSE_PIVOT 1  /* S.pivot_row/col chosen, but the step belongs to the sparse code (singleton row/column,
+                              * doubleton column, epoch counter exhausted): dense_exit, then pivot */
+#define DRUN_REMOVE 2        /* a step is done and a column has to be emptied (pivot.rs:96-106): dense_exit + post_remove_cols */
 
-/* ------------------------------------------------------------------ */
-/* pivot_any (pivot.rs:114-458) / pivot_small (pivot.rs:460-833)       */
-/* ------------------------------------------------------------------ */
-template <int NT, bool RES, bool SMALL> __device__ __noinline__ void dense_pivot(Shm &S) {
+template <int NT, bool RES, bool SMALL> __device__ __forceinline__ void dense_step(Shm &S, const int rank) {
     Mat &M = S.M;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = NT / 32;
     const int KD = S.kd, KW = S.kw, nr = S.nrs, nc = S.ncs;
     DENSE_VIEW(RES);
-    const int tp = S.dpt, cp = S.dpc, rank = S.rank;
+    const int tp = S.dpt, cp = S.dpc;
     const double droptol = M.prm.droptol, abstol = M.prm.abstol;
     const unsigned *cbp = cbm + cp * KW, *rbp = rbm + tp * KW;
     const int n = d.cnz[cp], k = d.rnz[tp];
     const int cnz1 = n - 1, rnz1 = k - 1;
-
-    i64 tq = clock64();
-    /* the keys of the pivot row are one contiguous segment of kd * 4 bytes in HBM/L2: one thread hands the copy
-     * to the bulk-copy engine (cp.async.bulk + mbarrier) and the block gathers the pivot column meanwhile */
     const unsigned phase = S.mbar_phase;
-    if (tid == 0) bulk_copy_g2s(d.rowk, dkey + (size_t)tp * KD, (unsigned)(KD * sizeof(BluKey2)), &S.mbar);
-    /* 1. the pivot column and the pivot row with their storage-order keys */
-    {
-        const int sc = S.dpcand;
-        for (int t = tid; t < nr; t += NT)
-            if (bit_test(cbp, t)) {
-                const int e = bits_rank(cbp, t);
-                d.tmps[e] = (unsigned short)t;
-                d.keyc[e] = sc >= 0 ? d.candk[sc * KD + t] : dkey[(size_t)t * KD + cp].c;
-            }
-    }
-#ifdef BLU_EMU
-    bsync<NT>();      /* (the emulator's copy ran on thread 0) */
-#endif
-    mbar_wait(&S.mbar, phase);
-    for (int c = tid; c < nc; c += NT)
-        if (bit_test(rbp, c)) { const int e = bits_rank(rbp, c); d.tmpr[e] = (unsigned short)c; d.keyr[e] = d.rowk[c].r; }
-    for (int w = tid; w < KW; w += NT) {
+    const unsigned *rowk32 = (const unsigned *)d.rowk;      /* (r << 16) | c of the pivot row's entries */
+    i64 tq = clock64();
+
+    /* C. storage order of the pivot column and the pivot row = ascending key, pivot first */
+    for (int w = NT - 1 - tid; w < KW; w += NT) {
         d.cmask[w] = cbp[w] & ~(w == (tp >> 5) ? 1u << (tp & 31) : 0u);
         d.rfull[w] = rbp[w];
         d.rmask[w] = rbp[w] & ~(w == (cp >> 5) ? 1u << (cp & 31) : 0u);
     }
-    bsync<NT>();
-    /* 2. storage order = ascending key (rank by counting) */
-    for (int e = tid; e < n; e += NT) {
-        const unsigned my = d.keyc[e];
-        int r = 0;
-        for (int f = 0; f < n; f++) r += d.keyc[f] < my;
-        const int t = d.tmps[e];
-        d.clist[r] = (unsigned short)t;
-        if (t == tp) S.wc = r;
+    if (tid == NT - 1) { S.flag_a = 0; S.flag_b = 0; }
+    {
+        const unsigned *stash = d.candk + S.dpcand * KD;      /* the column's keys, 0xffffffff where there is no entry */
+        const uint4 *s4 = (const uint4 *)stash;
+        const int n4 = (nr + 3) >> 2;
+        for (int t = tid; t < nr; t += NT) {
+            const unsigned my = stash[t];
+            if (my == 0xffffffffu) continue;
+            const unsigned pk = stash[tp];
+            int r = 0, wc = 0;
+            for (int f = 0; f < n4; f++) {
+                const uint4 q = s4[f];
+                r += (q.x < my) + (q.y < my) + (q.z < my) + (q.w < my);
+                wc += (q.x < pk) + (q.y < pk) + (q.z < pk) + (q.w < pk);
+            }
+            const int p = t == tp ? 0 : (r == 0 ? wc : r);
+            d.clist[p] = (unsigned short)t;
+            d.cvalp[p] = dv[(size_t)t * KD + cp];
+        }
     }
-    for (int e = tid; e < k; e += NT) {
-        const unsigned my = d.keyr[e];
-        int r = 0;
-        for (int f = 0; f < k; f++) r += d.keyr[f] < my;
-        const int c = d.tmpr[e];
-        d.rlist[r] = (unsigned short)c;
-        if (c == cp) S.wr = r;
-    }
-    bsync<NT>();
-    if (tid == 0) {
-        /* pivot to the front of its column and row, pivot.rs:142-154 */
-        unsigned short x = d.clist[0]; d.clist[0] = d.clist[S.wc]; d.clist[S.wc] = x;
-        x = d.rlist[0]; d.rlist[0] = d.rlist[S.wr]; d.rlist[S.wr] = x;
-        S.flag_a = 0; S.flag_b = 0;
-    }
-    bsync<NT>();
-    for (int p = tid; p < n; p += NT) d.cvalp[p] = dv[(size_t)d.clist[p] * KD + cp];
-    for (int kk = tid; kk < k; kk += NT) {
-        d.posr[d.rlist[kk]] = (unsigned short)kk;
-        if (SMALL) d.sdrop[kk] = 0;      /* (keyc / keyr are free again: the lists are ranked) */
+    mbar_wait(&S.mbar, phase);
+    {
+        const uint4 *s4 = (const uint4 *)rowk32;
+        const int n4 = (nc + 3) >> 2;
+        for (int it = tid; it < KD + nc; it += NT) {
+            if (it < KD) continue;      /* (the threads that ranked the column are busy) */
+            const int c = it - KD;
+            const unsigned my = rowk32[c];
+            if (!bit_test(rbp, c)) {
+#ifdef BLU_EMU
+                BLU_CHECK(S, (my >> 16) == 0xffffu);
+#endif
+                continue;
+            }
+#ifdef BLU_EMU
+            BLU_CHECK(S, (my >> 16) != 0xffffu);
+#endif
+            const unsigned pk = rowk32[cp];
+            int r = 0, wr = 0;
+            for (int f = 0; f < n4; f++) {
+                const uint4 q = s4[f];
+                r += (q.x < my) + (q.y < my) + (q.z < my) + (q.w < my);
+                wr += (q.x < pk) + (q.y < pk) + (q.z < pk) + (q.w < pk);
+            }
+            const int p = c == cp ? 0 : (r == 0 ? wr : r);
+            d.rlist[p] = (unsigned short)c;
+            d.posr[c] = (unsigned short)p;
+            if (c != cp) d.scm[c] = 0;
+            if (SMALL) d.sdrop[p] = 0;
+        }
     }
     bsync<NT>();
     const double pivot = d.cvalp[0];
     const int ubase = S.uput, lbase = S.lput;
     const i64 cbase = S.cstamp, rbase = S.rstamp;
     const unsigned ekey = S.epoch << 8;
+    if (tid == 0) { const i64 now = clock64(); S.t_phase[14] += now - tq; tq = now; }
 
-    /* 3. per column of the pivot row: the entries outside the pivot column (pivot.rs:231-262).  Their
-     * maximum seeds colmax; the first of them in storage order takes the place of the pivot-row entry. */
+    /* D. per column of the pivot row: the entries outside the pivot column (pivot.rs:231-262).  Their maximum
+     * seeds colmax; the first of them in storage order takes the place of the pivot-row entry. */
     for (int kk = 1 + tid; kk <= rnz1; kk += NT) {
         const int c = d.rlist[kk];
         const unsigned *cb = cbm + c * KW;
@@ -449,9 +362,9 @@ template <int NT, bool RES, bool SMALL> __device__ __noinline__ void dense_pivot
              * tail is full) has nothing to exchange and no maximum to seed: no key is needed */
             int others = 0;
             for (int w = 0; w < KW; w++) others += __popc(cb[w] & ~d.cmask[w]);
-            if (others == 1) { d.scm[c] = 0; continue; }
+            if (others == 1) continue;
         }
-        const unsigned short kpr = dkey[(size_t)tp * KD + c].c;
+        const unsigned short kpr = (unsigned short)(rowk32[c] & 0xffffu);
         /* the keys live in HBM/L2: fetch them eight at a time so that one round trip serves eight entries */
         int w = 0; unsigned tb = cb[0] & ~d.cmask[0];
         for (;;) {
@@ -474,38 +387,39 @@ template <int NT, bool RES, bool SMALL> __device__ __noinline__ void dense_pivot
         }
         if (tmin < 0) { BLU_CHECK(S, 0); }
         else if (tmin != tp) dkey[(size_t)tmin * KD + c].c = kpr;
-        d.scm[c] = (u64)__double_as_longlong(cmx);
+        if (cmx > 0.0) atomicMax((unsigned long long *)&d.scm[c], (unsigned long long)__double_as_longlong(cmx));
     }
-    bsync<NT>();
-    if (tid == 0) { const i64 now = clock64(); S.t_phase[14] += now - tq; tq = now; }
 
-    /* 4. the rank-1 update, pivot.rs:285-304 / 638-662: a warp owns 32 column slots (and every RS-th row
-     * of the pivot column when there are more warps than column words) */
+    /* E. the rank-1 update: a warp owns 32 column slots and every RS-th block of rows of the pivot column */
     {
         const int RS = NW >= KW ? NW / KW : 1;
+        const int chunk = (cnz1 + RS - 1) / RS;
+        BluKey2 gone; gone.c = 0xffffu; gone.r = 0xffffu;
         for (int u0 = wid; u0 < KW * RS; u0 += NW) {
             const int cw = u0 % KW, rs = u0 / KW;
             const unsigned rf = d.rfull[cw], rm = d.rmask[cw];
             if (rf == 0) continue;
             const int c = cw * 32 + lane;
             const bool inR = (rm >> lane) & 1u;
+            const bool isP = c == cp;
             double a = 0.0; unsigned rkv = 0; int kk = 0;
             if (inR) { kk = d.posr[c]; a = __ddiv_rn(dv[(size_t)tp * KD + c], pivot); rkv = ekey + (unsigned)kk; }
             double cmx = 0.0;
             u64 mydrop = 0;
-            for (int p0 = 1 + rs; p0 <= cnz1; p0 += 4 * RS) {
+            const int pend = (rs + 1) * chunk < cnz1 ? (rs + 1) * chunk : cnz1;
+            for (int p0 = 1 + rs * chunk; p0 <= pend; p0 += 4) {
                 int tt[4]; double xv[4], cv[4];
                 #pragma unroll
                 for (int u = 0; u < 4; u++) {      /* the four loads are in flight together */
-                    const int p = p0 + u * RS;
-                    tt[u] = p <= cnz1 ? (int)d.clist[p] : -1;
-                    cv[u] = p <= cnz1 ? d.cvalp[p] : 0.0;
+                    const int p = p0 + u;
+                    tt[u] = p <= pend ? (int)d.clist[p] : -1;
+                    cv[u] = p <= pend ? d.cvalp[p] : 0.0;
                     xv[u] = (inR && tt[u] >= 0) ? dv[(size_t)tt[u] * KD + c] : 0.0;
                 }
                 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (tt[u] < 0) continue;       /* uniform: p does not depend on the lane */
-                    const int p = p0 + u * RS;
+                    const int p = p0 + u;
                     const size_t off = (size_t)tt[u] * KD + c;
                     int keep = 0;
                     if (inR) {
@@ -519,9 +433,10 @@ template <int NT, bool RES, bool SMALL> __device__ __noinline__ void dense_pivot
                             if (ax > cmx) cmx = ax;
                         } else {
                             dv[off] = 0.0;
+                            dkey[off] = gone;
                             mydrop |= 1ull << (p - 1);
                         }
-                    }
+                    } else if (isP) dkey[off] = gone;      /* the pivot column leaves the active submatrix */
                     if (SMALL) {
                         const unsigned km = __ballot_sync(FULLMASK, keep);
                         if (lane == 0) { unsigned *wp = rbm + tt[u] * KW + cw; *wp = (*wp & ~rf) | km; }
@@ -543,7 +458,7 @@ template <int NT, bool RES, bool SMALL> __device__ __noinline__ void dense_pivot
     bsync<NT>();
     if (tid == 0) { const i64 now = clock64(); S.t_phase[15] += now - tq; tq = now; }
 
-    /* 5. counts, Markowitz keys, U row (pivot.rs:306-328), L column (:403-415) */
+    /* F. counts, Markowitz keys, U row (pivot.rs:306-328), L column (:403-415); the pivot row and column leave */
     double acc = 0.0;
     for (int kk = 1 + tid; kk <= rnz1; kk += NT) {
         const int c = d.rlist[kk], j = d.dcol[c];
@@ -590,11 +505,12 @@ template <int NT, bool RES, bool SMALL> __device__ __noinline__ void dense_pivot
     }
     acc = warp_sumd(acc);      /* (sums of small integers: exact in any order) */
     if (lane == 0 && acc != 0.0) atomicAdd(&S.elim_bytes, acc);
+    for (int w = NT - 1 - tid; w < KW; w += NT) { cbm[cp * KW + w] = 0; rbm[tp * KW + w] = 0; }
+    if (tid == NT - 1) { d.skeyc[cp] = KEY_INF; d.cnz[cp] = 0; d.rnz[tp] = 0; }
     bsync<NT>();
 
-    /* 6. the pivot row and column leave the active submatrix */
-    for (int w = tid; w < KW; w += NT) { cbm[cp * KW + w] = 0; rbm[tp * KW + w] = 0; }
-    if (wid == 0) {
+    /* the finisher warp closes the step while warp 0 already looks for the next candidates */
+    if (wid == (NW > 1 ? 1 : 0)) {
         int ln = cnz1, un = rnz1;
         if (S.flag_b) ln = warp_squeeze(M.l_idx, M.l_val, lbase, cnz1);
         if (S.flag_a) un = warp_squeeze(M.u_idx, M.u_val, ubase, rnz1);
@@ -604,13 +520,179 @@ template <int NT, bool RES, bool SMALL> __device__ __noinline__ void dense_pivot
             S.cstamp = cbase + rnz1 + 1;
             S.rstamp = rbase + cnz1 + 1;
             S.epoch++;
-            d.skeyc[cp] = KEY_INF; d.cnz[cp] = 0; d.rnz[tp] = 0;
-            S.n_kind[5]++;
-            S.n_kind[7] += clock64() - tq;
+            S.n_kind[5]++; S.n_kind[SMALL ? 3 : 4]++;
             S.mbar_phase = phase ^ 1u;
         }
     }
-    bsync<NT>();
+    if (tid == 0) S.n_kind[7] += clock64() - tq;
+}
+
+template <int NT, bool RES> __device__ __noinline__ int dense_run(Shm &S) {
+    Mat &M = S.M;
+    const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int KD = S.kd, KW = S.kw, nr = S.nrs, nc = S.ncs;
+    DENSE_VIEW(RES);
+    int maxsearch = M.prm.maxsearch;
+    if (maxsearch < 1) maxsearch = 1;
+    if (maxsearch > MAXCAND) maxsearch = MAXCAND;
+    const double abstol = M.prm.abstol, reltol = M.prm.reltol;
+    int rank = S.rank, rankdef = S.rankdef;      /* (the finisher warp updates S.rank behind the barrier) */
+    int code = DRUN_DONE;
+    for (;;) {
+        if (rank + rankdef >= m) break;
+        i64 t0 = clock64();
+        /* A. the first `maxsearch` live columns in ascending (count, stamp) order: one warp, no block barriers */
+        if (wid == 0) {
+            int ncand = 0;
+            u64 prev = 0; int have_prev = 0;
+            while (ncand < maxsearch) {
+                u64 k0 = KEY_INF, k1 = KEY_INF, k2 = KEY_INF;
+                int j0 = -1, j1 = -1, j2 = -1;
+                for (int c = lane; c < nc; c += 32) {
+                    const u64 kq = d.skeyc[c];
+                    if (kq >= KEY_PARK || (have_prev && kq <= prev)) continue;
+                    if (kq < k2) {
+                        if (kq < k1) {
+                            k2 = k1; j2 = j1;
+                            if (kq < k0) { k1 = k0; j1 = j0; k0 = kq; j0 = c; }
+                            else { k1 = kq; j1 = c; }
+                        } else { k2 = kq; j2 = c; }
+                    }
+                }
+                int got = 0;
+                for (int r = 0; r < 3 && ncand < maxsearch; r++) {
+                    const u64 best = warp_min64(k0);
+                    if (best == KEY_INF) break;
+                    if (k0 == best) {
+                        S.cand_col[ncand] = j0;
+                        k0 = k1; j0 = j1; k1 = k2; j1 = j2; k2 = KEY_INF; j2 = -1;
+                    }
+                    prev = best; have_prev = 1;
+                    ncand++; got++;
+                }
+                if (got < 3) break;
+            }
+            if (lane == 0) { S.ncand = ncand; S.cand_done = 0; }
+        }
+        bsync<NT>();
+        const int ncand = S.ncand;
+        if (ncand == 0) { if (tid == 0) { BLU_CHECK(S, 0); } break; }
+        if (key_cnt(d.skeyc[S.cand_col[0]]) == 0) {
+            /* markowitz.rs:73-78 + factorize_bump.rs:23-31: an empty column is dropped without a pivot */
+            bsync<NT>();
+            if (tid == 0) {
+                const int c0 = S.cand_col[0], pc = d.dcol[c0];
+                S.dpc = c0; S.pivot_col = pc; S.pivot_row = -1;
+                M.ckey[pc] = KEY_INF; d.skeyc[c0] = KEY_INF; S.ndead++; S.rankdef++;
+                S.t_phase[13] += clock64() - t0;
+            }
+            rankdef++;
+            bsync<NT>();
+            continue;
+        }
+        /* B. one warp per candidate column */
+        for (int cc = wid; cc < ncand; cc += NW) {
+            const int c = S.cand_col[cc];
+            const i64 nz1 = d.cnz[c];
+            const double cmx = __longlong_as_double((long long)d.scm[c]);
+            const double tol = fmax(abstol, reltol * cmx);
+            const unsigned *cb = cbm + c * KW;
+            u64 best = KEY_INF; int bt = -1;
+            if (cc < DENSE_STASH) {
+                /* all key loads of the column in flight together; the pivot step reuses them */
+                unsigned *stash = d.candk + cc * KD;
+                {   /* kd <= 256: at most eight rows per lane, their key loads issued back to back (one round trip) */
+                    unsigned kq[8];
+                    #pragma unroll
+                    for (int u = 0; u < 8; u++) { const int t = lane + 32 * u; kq[u] = (t < nr && bit_test(cb, t)) ? dkey[(size_t)t * KD + c].c : 0xffffffffu; }
+                    #pragma unroll
+                    for (int u = 0; u < 8; u++) { const int t = lane + 32 * u; if (t < KD) stash[t] = kq[u]; }
+                }
+                __syncwarp();
+                for (int t = lane; t < nr; t += 32) {
+                    const unsigned kq = stash[t];
+                    if (kq == 0xffffffffu) continue;
+                    const double x = fabs(dv[(size_t)t * KD + c]);
+                    if (x == 0.0 || x < tol) continue;
+                    const u64 mc = (u64)((nz1 - 1) * (i64)(d.rnz[t] - 1));
+                    const u64 key = (mc << 32) | (u64)kq;       /* ties: first in storage order, markowitz.rs:105 */
+                    if (key < best) { best = key; bt = t; }
+                }
+            } else {
+                for (int t = lane; t < nr; t += 32) {
+                    if (!bit_test(cb, t)) continue;
+                    const size_t off = (size_t)t * KD + c;
+                    const double x = fabs(dv[off]);
+                    if (x == 0.0 || x < tol) continue;
+                    const u64 mc = (u64)((nz1 - 1) * (i64)(d.rnz[t] - 1));
+                    const u64 key = (mc << 32) | (u64)dkey[off].c;
+                    if (key < best) { best = key; bt = t; }
+                }
+            }
+            const u64 wb = warp_min64(best);
+            const unsigned own = __ballot_sync(FULLMASK, best == wb && wb != KEY_INF);
+            int tt = -1;
+            if (own) tt = __shfl_sync(FULLMASK, bt, __ffs((int)own) - 1);
+            int last = 0;
+            if (lane == 0) {
+                S.cand_mc[cc] = wb == KEY_INF ? -1 : (i64)(wb >> 32);
+                S.cand_row[cc] = tt;
+                __threadfence_block();
+                last = atomicAdd(&S.cand_done, 1) == ncand - 1;
+            }
+            last = __shfl_sync(FULLMASK, last, 0);
+            if (!last) continue;
+            /* every candidate is evaluated: the choice (markowitz.rs:96-112, the first of minimum cost) */
+            __threadfence_block();
+            i64 mc64 = (i64)M.m * (i64)M.m;
+            int pt = -1, pc = -1, pcc = -1;
+            for (int q = 0; q < ncand; q++) {
+                const i64 v = S.cand_mc[q];
+                if (v >= 0 && v < mc64) { mc64 = v; pt = S.cand_row[q]; pc = S.cand_col[q]; pcc = q; }
+            }
+            if (pc < 0) { if (lane == 0) { BLU_CHECK(S, 0); } continue; }
+            if (pcc >= DENSE_STASH) {      /* (maxsearch > DENSE_STASH) the chosen column's keys were not kept: row 0 is free now */
+                const unsigned *cb2 = cbm + pc * KW;
+                for (int t = lane; t < KD; t += 32) d.candk[t] = (t < nr && bit_test(cb2, t)) ? dkey[(size_t)t * KD + pc].c : 0xffffffffu;
+                pcc = 0;
+            }
+            if (lane == 0) {
+                S.dpt = pt; S.dpc = pc; S.pivot_row = d.drow[pt]; S.pivot_col = d.dcol[pc]; S.dpcand = pcc;
+                S.nsearch += ncand;
+                const int nz_col = d.cnz[pc], nz_row = d.rnz[pt];
+                /* room in L and U, pivot.rs:69-81 */
+                int st = BLU_OK;
+                int room = M.l_mem - S.lput;
+                if (room < nz_col) { M.info->addmem_l = nz_col - room; st = BLU_REALLOCATE; }
+                room = M.u_mem - S.uput;
+                if (room < nz_row - 1) { M.info->addmem_u = nz_row - 1 - room; st = BLU_REALLOCATE; }
+                int general = 0;
+                if (st != BLU_OK) S.status = st;
+                else if (nz_row > 1 && nz_col > 2 && S.epoch < 255) {      /* (eight bits of epoch in the keys) */
+                    general = 1;
+                    /* the keys of the pivot row are one contiguous segment of kd * 4 bytes in HBM/L2: handed to the
+                     * bulk-copy engine (cp.async.bulk + mbarrier), it arrives while the block ranks the pivot column */
+                    bulk_fence();
+                    bulk_copy_g2s(d.rowk, dkey + (size_t)pt * KD, (unsigned)(KD * sizeof(BluKey2)), &S.mbar);
+                }
+                S.dgeneral = general;
+            }
+        }
+        bsync<NT>();
+        if (tid == 0) S.t_phase[13] += clock64() - t0;
+        if (S.status != BLU_OK) break;
+        if (!S.dgeneral) { code = DRUN_SPARSE_PIVOT; break; }
+        t0 = clock64();
+        if ((int)d.cnz[S.dpc] - 1 <= MAXROW_SMALL) dense_step<NT, RES, true>(S, rank);
+        else dense_step<NT, RES, false>(S, rank);
+        rank++;
+        if (tid == 0) S.t_phase[12] += clock64() - t0;
+        if (S.status != BLU_OK) break;
+        if (S.need_remove) { code = DRUN_REMOVE; break; }
+    }
+    bsync<NT>();      /* (the finisher warp is through) */
+    return code;
 }
 
 #endif

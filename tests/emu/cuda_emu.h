@@ -38,6 +38,7 @@ extern emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define warpSize 32
+struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
 
 typedef int cudaError_t;
 typedef void *cudaStream_t;
