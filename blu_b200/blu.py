@@ -33,7 +33,7 @@ class Status:
 # selectors (include/blu_b200.h)
 P = dict(droptol=0, abstol=1, reltol=2, nzbias=3, maxsearch=4, pad=5, stretch=6, compress_thres=7,
          sparse_thres=8, search_rows=9, realloc_factor=10, l_mem=11, u_mem=12, w_mem=13,
-         threads_per_basis=14, norms=15, dense_k=16, tail_threads=17, split_min=18, tree_min=19)
+         threads_per_basis=14, norms=15, dense_k=16, tail_threads=17, split_min=18, tree_min=19, dense_k_big=20)
 _INFO_NAMES = ["m", "rank", "bump_size", "bump_nz", "matrix_nz", "l_nz", "u_nz", "r_nz", "nsearch_pivot",
                "nexpand", "ngarbage", "factor_flops", "min_pivot", "max_pivot", "max_eta", "nupdate",
                "nforrest", "nfactorize", "nupdate_total", "nforrest_total", "nsymperm_total", "l_flops",

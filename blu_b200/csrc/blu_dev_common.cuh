@@ -49,7 +49,7 @@ struct Mat {
     int *rowmark, *colmark, *marked, *iwork1, *pstack, *acols, *tmpi;
     u64 *cancelled;
     double *work0, *work1, *gwork;
-    double *dn_val; BluKey2 *dn_key; unsigned *dn_rbits, *dn_cbits;
+    double *dn_val; BluKey2 *dn_key, *dn_key2; unsigned *dn_rbits, *dn_cbits;
     BluInfo *info;
 };
 
@@ -90,8 +90,9 @@ __device__ __forceinline__ void mat_view(Mat &M, const BluDev &D, int s) {
     M.work0 = D.work0 + S * m; M.work1 = D.work1 + S * m;
     M.gwork = D.gwork + S * (size_t)D.gwork_warps * m;
     {
-        const size_t kd = (size_t)D.dense_k, kw = kd / 32;
+        const size_t k2 = (size_t)D.dense_k, kd = D.dense_kbig > D.dense_k ? (size_t)D.dense_kbig : k2, kw = kd / 32;
         M.dn_val = D.dn_val + S * kd * kd; M.dn_key = D.dn_key + S * kd * kd;
+        M.dn_key2 = D.dn_key2 + (D.dense_kbig > D.dense_k ? S * k2 * k2 : 0);
         M.dn_rbits = D.dn_rbits + S * kd * kw; M.dn_cbits = D.dn_cbits + S * kd * kw;
     }
     M.info = D.info + s;
@@ -138,7 +139,10 @@ struct Shm {
     unsigned epoch;           /* number of the next dense step (storage-order keys, BluKey2) */
     int dense_entries, dense_block_rank;
     int mode, suspend;        /* BLU_MODE_*; 1 = park for the tail kernel, 2 = park for the build kernel */
-    int dv_smem;              /* the launch has room for the dense values and bitmaps in shared memory */
+    int dv_smem;              /* where the dense arrays of the current stage live: 0 = HBM, 1 = values and bitmaps in shared memory,
+                               * 2 = bitmaps in shared memory, values in HBM/L2 (the first stage of a two-stage tail) */
+    int launch_res;           /* the launch has room for the dense values and bitmaps of order kd_small in shared memory */
+    int kd_small, kd_big;     /* orders of the (last) stage and of the HBM/L2 stage in front of it (0: none) */
     int use_tree, tree_levels, tree_off[8], tree_n[8];   /* min-tree over the column keys (markowitz_search of large bumps) */
     u64 mbar; unsigned mbar_phase;   /* completion barrier of the bulk copies (dense_pivot) and its current phase */
     int lput, uput;           /* fill pointers of L and U (= l_begin_p[rank], u_begin[rank]) */

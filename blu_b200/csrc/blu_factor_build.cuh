@@ -318,6 +318,7 @@ template <int NT> __global__ void __launch_bounds__(NT, FACT_MINB(NT)) k_factori
             S.need_remove = 0;
             S.wc = -1; S.wr = -1;
             S.dyn = dyn; S.dense = 0; S.kd = dense_kd; S.kw = dense_kd / 32; S.dv_smem = dense_smem;
+            S.launch_res = dense_smem; S.kd_small = dense_kd; S.kd_big = D.dense_kbig_eff > dense_kd && (mode == BLU_MODE_HEAD || NT >= D.dense_kbig_eff) ? D.dense_kbig_eff : 0;
             S.mode = mode; S.suspend = 0;
             if (fresh) {
                 /* LU::reset, lu.rs:329-396 (cumulative counters survive) */

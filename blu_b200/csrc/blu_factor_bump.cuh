@@ -1307,9 +1307,15 @@ template <int NT> __device__ void pivot_doubleton_col(Shm &S) {
 #define DENSE_MIN_ROWS 4      /* the last pivots are singletons / doubletons: not worth a conversion */
 #define DENSE_MAX_ENTRIES 8   /* conversions per factorization (each costs O(kd^2)) */
 /* dense-tail dispatch: RES (values in shared memory) is a launch property, uniform over the block */
-template <int NT> __device__ __forceinline__ void dense_enter_d(Shm &S) { if (S.dv_smem) dense_enter<NT, true>(S); else dense_enter<NT, false>(S); }
-template <int NT> __device__ __forceinline__ void dense_exit_d(Shm &S) { if (S.dv_smem) dense_exit<NT, true>(S); else dense_exit<NT, false>(S); }
-template <int NT> __device__ __forceinline__ int dense_run_d(Shm &S) { return S.dv_smem ? dense_run<NT, true>(S) : dense_run<NT, false>(S); }
+template <int NT> __device__ __forceinline__ void dense_enter_d(Shm &S) {
+    if (S.dv_smem == 1) dense_enter<NT, 1>(S); else if (S.dv_smem == 2) dense_enter<NT, 2>(S); else dense_enter<NT, 0>(S);
+}
+template <int NT> __device__ __forceinline__ void dense_exit_d(Shm &S) {
+    if (S.dv_smem == 1) dense_exit<NT, 1>(S); else if (S.dv_smem == 2) dense_exit<NT, 2>(S); else dense_exit<NT, 0>(S);
+}
+template <int NT> __device__ __forceinline__ int dense_run_d(Shm &S) {
+    return S.dv_smem == 1 ? dense_run<NT, 1>(S) : S.dv_smem == 2 ? dense_run<NT, 2>(S) : dense_run<NT, 0>(S);
+}
 
 template <int NT> __device__ void phase_bump(Shm &S) {
     Mat &M = S.M;
@@ -1325,7 +1331,8 @@ template <int NT> __device__ void phase_bump(Shm &S) {
     if (S.use_tree) ctree_build<NT>(S);
     while (S.rank + S.rankdef < m) {
         i64 t0 = clock64();
-        if (!S.dense && S.kd > 0 && m - S.rank <= S.kd && m - S.rank >= DENSE_MIN_ROWS &&
+        const int kd_first = S.kd_big > S.kd_small ? S.kd_big : S.kd_small;
+        if (!S.dense && kd_first > 0 && m - S.rank <= kd_first && m - S.rank >= DENSE_MIN_ROWS &&
             S.rank >= S.dense_block_rank && S.dense_entries < DENSE_MAX_ENTRIES && M.prm.search_rows == 0) {
             if (S.mode == BLU_MODE_HEAD) {      /* the tail kernel takes over from here */
                 bsync<NT>();
@@ -1333,6 +1340,15 @@ template <int NT> __device__ void phase_bump(Shm &S) {
                 bsync<NT>();
                 return;
             }
+            /* a two-stage tail starts in HBM/L2 at order kd_big and moves to shared memory at kd_small */
+            bsync<NT>();
+            if (tid == 0) {
+                if (S.kd_big > S.kd_small && m - S.rank > S.kd_small) { S.kd = S.kd_big; S.dv_smem = 2; }
+                else { S.kd = S.kd_small; S.dv_smem = S.launch_res; }
+                S.kw = S.kd / 32;
+                M.dn_key = S.kd == S.kd_small && S.kd_big > S.kd_small ? M.dn_key2 : M.dn_key;
+            }
+            bsync<NT>();
             dense_enter_d<NT>(S);
             if (tid == 0) { S.t_phase[13] += clock64() - t0; S.use_tree = 0; }      /* at most dense_k columns are left: the scan is cheap */
             if (S.status != BLU_OK) return;
@@ -1343,6 +1359,13 @@ template <int NT> __device__ void phase_bump(Shm &S) {
             const int code = dense_run_d<NT>(S);
             if (S.status != BLU_OK) return;
             if (code == DRUN_DONE) continue;
+            if (code == DRUN_RESTAGE) {
+                t0 = clock64();
+                dense_restage<NT>(S);
+                if (tid == 0) S.t_phase[13] += clock64() - t0;
+                if (S.status != BLU_OK) return;
+                continue;
+            }
             t0 = clock64();
             dense_exit_d<NT>(S);
             if (tid == 0) S.t_phase[13] += clock64() - t0;

@@ -9,9 +9,12 @@
  *                      .r = storage-order key inside its row (the row file); only order matters
  *   rb, cb             presence bitmaps by row and by column
  *
- * RES = true: dv, rb and cb live in shared memory (one CTA per SM, kd <= 160 on B200: 200 KB of values);
+ * RES = 1: dv, rb and cb live in shared memory (one CTA per SM, kd <= 160 on B200: 200 KB of values);
  * the keys stay in HBM/L2 and are written fire-and-forget by the update and read O(kd) times per step.
- * RES = false: dv, rb, cb are the HBM arrays dn_val, dn_rbits, dn_cbits (any kd).
+ * RES = 0: dv, rb, cb are the HBM arrays dn_val, dn_rbits, dn_cbits (any kd).
+ * RES = 2: the bitmaps in shared memory, the values in HBM/L2: the first stage of a two-stage tail, which starts at
+ * order kd_big (256) in a launch with one CTA per SM and moves the active submatrix into shared memory
+ * (dense_restage) when it has shrunk to kd_small.
  *
  * What the line file encodes by position is carried by the keys:
  *   - markowitz.rs:96-112 takes, per candidate column, the first entry in storage order among those of
@@ -81,7 +84,7 @@ __device__ __forceinline__ void dense_view(DenseSm &d, unsigned char *dyn, int K
 }
 #define DENSE_VIEW(RES) \
     BLU_DYN_SMEM(dyn_); DenseSm d; dense_view(d, dyn_, S.kd, S.kw); \
-    double *const dv = RES ? d.dv_s : S.M.dn_val; \
+    double *const dv = RES == 1 ? d.dv_s : S.M.dn_val; \
     unsigned *const rbm = RES ? d.rb_s : S.M.dn_rbits; \
     unsigned *const cbm = RES ? d.cb_s : S.M.dn_cbits; \
     BluKey2 *const dkey = S.M.dn_key
@@ -98,7 +101,7 @@ __device__ __forceinline__ int bits_rank(const unsigned *row, int t) {
 /* ------------------------------------------------------------------ */
 /* line file -> dense arrays                                           */
 /* ------------------------------------------------------------------ */
-template <int NT, bool RES> __device__ __noinline__ void dense_enter(Shm &S) {
+template <int NT, int RES> __device__ __noinline__ void dense_enter(Shm &S) {
     Mat &M = S.M;
     const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = NT / 32;
@@ -164,7 +167,7 @@ template <int NT, bool RES> __device__ __noinline__ void dense_enter(Shm &S) {
 /* ------------------------------------------------------------------ */
 /* dense arrays -> line file (key order == storage order)              */
 /* ------------------------------------------------------------------ */
-template <int NT, bool RES> __device__ __noinline__ void dense_exit(Shm &S) {
+template <int NT, int RES> __device__ __noinline__ void dense_exit(Shm &S) {
     Mat &M = S.M;
     const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = NT / 32;
@@ -272,8 +275,9 @@ template <int NT, bool RES> __device__ __noinline__ void dense_exit(Shm &S) {
 #define DRUN_SPARSE_PIVOT 1  /* S.pivot_row/col chosen, but the step belongs to the sparse code (singleton row/column,
                               * doubleton column, epoch counter exhausted): dense_exit, then pivot */
 #define DRUN_REMOVE 2        /* a step is done and a column has to be emptied (pivot.rs:96-106): dense_exit + post_remove_cols */
+#define DRUN_RESTAGE 3       /* the first stage has shrunk to kd_small rows: dense_restage, then on in shared memory */
 
-template <int NT, bool RES, bool SMALL> __device__ __forceinline__ void dense_step(Shm &S, const int rank) {
+template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_step(Shm &S, const int rank) {
     Mat &M = S.M;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = NT / 32;
@@ -407,17 +411,18 @@ template <int NT, bool RES, bool SMALL> __device__ __forceinline__ void dense_st
             double cmx = 0.0;
             u64 mydrop = 0;
             const int pend = (rs + 1) * chunk < cnz1 ? (rs + 1) * chunk : cnz1;
-            for (int p0 = 1 + rs * chunk; p0 <= pend; p0 += 4) {
-                int tt[4]; double xv[4], cv[4];
+            constexpr int UR = RES == 1 ? 4 : 8;      /* (values in HBM/L2: more loads in flight) */
+            for (int p0 = 1 + rs * chunk; p0 <= pend; p0 += UR) {
+                int tt[UR]; double xv[UR], cv[UR];
                 #pragma unroll
-                for (int u = 0; u < 4; u++) {      /* the four loads are in flight together */
+                for (int u = 0; u < UR; u++) {      /* the loads are in flight together */
                     const int p = p0 + u;
                     tt[u] = p <= pend ? (int)d.clist[p] : -1;
                     cv[u] = p <= pend ? d.cvalp[p] : 0.0;
                     xv[u] = (inR && tt[u] >= 0) ? dv[(size_t)tt[u] * KD + c] : 0.0;
                 }
                 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < UR; u++) {
                     if (tt[u] < 0) continue;       /* uniform: p does not depend on the lane */
                     const int p = p0 + u;
                     const size_t off = (size_t)tt[u] * KD + c;
@@ -527,7 +532,7 @@ template <int NT, bool RES, bool SMALL> __device__ __forceinline__ void dense_st
     if (tid == 0) S.n_kind[7] += clock64() - tq;
 }
 
-template <int NT, bool RES> __device__ __noinline__ int dense_run(Shm &S) {
+template <int NT, int RES> __device__ __noinline__ int dense_run(Shm &S) {
     Mat &M = S.M;
     const int m = M.m, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = NT / 32;
@@ -541,6 +546,7 @@ template <int NT, bool RES> __device__ __noinline__ int dense_run(Shm &S) {
     int code = DRUN_DONE;
     for (;;) {
         if (rank + rankdef >= m) break;
+        if (RES == 2 && m - rank <= S.kd_small) { code = DRUN_RESTAGE; break; }
         i64 t0 = clock64();
         /* A. the first `maxsearch` live columns in ascending (count, stamp) order: one warp, no block barriers */
         if (wid == 0) {
@@ -693,6 +699,91 @@ template <int NT, bool RES> __device__ __noinline__ int dense_run(Shm &S) {
     }
     bsync<NT>();      /* (the finisher warp is through) */
     return code;
+}
+
+/* ------------------------------------------------------------------ */
+/* first stage (order kd_big, values in HBM/L2) -> second stage (order kd_small, everything in shared memory)  */
+/* ------------------------------------------------------------------ */
+/* The live rows and columns keep their relative slot order; values, bitmaps and per-slot arrays are compacted into
+ * the layout of order kd_small, the keys into dn_key2 with their values unchanged (the epoch counter goes on: the
+ * two stages together take at most kd_big - DENSE_MIN_ROWS < 255 steps).  Needs a thread per old slot. */
+template <int NT> __device__ __noinline__ void dense_restage(Shm &S) {
+    Mat &M = S.M;
+    const int tid = threadIdx.x;
+    const int KDb = S.kd, KWb = S.kw, KDs = S.kd_small, KWs = KDs / 32;
+    const int nrb = S.nrs, ncb = S.ncs;
+    BLU_DYN_SMEM(dyn_);
+    DenseSm o, n;
+    dense_view(o, dyn_, KDb, KWb);      /* the two layouts overlap: everything of the old one goes through registers */
+    dense_view(n, dyn_, KDs, KWs);
+    /* a. per-slot state of the old layout */
+    const int t = tid;
+    const int ra = t < nrb && M.rkey[o.drow[t < nrb ? t : 0]] != KEY_INF;
+    const int ca = t < ncb && o.skeyc[t < ncb ? t : 0] != KEY_INF;
+    const int r_drow = ra ? o.drow[t] : 0, r_rnz = ra ? (int)o.rnz[t] : 0;
+    const int c_dcol = ca ? o.dcol[t] : 0, c_cnz = ca ? (int)o.cnz[t] : 0;
+    const u64 c_key = ca ? o.skeyc[t] : KEY_INF, c_cm = ca ? o.scm[t] : 0;
+    int nr2, nc2;
+    const int rpos = block_excl_scan<NT>(ra, &nr2, S.iscr);
+    const int cpos = block_excl_scan<NT>(ca, &nc2, S.iscr);
+    if (nr2 > KDs || nc2 > KDs) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
+    /* b. per-slot state of the new layout; tmps / tmpr map the new slots to the old ones */
+    for (int q = tid; q < KDs; q += NT) { n.skeyc[q] = KEY_INF; n.scm[q] = 0; n.cnz[q] = 0; n.rnz[q] = 0; }
+    bsync<NT>();
+    if (ra) { n.drow[rpos] = r_drow; n.rnz[rpos] = (unsigned short)r_rnz; n.tmps[rpos] = (unsigned short)t; }
+    if (ca) { n.dcol[cpos] = c_dcol; n.cnz[cpos] = (unsigned short)c_cnz; n.skeyc[cpos] = c_key; n.scm[cpos] = c_cm; n.tmpr[cpos] = (unsigned short)t; }
+    bsync<NT>();
+    /* c. bitmaps: the old ones sit behind the old per-slot arrays, clear of the new per-slot arrays but not of the
+     * new bitmaps, so the new words wait in registers (at most 8 per thread: NT >= kd_big) until all are computed */
+    {
+        unsigned rwv[8], cwv[8];
+        #pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int q = tid + i * NT;
+            unsigned rw = 0, cw = 0;
+            if (q < KDs * KWs) {
+                const int a = q / KWs, w = q % KWs;
+                if (a < nr2) {
+                    const unsigned *orow = o.rb_s + (int)n.tmps[a] * KWb;
+                    for (int j = 0; j < 32; j++) { const int c2 = w * 32 + j; if (c2 < nc2 && bit_test(orow, n.tmpr[c2])) rw |= 1u << j; }
+                }
+                if (a < nc2) {
+                    const unsigned *ocol = o.cb_s + (int)n.tmpr[a] * KWb;
+                    for (int j = 0; j < 32; j++) { const int t2 = w * 32 + j; if (t2 < nr2 && bit_test(ocol, n.tmps[t2])) cw |= 1u << j; }
+                }
+            }
+            rwv[i] = rw; cwv[i] = cw;
+        }
+        bsync<NT>();
+        #pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int q = tid + i * NT;
+            if (q < KDs * KWs) { n.rb_s[q] = rwv[i]; n.cb_s[q] = cwv[i]; }
+        }
+    }
+    bsync<NT>();
+    /* d. values and keys (the values overwrite the old bitmaps) */
+    {
+        const double *dvb = M.dn_val;
+        const unsigned *kb = (const unsigned *)M.dn_key;
+        unsigned *ks = (unsigned *)M.dn_key2;
+        for (int q = tid; q < KDs * KDs; q += NT) {
+            const int a = q / KDs, c2 = q % KDs;
+            double v = 0.0; unsigned key = 0xffffffffu;
+            if (a < nr2 && c2 < nc2 && bit_test(n.rb_s + a * KWs, c2)) {
+                const size_t off = (size_t)n.tmps[a] * KDb + n.tmpr[c2];
+                v = dvb[off]; key = kb[off];
+            }
+            n.dv_s[q] = v; ks[q] = key;
+        }
+    }
+    bsync<NT>();
+    if (tid == 0) {
+        S.kd = KDs; S.kw = KWs; S.dv_smem = 1; S.nrs = nr2; S.ncs = nc2;
+        M.dn_key = M.dn_key2;
+        S.n_kind[6]++;
+    }
+    bsync<NT>();
 }
 
 #endif

@@ -33,6 +33,7 @@ struct blu_b200 {
     int tail_threads;           /* CTA size of the dense-tail launch of a split batch factorization */
     int num_sms, smem_optin;    /* device properties */
     int kd_smem_max;            /* largest dense-tail order whose values fit in shared memory */
+    int want_kbig;              /* BLU_P_DENSE_K_BIG as asked for (alloc_dense clips it) */
     int split_min;              /* batches of more bases than this run as head / tail / build launches */
     int cap;                    /* smem line cache entries */
     std::vector<void *> allocs; /* every device allocation */
@@ -158,10 +159,10 @@ static int clear_overrides(blu_b200 *o) {
 /* the dense-tail arrays (blu_factor_dense.cuh); dense_k = 0 disables the dense tail */
 static void free_dense(blu_b200 *o) {
     BluDev &d = o->d;
-    dfree(o, d.dn_val); dfree(o, d.dn_key); dfree(o, d.dn_rbits); dfree(o, d.dn_cbits);
-    d.dn_val = nullptr; d.dn_key = nullptr; d.dn_rbits = d.dn_cbits = nullptr;
+    dfree(o, d.dn_val); dfree(o, d.dn_key); dfree(o, d.dn_key2); dfree(o, d.dn_rbits); dfree(o, d.dn_cbits);
+    d.dn_val = nullptr; d.dn_key = nullptr; d.dn_key2 = nullptr; d.dn_rbits = d.dn_cbits = nullptr;
 }
-static int alloc_dense(blu_b200 *o, int want) {
+static int alloc_dense(blu_b200 *o, int want, int want_big) {
     BluDev &d = o->d;
     free_dense(o);
     int kd = want < 0 ? 0 : want;
@@ -169,14 +170,21 @@ static int alloc_dense(blu_b200 *o, int want) {
     if (kd > mcap) kd = mcap;
     kd &= ~31;
     if (kd > BLU_DENSE_K_MAX) kd = BLU_DENSE_K_MAX;
-    d.dense_k = kd;
-    const size_t n = (size_t)d.nmat, k = (size_t)kd;
+    int kb = want_big < 0 ? 0 : want_big;
+    if (kb > mcap) kb = mcap;
+    kb &= ~31;
+    if (kb > BLU_DENSE_K_MAX) kb = BLU_DENSE_K_MAX;
+    /* the first stage only exists in front of a shared-memory resident second one */
+    if (kd == 0 || kd > o->kd_smem_max || kb <= kd) kb = 0;
+    d.dense_k = kd; d.dense_kbig = kb; d.dense_kbig_eff = 0;
+    const size_t n = (size_t)d.nmat, k = (size_t)(kb > kd ? kb : kd);
     /* up to kd_smem_max the values live in shared memory (blu_factor_dense.cuh); beyond, in HBM */
-    int st = dalloc(o, &d.dn_val, kd > o->kd_smem_max ? n * k * k : 1);
+    int st = dalloc(o, &d.dn_val, (kb || k > (size_t)o->kd_smem_max) ? n * k * k : 1);
     if (st == BLU_OK) st = dalloc(o, &d.dn_key, n * k * k);
+    if (st == BLU_OK) st = dalloc(o, &d.dn_key2, kb ? n * (size_t)kd * kd : 1);
     if (st == BLU_OK) st = dalloc(o, &d.dn_rbits, n * k * (k / 32));
     if (st == BLU_OK) st = dalloc(o, &d.dn_cbits, n * k * (k / 32));
-    if (st != BLU_OK) { free_dense(o); d.dense_k = 0; }
+    if (st != BLU_OK) { free_dense(o); d.dense_k = 0; d.dense_kbig = 0; }
     return st;
 }
 
@@ -254,9 +262,11 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     if (st == BLU_OK) st = alloc_stores(o);
     if (st == BLU_OK) { d.slot_store = o->d_slot; st = clear_overrides(o); }
     if (st == BLU_OK) {
-        int kd = o->kd_smem_max;
+        int kd = o->kd_smem_max, kb = single ? 0 : BLU_DENSE_K_MAX;
         if (const char *e = getenv("BLU_B200_DENSE_K")) kd = atoi(e);      /* tuning knob, same as BLU_P_DENSE_K */
-        st = alloc_dense(o, kd);
+        if (const char *e = getenv("BLU_B200_DENSE_K_BIG")) kb = atoi(e);  /* tuning knob, same as BLU_P_DENSE_K_BIG */
+        o->want_kbig = kb;
+        st = alloc_dense(o, kd, kb);
     }
     if (st == BLU_OK) {
         /* nupdate = None until the first factorization (lu.rs:329-331) */
@@ -350,6 +360,15 @@ static int launch_factorize_mode(blu_b200 *o, cudaStream_t stream, int slot0, in
     size_t smem = blu_factor_smem_bytes(o->cap, nt / 32, o->d.m);
     if (dense_here) smem = std::max(smem, resident ? blu_dense_smem_bytes_resident(kd) : blu_dense_smem_bytes(kd));
     BluDev dv = o->d; dv.slot0 = slot0; dv.nslot = nslot;
+    /* the first (HBM/L2) stage of the dense tail: the launch that runs it has the second stage in shared memory and a
+     * thread per slot (dense_restage); the head of a split factorization stops where that launch takes over */
+    {
+        const int run_nt = mode == BLU_MODE_HEAD ? o->tail_threads : nt;
+        const bool res2 = kd > 0 && kd <= o->kd_smem_max && mode != BLU_MODE_BUILD;
+        dv.dense_kbig_eff = (res2 && o->d.dense_kbig > kd && run_nt >= o->d.dense_kbig) ? o->d.dense_kbig : 0;
+        if (dv.dense_kbig_eff && dense_here)
+            smem = std::max(smem, blu_dense_smem_bytes(dv.dense_kbig_eff) + (size_t)2 * dv.dense_kbig_eff * (dv.dense_kbig_eff / 32) * 4);
+    }
     int e;
     switch (nt) {
     case 32: e = blu_launch_factorize_32(stream, dv, nslot, o->cap, mode, kd, resident ? 1 : 0, rerun, smem); break;
@@ -882,12 +901,13 @@ extern "C" int blu_set_param(blu_t *o, int what, double v) {
     case BLU_P_SEARCH_ROWS: p.search_rows = (int)v != 0; break;      /* markowitz.rs:125-189 (markowitz_search_rows); the crate's default is 0 (D8) */
     case BLU_P_REALLOC_FACTOR: o->realloc_factor = v; break;
     case BLU_P_NORMS: o->norms = v != 0.0; break;
-    case BLU_P_DENSE_K: {
+    case BLU_P_DENSE_K: case BLU_P_DENSE_K_BIG: {
         if (v < 0 || v > BLU_DENSE_K_MAX) return BLU_ERROR_INVALID_ARGUMENT;
         if (cudaSetDevice(o->device) != cudaSuccess) return BLU_ERROR_CUDA;
         cudaStreamSynchronize(o->stream);
-        int st = alloc_dense(o, (int)v);
+        int st = what == BLU_P_DENSE_K ? alloc_dense(o, (int)v, o->want_kbig) : alloc_dense(o, o->d.dense_k, (int)v);
         if (st != BLU_OK) return st;
+        if (what == BLU_P_DENSE_K_BIG) o->want_kbig = (int)v;
         break;
     }
     case BLU_P_THREADS_PER_BASIS: case BLU_P_TAIL_THREADS: {
@@ -935,6 +955,7 @@ extern "C" double blu_get_param(const blu_t *o, int what) {
     case BLU_P_W_MEM: return (double)o->d.w_mem;
     case BLU_P_THREADS_PER_BASIS: return o->nthreads;
     case BLU_P_DENSE_K: return o->d.dense_k;
+    case BLU_P_DENSE_K_BIG: return o->d.dense_kbig;
     case BLU_P_TAIL_THREADS: return o->tail_threads;
     case BLU_P_SPLIT_MIN: return o->split_min;
     case BLU_P_TREE_MIN: return o->d.tree_min;

@@ -125,9 +125,12 @@ struct BluDev {
     /* dense tail (blu_factor_dense.cuh): the last dense_k x dense_k active submatrix as a row-major value
      * array, per-entry storage-order keys, and row/column presence bitmaps.  dense_k = 0: disabled. */
     int dense_k;
+    int dense_kbig;             /* order of the first, HBM/L2-resident stage of the dense tail (BLU_P_DENSE_K_BIG; 0 = none) */
+    int dense_kbig_eff;         /* ... as this launch uses it (0 unless the second stage is shared-memory resident and the CTA has a thread per slot) */
     int tree_min;               /* bumps with more columns than this search through the min-tree (ctree) */
     double *dn_val;             /* dense_k^2 per basis */
     BluKey2 *dn_key;            /* dense_k^2 per basis: (position key in its column, position key in its row) */
+    BluKey2 *dn_key2;           /* the keys of the second stage (dense_k^2 per basis) when there are two */
     unsigned *dn_rbits, *dn_cbits; /* dense_k * dense_k/32 each per basis */
     BluInfo *info;              /* nmat */
 };

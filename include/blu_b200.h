@@ -50,6 +50,7 @@ enum {
     BLU_P_TAIL_THREADS,                 /* CTA size of the dense-tail launch of a split batch factorization (default 512) */
     BLU_P_SPLIT_MIN,                    /* batches of more bases than this run as three launches: sparse head, dense tail with one CTA per SM, build_factors (default 0: always, when the dense tail is shared-memory resident -- a single launch sized for 200+ KB of shared memory would leave the sparse head without L1) */
     BLU_P_TREE_MIN,                     /* bumps with more active columns than this find their Markowitz candidates through a min-tree over the column keys instead of a scan (default 4096; needs maxsearch <= 4) */
+    BLU_P_DENSE_K_BIG,                  /* two-stage dense tail: the active submatrix turns dense already at this order (multiple of 32, <= 256, > BLU_P_DENSE_K) with its values in HBM/L2, and moves into shared memory when it has shrunk to BLU_P_DENSE_K (0 = one stage; default 256 for batches when BLU_P_DENSE_K is shared-memory resident).  Results do not depend on it. */
     BLU_I_M = 100, BLU_I_RANK, BLU_I_BUMP_SIZE, BLU_I_BUMP_NZ, BLU_I_MATRIX_NZ, BLU_I_L_NZ,
     BLU_I_U_NZ, BLU_I_R_NZ, BLU_I_NSEARCH_PIVOT, BLU_I_NEXPAND, BLU_I_NGARBAGE,
     BLU_I_FACTOR_FLOPS, BLU_I_MIN_PIVOT, BLU_I_MAX_PIVOT, BLU_I_MAX_ETA, BLU_I_NUPDATE,

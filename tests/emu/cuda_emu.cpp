@@ -14,6 +14,27 @@ ucontext_t sched_ctx;
 static std::function<void()> *g_body;
 static const size_t STACK = 256 * 1024;
 
+}
+void emu_strict_check() {
+    static const int strict = getenv("EMU_STRICT") != nullptr;
+    if (!strict) return;
+    static void *site[6]; static unsigned site_gen = ~0u; static int site_thread = -1;
+    void *bt0[8];
+    const int n = backtrace(bt0, 8) - 1;
+    void **bt = bt0 + 1;      /* (frame 0 is this function) */
+    if (site_gen != emu::blk_gen || emu::blk_arrived == 0) { site_gen = emu::blk_gen; site_thread = emu::cur; for (int q = 0; q < 6; q++) site[q] = q < n ? bt[q] : nullptr; return; }
+    for (int q = 3; q < 5; q++)      /* (frames 0-1 are this check and __syncthreads; frame 2 differs when the compiler duplicates a barrier) */
+        if ((q < n ? bt[q] : nullptr) != site[q]) {
+            Dl_info di;
+            fprintf(stderr, "cuda_emu: DIVERGENT block barrier: thread %d at", emu::cur);
+            for (int r = 0; r < n; r++) if (dladdr(bt[r], &di) && di.dli_fbase) fprintf(stderr, " +0x%zx", (size_t)((char *)bt[r] - (char *)di.dli_fbase));
+            fprintf(stderr, "\n   thread %d at", site_thread);
+            for (int r = 0; r < 6; r++) if (site[r] && dladdr(site[r], &di) && di.dli_fbase) fprintf(stderr, " +0x%zx", (size_t)((char *)site[r] - (char *)di.dli_fbase));
+            fprintf(stderr, "\n");
+            abort();
+        }
+}
+namespace emu {
 void yield_wait(unsigned *gen, unsigned mygen) {
     Fiber &f = fibers[cur];
     f.state = 1; f.gen = gen; f.mygen = mygen;

@@ -79,7 +79,11 @@ inline void warp_barrier() {
 }
 }
 
+/* EMU_STRICT=1: every thread of the block must reach a block barrier from the same call site (two frames of the
+ * call stack are compared); the first mismatch is reported with both stacks (addr2line -e the library). */
+void emu_strict_check();
 inline void __syncthreads() {
+    emu_strict_check();
     unsigned g = emu::blk_gen;
     if (++emu::blk_arrived >= emu::blk_live) { emu::blk_arrived = 0; emu::blk_gen++; }
     else emu::yield_wait(&emu::blk_gen, g);

@@ -325,6 +325,35 @@ def test_emu_split_batch(emu, kd, tail):
         assert np.array_equal(x[k], xo)
 
 
+@pytest.mark.parametrize("kd,kbig,tail,m", [(64, 128, 128, 200), (32, 64, 64, 120), (96, 160, 256, 220), (160, 192, 256, 300)])
+def test_emu_two_stage_tail(emu, kd, kbig, tail, m):
+    """Two-stage dense tail (BLU_P_DENSE_K_BIG): the active submatrix turns dense at order kbig with its values in
+    HBM/L2, is compacted into shared memory at order kd (dense_restage), and the factors stay those of the oracle."""
+    from parity import STATS
+    nmat = 3
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 30, 5.0, 9300, 9800)
+    b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()), lib=emu)
+    b.dense_k = kd; b.dense_k_big = kbig; b.split_min = 0; b.threads_per_basis = 64; b.tail_threads = tail
+    assert int(b.get_param("dense_k_big")) == kbig
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all()
+    st, x, sst = b.solve_dense(rhs, "N")
+    assert st == 0 and (sst == 0).all()
+    for k in range(nmat):
+        cp, ri, v = gen.basis(9300 + k, m, 30, 5.0)
+        o = oracle_for(m, len(v), 400)
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        _, fo = o.get_factors()
+        _, fg = b.get_factors(k)
+        for key in fo:
+            assert np.array_equal(fo[key], fg[key]), (k, key)
+        for name in STATS:
+            assert o.info(name) == b.info(k, name), (k, name)
+        assert b.info(k, "n_kind6") >= 2, "both stages ran"      # dense_enter + dense_restage
+        _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
+        assert np.array_equal(x[k], xo)
+
+
 def test_emu_dense_tail_structures(emu):
     """Exact cancellation, rank deficiency and columns that fall below abstol inside the dense tail
     (the paths that leave it early: dense_exit + pivot.rs:96-106 on the line file)."""

@@ -537,15 +537,16 @@ def test_dense_tail_orders(kd):
     assert np.array_equal(xg, xo)
 
 
-@pytest.mark.parametrize("kd,tail,nt", [(160, 512, 128), (96, 256, 64), (160, 1024, 256)])
-def test_split_batch_parity(kd, tail, nt):
+@pytest.mark.parametrize("kd,tail,nt,kbig", [(160, 512, 128, 256), (96, 256, 64, 0), (160, 1024, 256, 224), (160, 512, 128, 0), (64, 256, 128, 256), (160, 512, 128, 192)])
+def test_split_batch_parity(kd, tail, nt, kbig):
     """A batch large enough to run as head / tail / build launches (the bench path): every basis equals the
-    oracle, including the counters."""
+    oracle, including the counters.  kbig != 0: two-stage dense tail (HBM/L2 at order kbig, then shared memory)."""
     from parity import STATS
     nmat, m = 160, 600
     bb, be, bi, bx, rhs = gen.batch(nmat, m, 200, 5.0, 9200, 9700)
     b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()))
-    b.dense_k = kd; b.tail_threads = tail; b.threads_per_basis = nt; b.split_min = 100
+    b.dense_k = kd; b.dense_k_big = kbig; b.tail_threads = tail; b.threads_per_basis = nt; b.split_min = 100
+    assert int(b.get_param("dense_k_big")) == kbig
     l0 = b.launch_count()
     st, status = b.factorize(bb, be, bi, bx)
     assert st == 0 and (status == 0).all()
@@ -563,6 +564,8 @@ def test_split_batch_parity(kd, tail, nt):
         for name in STATS:
             assert o.info(name) == b.info(k, name), (k, name)
         assert b.info(k, "n_kind5") > 0
+        if kbig:
+            assert b.info(k, "n_kind6") >= 2, "both stages ran"
         _, xo = o.solve_dense(rhs[k * m:(k + 1) * m], "N")
         assert np.array_equal(x[k], xo)
 
