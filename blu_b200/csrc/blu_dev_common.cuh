@@ -24,6 +24,7 @@ static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x
 #define STAMP_BITS 40
 #define MAXROW_SMALL 64 /* pivot.rs:22 */
 #define MAXCAND 32      /* upper bound on maxsearch honoured by the search kernel */
+#define RING_BARS 128       /* completion barriers of the row ring (warps x buffers per warp), in front of the ring */
 #define TREE_MAX_SEARCH 4    /* ... when maxsearch is at most this (the frontier of the top-k walk lives in shared memory) */
 
 /* per-slot view of BluDev */
@@ -147,6 +148,9 @@ struct Shm {
     u64 mbar; unsigned mbar_phase;   /* completion barrier of the bulk copies (dense_pivot) and its current phase */
     int lput, uput;           /* fill pointers of L and U (= l_begin_p[rank], u_begin[rank]) */
     int dpcand;               /* stash row of the pivot column's keys */
+    /* first stage of a two-stage tail: per-warp ring of row buffers filled and drained by bulk copies (dense_step) */
+    unsigned ring_phase[32];  /* per warp: current phase bit of each of its buffers */
+    int ring_nbuf;            /* buffers per warp in this stage (0: no ring) */
     int cand_done;            /* candidate columns evaluated so far (the warp that finishes last makes the choice) */
     int dgeneral;             /* the chosen pivot is a general dense step (pivot_any / pivot_small) */
 };
@@ -342,6 +346,7 @@ __device__ __forceinline__ void mbar_init(u64 *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_inval(u64 *bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ void bulk_copy_g2s(void *sdst, const void *gsrc, unsigned bytes, u64 *bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -352,10 +357,31 @@ __device__ __forceinline__ void bulk_fence() { asm volatile("fence.proxy.async;"
 __device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
     asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+/* shared -> global bulk copy (completion tracked per thread in bulk async-groups) */
+__device__ __forceinline__ void bulk_copy_s2g(void *gdst, const void *ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+/* all but the N most recent groups have read their shared-memory source (the buffer may be refilled) */
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+/* all but the N most recent groups are complete (their writes performed) */
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+/* this thread's shared-memory writes become visible to the bulk-copy engine */
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+/* values that bulk stores rewrite are read past L1 (the async proxy does not keep L1 coherent) */
+__device__ __forceinline__ double ld_l2(const double *p) { return __ldcg(p); }
 #else
-static inline void mbar_init(u64 *, unsigned) {}
-static inline void bulk_copy_g2s(void *sdst, const void *gsrc, unsigned bytes, u64 *) { memcpy(sdst, gsrc, bytes); }
-static inline void mbar_wait(u64 *, unsigned) {}
+static inline void bulk_copy_s2g(void *gdst, const void *ssrc, unsigned bytes) { memcpy(gdst, ssrc, bytes); }
+static inline void bulk_commit() {}
+template <int N> static inline void bulk_wait_read() {}
+template <int N> static inline void bulk_wait() {}
+static inline void fence_async_smem() {}
+static inline double ld_l2(const double *p) { return *p; }
+/* emulated completion barrier: the word counts completed phases; a waiter yields until the phase of its parity is over */
+static inline void mbar_init(u64 *bar, unsigned) { *bar = 0; }
+static inline void mbar_inval(u64 *) {}
+static inline void bulk_copy_g2s(void *sdst, const void *gsrc, unsigned bytes, u64 *bar) { memcpy(sdst, gsrc, bytes); (*(unsigned *)bar)++; }
+static inline void mbar_wait(u64 *bar, unsigned parity) { unsigned *g = (unsigned *)bar; while ((*g & 1u) == parity) emu::yield_wait(g, *g); }
 static inline void bulk_fence() {}
 #endif
 

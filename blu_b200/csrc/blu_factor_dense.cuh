@@ -53,6 +53,7 @@ struct DenseSm {
     BluKey2 *rowk;         /* the pivot row's keys, fetched by one bulk copy (16-byte aligned: kd is a multiple of 32) */
     unsigned *cmask, *rmask, *rfull;
     unsigned short *clist, *rlist, *posr, *rnz, *cnz, *tmps, *tmpr;
+    unsigned *kminp;       /* per column of the pivot row: (key << 8 | row slot) of its first entry outside the pivot column and row (overlays tmps|tmpr) */
     unsigned *rb_s, *cb_s; double *dv_s;   /* resident bitmaps and values (RES only) */
 };
 __device__ __forceinline__ void dense_view(DenseSm &d, unsigned char *dyn, int KD, int KW) {
@@ -76,7 +77,7 @@ __device__ __forceinline__ void dense_view(DenseSm &d, unsigned char *dyn, int K
     d.posr = p2; p2 += KD;
     d.rnz = p2; p2 += KD;
     d.cnz = p2; p2 += KD;
-    d.tmps = p2; p2 += KD;
+    d.tmps = p2; d.kminp = (unsigned *)p2; p2 += KD;
     d.tmpr = p2; p2 += KD;
     unsigned *b = (unsigned *)(dyn + blu_dense_smem_bytes(KD));
     d.rb_s = b; d.cb_s = b + KD * KW;
@@ -88,7 +89,24 @@ __device__ __forceinline__ void dense_view(DenseSm &d, unsigned char *dyn, int K
     unsigned *const rbm = RES ? d.rb_s : S.M.dn_rbits; \
     unsigned *const cbm = RES ? d.cb_s : S.M.dn_cbits; \
     BluKey2 *const dkey = S.M.dn_key
+/* a value of the dense array (past L1 in the first stage of a two-stage tail, whose rows bulk stores rewrite) */
+#define DV(off) (RES == 2 ? ld_l2(dv + (off)) : dv[off])
 
+/* byte offset of the row ring behind the per-step arrays and the bitmaps of order kd (128-byte aligned) */
+__device__ __forceinline__ size_t dense_ring_offset(int kd) {
+    return ((blu_dense_smem_bytes(kd) + (size_t)2 * kd * (kd / 32) * 4 + 127) & ~(size_t)127) + RING_BARS * sizeof(u64);
+}
+/* the ring's completion barriers live right in front of it; they exist from dense_enter to the end of the stage */
+__device__ __forceinline__ u64 *dense_ring_bars(unsigned char *dyn, int kd) { return (u64 *)(dyn + dense_ring_offset(kd)) - RING_BARS; }
+template <int NT> __device__ __forceinline__ void dense_ring_retire(Shm &S) {
+    if (S.ring_nbuf) {
+        BLU_DYN_SMEM(dynq_);
+        u64 *bars = dense_ring_bars(dynq_, S.kd);
+        for (int q = threadIdx.x; q < (NT / 32) * S.ring_nbuf; q += NT) mbar_inval(&bars[q]);
+    }
+    bsync<NT>();
+    if (threadIdx.x == 0) S.ring_nbuf = 0;
+}
 __device__ __forceinline__ int bit_test(const unsigned *row, int t) { return (row[t >> 5] >> (t & 31)) & 1; }
 /* number of set bits below position t */
 __device__ __forceinline__ int bits_rank(const unsigned *row, int t) {
@@ -156,12 +174,28 @@ template <int NT, int RES> __device__ __noinline__ void dense_enter(Shm &S) {
         if (lane == 0) d.rnz[t] = (unsigned short)(e - b);
     }
     if (tid == 0) {
+        S.ring_nbuf = 0;
+        if (RES == 2) {      /* what the launch has beyond this stage's arrays becomes the row ring of the update */
+            const size_t base = dense_ring_offset(KD);
+            const size_t have = blu_dense_smem_bytes_resident(S.kd_small);
+            const size_t level = (size_t)NW * KD * sizeof(double);
+            int nb = have > base ? (int)((have - base) / level) : 0;
+            if (nb > RING_BARS / NW) nb = RING_BARS / NW;
+            if (nb > 8) nb = 8;
+            S.ring_nbuf = nb >= 2 ? nb : 0;
+        }
         S.dense = 1; S.nrs = nr; S.ncs = nc;
         S.epoch = 1;          /* the position keys handed out here are epoch 0 */
         S.dense_entries++;
         S.n_kind[6]++;
     }
     bsync<NT>();
+    if (RES == 2 && S.ring_nbuf) {
+        u64 *bars = dense_ring_bars(dyn_, KD);
+        for (int q = tid; q < NW * S.ring_nbuf; q += NT) mbar_init(&bars[q], 1);
+        if (tid < 32) S.ring_phase[tid] = 0;
+        bsync<NT>();
+    }
 }
 
 /* ------------------------------------------------------------------ */
@@ -173,6 +207,7 @@ template <int NT, int RES> __device__ __noinline__ void dense_exit(Shm &S) {
     constexpr int NW = NT / 32;
     const int KD = S.kd, KW = S.kw, nr = S.nrs, nc = S.ncs;
     DENSE_VIEW(RES);
+    if (RES == 2) dense_ring_retire<NT>(S);
     const int base = S.w_half * M.w_mem;
     int put = 0, nact = 0;
     for (int b0 = 0; b0 < nc; b0 += NT) {
@@ -222,7 +257,7 @@ template <int NT, int RES> __device__ __noinline__ void dense_exit(Shm &S) {
                 unsigned word = cb[w];
                 while (word) { const int t2 = w * 32 + __ffs((int)word) - 1; word &= word - 1; r += dkey[(size_t)t2 * KD + c].c < my; }
             }
-            M.w_idx[b + r] = d.drow[t]; M.w_val[b + r] = dv[off];
+            M.w_idx[b + r] = d.drow[t]; M.w_val[b + r] = DV(off);
         }
     }
     for (int t = wid; t < nr; t += NW) {
@@ -315,7 +350,7 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
             }
             const int p = t == tp ? 0 : (r == 0 ? wc : r);
             d.clist[p] = (unsigned short)t;
-            d.cvalp[p] = dv[(size_t)t * KD + cp];
+            d.cvalp[p] = DV((size_t)t * KD + cp);
         }
     }
     mbar_wait(&S.mbar, phase);
@@ -345,7 +380,7 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
             const int p = c == cp ? 0 : (r == 0 ? wr : r);
             d.rlist[p] = (unsigned short)c;
             d.posr[c] = (unsigned short)p;
-            if (c != cp) d.scm[c] = 0;
+            if (c != cp) { d.scm[c] = 0; d.kminp[c] = 0xffffffffu; }
             if (SMALL) d.sdrop[p] = 0;
         }
     }
@@ -356,46 +391,121 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
     const unsigned ekey = S.epoch << 8;
     if (tid == 0) { const i64 now = clock64(); S.t_phase[14] += now - tq; tq = now; }
 
-    /* D. per column of the pivot row: the entries outside the pivot column (pivot.rs:231-262).  Their maximum
-     * seeds colmax; the first of them in storage order takes the place of the pivot-row entry. */
-    for (int kk = 1 + tid; kk <= rnz1; kk += NT) {
-        const int c = d.rlist[kk];
-        const unsigned *cb = cbm + c * KW;
-        double cmx = 0.0; unsigned kmin = 0xffffffffu; int tmin = -1;
-        {   /* a column whose only entry outside the pivot column is the pivot-row entry (the usual case once the
-             * tail is full) has nothing to exchange and no maximum to seed: no key is needed */
-            int others = 0;
-            for (int w = 0; w < KW; w++) others += __popc(cb[w] & ~d.cmask[w]);
-            if (others == 1) continue;
-        }
-        const unsigned short kpr = (unsigned short)(rowk32[c] & 0xffffu);
-        /* the keys live in HBM/L2: fetch them eight at a time so that one round trip serves eight entries */
-        int w = 0; unsigned tb = cb[0] & ~d.cmask[0];
-        for (;;) {
-            int tt[8]; unsigned kq[8];
-            #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                while (tb == 0 && w + 1 < KW) { w++; tb = cb[w] & ~d.cmask[w]; }
-                if (tb) { tt[u] = w * 32 + __ffs((int)tb) - 1; tb &= tb - 1; } else tt[u] = -1;
+    /* D. per column of the pivot row: the entries outside the pivot column and the pivot row (pivot.rs:231-262).
+     * Their maximum seeds colmax, and the first of them in storage order -- if it comes before the pivot-row entry
+     * -- takes that entry's place (its key, written in F).  G threads share a column (each a few words of its
+     * bitmap), so that a thread has at most eight entries and all their key (HBM/L2) and value loads are in flight
+     * together: one round trip per step.  A column with no such entry (the usual case once the tail is full) costs
+     * no memory access at all. */
+    {
+        int G = 1;
+        while (G < 8 && G * 2 <= KW && rnz1 * G * 2 <= NT) G *= 2;
+        for (int it = tid; it < rnz1 * G; it += NT) {
+            const int kk = 1 + it / G, g = it % G;
+            const int c = d.rlist[kk];
+            const unsigned *cb = cbm + c * KW;
+            double cmx = 0.0; unsigned kmin = 0xffffffffu;
+            int w = g; unsigned tb = 0;
+            if (w < KW) { tb = cb[w] & ~d.cmask[w]; if (w == (tp >> 5)) tb &= ~(1u << (tp & 31)); }
+            for (;;) {
+                int tt[8]; unsigned kq[8]; double xq[8];
+                #pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    while (tb == 0 && w + G < KW) { w += G; tb = cb[w] & ~d.cmask[w]; if (w == (tp >> 5)) tb &= ~(1u << (tp & 31)); }
+                    if (tb) { tt[u] = w * 32 + __ffs((int)tb) - 1; tb &= tb - 1; } else tt[u] = -1;
+                }
+                if (tt[0] < 0) break;
+                #pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    kq[u] = tt[u] >= 0 ? dkey[(size_t)tt[u] * KD + c].c : 0xffffu;
+                    xq[u] = tt[u] >= 0 ? DV((size_t)tt[u] * KD + c) : 0.0;
+                }
+                #pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (tt[u] < 0) continue;
+                    const unsigned pk = (kq[u] << 8) | (unsigned)tt[u];
+                    if (pk < kmin) kmin = pk;
+                    const double ax = fabs(xq[u]);
+                    if (ax > cmx) cmx = ax;
+                }
+                if (tt[7] < 0) break;
             }
-            if (tt[0] < 0) break;
-            #pragma unroll
-            for (int u = 0; u < 8; u++) kq[u] = tt[u] >= 0 ? dkey[(size_t)tt[u] * KD + c].c : 0xffffffffu;
-            #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                if (tt[u] < 0) continue;
-                if (kq[u] < kmin) { kmin = kq[u]; tmin = tt[u]; }
-                if (tt[u] != tp) { const double ax = fabs(dv[(size_t)tt[u] * KD + c]); if (ax > cmx) cmx = ax; }
-            }
-            if (tt[7] < 0) break;
+            if (kmin != 0xffffffffu) atomicMin(&d.kminp[c], kmin);
+            if (cmx > 0.0) atomicMax((unsigned long long *)&d.scm[c], (unsigned long long)__double_as_longlong(cmx));
         }
-        if (tmin < 0) { BLU_CHECK(S, 0); }
-        else if (tmin != tp) dkey[(size_t)tmin * KD + c].c = kpr;
-        if (cmx > 0.0) atomicMax((unsigned long long *)&d.scm[c], (unsigned long long)__double_as_longlong(cmx));
     }
 
-    /* E. the rank-1 update: a warp owns 32 column slots and every RS-th block of rows of the pivot column */
-    {
+    /* E. the rank-1 update.  First stage of a two-stage tail (values in HBM/L2), pivot_any: every warp streams its
+     * share of the pivot column's rows through a private ring of shared-memory buffers -- a bulk copy brings a
+     * whole row (kd * 8 bytes, contiguous) in, the warp updates it in place, a bulk copy takes it back -- so
+     * that nbuf rows per warp are in flight whatever the register budget (cp.async.bulk + mbarrier, SASS
+     * UBLKCP); with plain loads the step is bound by the latency of eight loads per thread. */
+    if (RES == 2 && !SMALL && S.ring_nbuf >= 2) {
+        const int NB = S.ring_nbuf;
+        BLU_DYN_SMEM(dynr_);
+        double *const mybuf = (double *)(dynr_ + dense_ring_offset(KD)) + (size_t)wid * NB * KD;
+        u64 *const mybar = dense_ring_bars(dynr_, KD) + wid * NB;
+        unsigned ph = S.ring_phase[wid];
+        const unsigned rowbytes = (unsigned)(KD * sizeof(double));
+        double a[8], cmx[8]; unsigned rkv[8]; unsigned inRm = 0; int pw = -1;
+        #pragma unroll
+        for (int cw = 0; cw < 8; cw++) {
+            a[cw] = 0.0; cmx[cw] = 0.0; rkv[cw] = 0;
+            if (cw < KW) {
+                const int c = cw * 32 + lane;
+                if ((d.rmask[cw] >> lane) & 1u) {
+                    inRm |= 1u << cw;
+                    a[cw] = __ddiv_rn(DV((size_t)tp * KD + c), pivot);
+                    rkv[cw] = ekey + (unsigned)d.posr[c];
+                }
+                if (c == cp) pw = cw;
+            }
+        }
+        const int nmine = cnz1 > wid ? (cnz1 - 1 - wid) / NW + 1 : 0;      /* rows p = 1 + wid + i * NW */
+        BluKey2 gone; gone.c = 0xffffu; gone.r = 0xffffu;
+        if (lane == 0) {
+            bulk_fence();
+            for (int i = 0; i < NB && i < nmine; i++)
+                bulk_copy_g2s(mybuf + (size_t)i * KD, dv + (size_t)d.clist[1 + wid + i * NW] * KD, rowbytes, &mybar[i]);
+        }
+        for (int i = 0; i < nmine; i++) {
+            const int b = i % NB, p = 1 + wid + i * NW;
+            const int t = d.clist[p];
+            const double cv = d.cvalp[p];
+            double *const buf = mybuf + (size_t)b * KD;
+            mbar_wait(&mybar[b], (ph >> b) & 1u);
+            ph ^= 1u << b;
+            #pragma unroll
+            for (int cw = 0; cw < 8; cw++) {
+                if (cw >= KW) continue;
+                const int c = cw * 32 + lane;
+                if ((inRm >> cw) & 1u) {
+                    const double x = __dsub_rn(buf[c], __dmul_rn(a[cw], cv));
+                    buf[c] = x;
+                    BluKey2 kv; kv.c = (unsigned short)(ekey + (unsigned)p); kv.r = (unsigned short)rkv[cw];
+                    dkey[(size_t)t * KD + c] = kv;
+                    const double ax = fabs(x);
+                    if (ax > cmx[cw]) cmx[cw] = ax;
+                } else if (cw == pw) dkey[(size_t)t * KD + c] = gone;      /* the pivot column leaves the active submatrix */
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_copy_s2g(dv + (size_t)t * KD, buf, rowbytes);
+                bulk_commit();
+                if (i >= 1 && i - 1 + NB < nmine) {      /* the buffer of the previous row is free once its store has read it */
+                    bulk_wait_read<1>();
+                    const int bp = (i - 1) % NB;
+                    bulk_copy_g2s(mybuf + (size_t)bp * KD, dv + (size_t)d.clist[1 + wid + (i - 1 + NB) * NW] * KD, rowbytes, &mybar[bp]);
+                }
+            }
+        }
+        if (lane == 0) { bulk_wait<0>(); bulk_fence(); S.ring_phase[wid] = ph; }
+        #pragma unroll
+        for (int cw = 0; cw < 8; cw++)
+            if (((inRm >> cw) & 1u) && cmx[cw] > 0.0)
+                atomicMax((unsigned long long *)&d.scm[cw * 32 + lane], (unsigned long long)__double_as_longlong(cmx[cw]));
+    } else {
         const int RS = NW >= KW ? NW / KW : 1;
         const int chunk = (cnz1 + RS - 1) / RS;
         BluKey2 gone; gone.c = 0xffffu; gone.r = 0xffffu;
@@ -407,7 +517,7 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
             const bool inR = (rm >> lane) & 1u;
             const bool isP = c == cp;
             double a = 0.0; unsigned rkv = 0; int kk = 0;
-            if (inR) { kk = d.posr[c]; a = __ddiv_rn(dv[(size_t)tp * KD + c], pivot); rkv = ekey + (unsigned)kk; }
+            if (inR) { kk = d.posr[c]; a = __ddiv_rn(DV((size_t)tp * KD + c), pivot); rkv = ekey + (unsigned)kk; }
             double cmx = 0.0;
             u64 mydrop = 0;
             const int pend = (rs + 1) * chunk < cnz1 ? (rs + 1) * chunk : cnz1;
@@ -419,7 +529,7 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
                     const int p = p0 + u;
                     tt[u] = p <= pend ? (int)d.clist[p] : -1;
                     cv[u] = p <= pend ? d.cvalp[p] : 0.0;
-                    xv[u] = (inR && tt[u] >= 0) ? dv[(size_t)tt[u] * KD + c] : 0.0;
+                    xv[u] = (inR && tt[u] >= 0) ? DV((size_t)tt[u] * KD + c) : 0.0;
                 }
                 #pragma unroll
                 for (int u = 0; u < UR; u++) {
@@ -489,7 +599,11 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
         const double cmx = __longlong_as_double((long long)d.scm[c]);
         M.colpiv[j] = cmx;
         d.skeyc[c] = mkckey(cnt, cbase + kk, cmx, abstol);
-        const double xr = dv[(size_t)tp * KD + c];
+        {   /* pivot.rs:261-262: the first entry outside the pivot column moves to the place of the pivot-row entry */
+            const unsigned pk = d.kminp[c], kpr = rowk32[c] & 0xffffu;
+            if ((pk >> 8) < kpr) dkey[(size_t)(pk & 0xffu) * KD + c].c = (unsigned short)kpr;
+        }
+        const double xr = DV((size_t)tp * KD + c);
         if (fabs(xr) > droptol) { M.u_idx[ubase + kk - 1] = j; M.u_val[ubase + kk - 1] = xr; }
         else { M.u_idx[ubase + kk - 1] = -2; M.u_val[ubase + kk - 1] = 0.0; S.flag_a = 1; }
         if (cmx == 0.0 || cmx < abstol) S.need_remove = 1;
@@ -608,28 +722,33 @@ template <int NT, int RES> __device__ __noinline__ int dense_run(Shm &S) {
             if (cc < DENSE_STASH) {
                 /* all key loads of the column in flight together; the pivot step reuses them */
                 unsigned *stash = d.candk + cc * KD;
-                {   /* kd <= 256: at most eight rows per lane, their key loads issued back to back (one round trip) */
-                    unsigned kq[8];
+                {   /* kd <= 256: at most eight rows per lane; their key and value loads are issued back to back (one
+                     * round trip to HBM/L2 for the keys, and for the values too in the first stage) */
+                    unsigned kq[8]; double xq[8];
                     #pragma unroll
-                    for (int u = 0; u < 8; u++) { const int t = lane + 32 * u; kq[u] = (t < nr && bit_test(cb, t)) ? dkey[(size_t)t * KD + c].c : 0xffffffffu; }
+                    for (int u = 0; u < 8; u++) {
+                        const int t = lane + 32 * u;
+                        const bool on = t < nr && bit_test(cb, t);
+                        kq[u] = on ? dkey[(size_t)t * KD + c].c : 0xffffffffu;
+                        xq[u] = on ? DV((size_t)t * KD + c) : 0.0;
+                    }
                     #pragma unroll
-                    for (int u = 0; u < 8; u++) { const int t = lane + 32 * u; if (t < KD) stash[t] = kq[u]; }
-                }
-                __syncwarp();
-                for (int t = lane; t < nr; t += 32) {
-                    const unsigned kq = stash[t];
-                    if (kq == 0xffffffffu) continue;
-                    const double x = fabs(dv[(size_t)t * KD + c]);
-                    if (x == 0.0 || x < tol) continue;
-                    const u64 mc = (u64)((nz1 - 1) * (i64)(d.rnz[t] - 1));
-                    const u64 key = (mc << 32) | (u64)kq;       /* ties: first in storage order, markowitz.rs:105 */
-                    if (key < best) { best = key; bt = t; }
+                    for (int u = 0; u < 8; u++) {
+                        const int t = lane + 32 * u;
+                        if (t < KD) stash[t] = kq[u];
+                        if (kq[u] == 0xffffffffu) continue;
+                        const double x = fabs(xq[u]);
+                        if (x == 0.0 || x < tol) continue;
+                        const u64 mc = (u64)((nz1 - 1) * (i64)(d.rnz[t] - 1));
+                        const u64 key = (mc << 32) | (u64)kq[u];       /* ties: first in storage order, markowitz.rs:105 */
+                        if (key < best) { best = key; bt = t; }
+                    }
                 }
             } else {
                 for (int t = lane; t < nr; t += 32) {
                     if (!bit_test(cb, t)) continue;
                     const size_t off = (size_t)t * KD + c;
-                    const double x = fabs(dv[off]);
+                    const double x = fabs(DV(off));
                     if (x == 0.0 || x < tol) continue;
                     const u64 mc = (u64)((nz1 - 1) * (i64)(d.rnz[t] - 1));
                     const u64 key = (mc << 32) | (u64)dkey[off].c;
@@ -714,6 +833,7 @@ template <int NT> __device__ __noinline__ void dense_restage(Shm &S) {
     const int nrb = S.nrs, ncb = S.ncs;
     BLU_DYN_SMEM(dyn_);
     DenseSm o, n;
+    dense_ring_retire<NT>(S);
     dense_view(o, dyn_, KDb, KWb);      /* the two layouts overlap: everything of the old one goes through registers */
     dense_view(n, dyn_, KDs, KWs);
     /* a. per-slot state of the old layout */
@@ -772,7 +892,7 @@ template <int NT> __device__ __noinline__ void dense_restage(Shm &S) {
             double v = 0.0; unsigned key = 0xffffffffu;
             if (a < nr2 && c2 < nc2 && bit_test(n.rb_s + a * KWs, c2)) {
                 const size_t off = (size_t)n.tmps[a] * KDb + n.tmpr[c2];
-                v = dvb[off]; key = kb[off];
+                v = ld_l2(dvb + off); key = kb[off];
             }
             n.dv_s[q] = v; ks[q] = key;
         }
