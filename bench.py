@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--nmat", type=int, default=4096, help="bases of the batch (strong scaling: in all; weak: per GPU)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--dense-k", type=int, default=-1, help="dense-tail order (library default if < 0)")
+    ap.add_argument("--dense-k-big", type=int, default=-1, help="order of the HBM/L2 stage in front of the shared-memory dense tail (library default if < 0, 0 = none)")
     ap.add_argument("--threads-per-basis", type=int, default=0)
     ap.add_argument("--ref-per-core", type=int, default=16, help="bases per host core in one reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -232,6 +233,8 @@ def main():
         b.threads_per_basis = args.threads_per_basis
     if args.dense_k >= 0:
         b.dense_k = args.dense_k
+    if args.dense_k_big >= 0:
+        b.dense_k_big = args.dense_k_big
     stream = torch.cuda.Stream()
     b.set_stream(stream.cuda_stream)
 
@@ -311,21 +314,33 @@ def main():
         bytes_f, bytes_h, bytes_s = algorithmic_bytes(b, nmat, M)
         peak, peak_src = peaks()
         split = float(np.mean(tail_ms)) > 0.0
-        # the dominant kernel: the head launch of the split factorization (singletons, bump set-up and the
-        # sparse part of the elimination); not split: the one k_factorize launch with everything in it
-        dom_ms = float(np.mean(head_ms)) if split else float(np.mean(fact_ms))
-        dom_bytes = bytes_h if split else bytes_f
+        # the dominant kernel: the longer of the two big launches of the split factorization -- HEAD (singletons, bump
+        # set-up and the sparse part of the elimination) or TAIL (the dense tail: first stage in HBM/L2, second in
+        # shared memory, and the last sparse pivots); not split: the one k_factorize launch with everything in it
+        hm, tm = float(np.mean(head_ms)), float(np.mean(tail_ms))
+        build_b = bytes_f - sum(b.info(k, "elim_bytes") for k in range(nmat)) - (bytes_h - sum(b.info(k, "elim_bytes_head") for k in range(nmat)))
+        bytes_t = bytes_f - bytes_h - build_b          # the tail's share of the elimination (device counter elim_bytes)
+        kinds = {"head": ("mode HEAD (singletons + setup_bump + sparse elimination)", hm, bytes_h),
+                 "tail": ("mode TAIL (dense tail: HBM/L2 stage, then shared memory)", tm, bytes_t)}
+        dom = "head" if hm >= tm else "tail"
+        dom_ms = kinds[dom][1] if split else float(np.mean(fact_ms))
+        dom_bytes = kinds[dom][2] if split else bytes_f
+        other = "tail" if dom == "head" else "head"
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_factorize<%d> %s" % (int(b.get_param("threads_per_basis")), "mode HEAD (singletons + setup_bump + sparse elimination)" if split else "(whole factorization)"),
+        nt_dom = int(b.get_param("threads_per_basis")) if (dom == "head" or not split) else int(b.get_param("tail_threads"))
+        roofline = {"bound": "hbm", "kernel": "k_factorize<%d> %s" % (nt_dom, kinds[dom][0] if split else "(whole factorization)"),
                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
                     "whole_factorization": {"algorithmic_bytes": bytes_f, "ms": float(np.mean(fact_ms)),
-                                            "achieved_GBps": bytes_f / (float(np.mean(fact_ms)) * 1e-3) / 1e9},
-                    "other_kernels_ms_per_step": {"k_factorize mode TAIL (dense tail in shared memory, one CTA per SM)": float(np.mean(tail_ms)),
+                                            "achieved_GBps": bytes_f / (float(np.mean(fact_ms)) * 1e-3) / 1e9,
+                                            "frac": bytes_f / (float(np.mean(fact_ms)) * 1e-3) / 1e9 / peak},
+                    "other_kernels_ms_per_step": {"k_factorize %s" % kinds[other][0]: kinds[other][1],
                                                   "k_factorize mode BUILD (build_factors)": float(np.mean(build_ms)),
                                                   "k_factor_norms (condest x2 + residual_test, factorize.rs:121-147)": float(np.mean(norms_ms)),
-                                                  "k_solve_dense": float(b.last_kernel_ms(1))}}
+                                                  "k_solve_dense": float(b.last_kernel_ms(1))},
+                    "other_kernels_algorithmic_bytes": {"k_factorize %s" % kinds[other][0]: kinds[other][2], "k_factorize mode BUILD": build_b}}
+        roofline["dominant"] = dom
         tf = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tf):
             try:
@@ -361,7 +376,7 @@ def main():
                 "config": {"workload": "configs[1]: 4096 x (2000x2000 simplex-style basis, ~6 nnz/col) factorize+solve_dense",
                            "m": M, "bases": total, "bases_per_gpu": nmat, "nnz_per_basis": float(len(bi)) / nmat,
                            "sharding": f"bases by index (shard_range), {world} rank(s), no collective",
-                           "dense_k": int(b.get_param("dense_k")), "tail_threads": int(b.get_param("tail_threads")),
+                           "dense_k": int(b.get_param("dense_k")), "dense_k_big": int(b.get_param("dense_k_big")), "tail_threads": int(b.get_param("tail_threads")),
                            "store_entries_per_basis": {"l_mem": int(b.get_param("l_mem")), "u_mem": int(b.get_param("u_mem")), "w_mem": int(b.get_param("w_mem"))},
                            "l2": "inputs exceed L2: %.0f MB of B + rhs are re-read every step (L2 126 MB)" % ((pbi.nbytes + pbx.nbytes + pbb.nbytes + pbe.nbytes + prhs.nbytes) / 1e6),
                            "threads_per_basis": int(b.get_param("threads_per_basis")), "reallocations_in_warmup": nrealloc, "reallocations_in_timed_steps": nrealloc_after - nrealloc,

@@ -151,6 +151,7 @@ struct Shm {
     /* first stage of a two-stage tail: per-warp ring of row buffers filled and drained by bulk copies (dense_step) */
     unsigned ring_phase[32];  /* per warp: current phase bit of each of its buffers */
     int ring_nbuf;            /* buffers per warp in this stage (0: no ring) */
+    i64 dstamp_base;          /* dense tail: stamp - dstamp_base is the 23-bit stamp of the 32-bit search keys (skey32) */
     int cand_done;            /* candidate columns evaluated so far (the warp that finishes last makes the choice) */
     int dgeneral;             /* the chosen pivot is a general dense step (pivot_any / pivot_small) */
 };
@@ -211,6 +212,14 @@ __device__ __forceinline__ double warp_mind(double v) {
     for (int d = 16; d > 0; d >>= 1) { double t = __shfl_xor_sync(FULLMASK, v, d); v = t < v ? t : v; }
     return v;
 }
+#ifndef BLU_EMU
+__device__ __forceinline__ unsigned warp_min_u32(unsigned v) { return __reduce_min_sync(FULLMASK, v); }   /* REDUX */
+#else
+static inline unsigned warp_min_u32(unsigned v) {
+    for (int d = 16; d > 0; d >>= 1) { unsigned t = __shfl_xor_sync(FULLMASK, v, d); v = t < v ? t : v; }
+    return v;
+}
+#endif
 __device__ __forceinline__ u64 warp_min64(u64 v) {
     #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { u64 t = __shfl_xor_sync(FULLMASK, v, d); v = t < v ? t : v; }

@@ -44,6 +44,8 @@
  * stores of the update loop). */
 struct DenseSm {
     u64 *skeyc;            /* Markowitz key of column slot c (count<<40 | stamp), KEY_INF when gone */
+    unsigned *skey32;      /* the same order in 32 bits for the candidate scan: count<<23 | (stamp - dstamp_base), or the rank of the
+                            * stamp among the columns present at dense_enter; 0xffffffff when gone or hidden (KEY_PARK) */
     u64 *scm;              /* colmax of column slot c as the bits of a non-negative double */
     double *cvalp;         /* values of the pivot column in its storage order */
     int *drow, *dcol;      /* slot -> row / column index */
@@ -68,6 +70,7 @@ __device__ __forceinline__ void dense_view(DenseSm &d, unsigned char *dyn, int K
     d.keyr = (unsigned *)p4; p4 += KD;
     d.rowk = (BluKey2 *)p4; p4 += KD;
     d.candk = (unsigned *)p4; p4 += DENSE_STASH * KD;
+    d.skey32 = (unsigned *)p4; p4 += KD;
     d.cmask = (unsigned *)p4; p4 += KW;
     d.rmask = (unsigned *)p4; p4 += KW;
     d.rfull = (unsigned *)p4; p4 += KW;
@@ -189,6 +192,22 @@ template <int NT, int RES> __device__ __noinline__ void dense_enter(Shm &S) {
         S.dense_entries++;
         S.n_kind[6]++;
     }
+    bsync<NT>();
+    /* 32-bit search keys: the stamps of the columns present now are replaced by their ranks (< nc); the stamps handed
+     * out from here on count up from nc */
+    for (int c = tid; c < KD; c += NT) {
+        const u64 key = d.skeyc[c];
+        unsigned k32 = 0xffffffffu;
+        if (key < KEY_PARK) {
+            const u64 smask = ((u64)1 << STAMP_BITS) - 1;
+            const u64 st = key & smask;
+            unsigned r = 0;
+            for (int c2 = 0; c2 < nc; c2++) { const u64 k2 = d.skeyc[c2]; r += k2 != KEY_INF && (k2 & smask) < st; }
+            k32 = ((unsigned)key_cnt(key) << 23) | r;
+        }
+        d.skey32[c] = k32;
+    }
+    if (tid == 0) S.dstamp_base = S.cstamp - nc;
     bsync<NT>();
     if (RES == 2 && S.ring_nbuf) {
         u64 *bars = dense_ring_bars(dyn_, KD);
@@ -338,56 +357,66 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
         const unsigned *stash = d.candk + S.dpcand * KD;      /* the column's keys, 0xffffffff where there is no entry */
         const uint4 *s4 = (const uint4 *)stash;
         const int n4 = (nr + 3) >> 2;
-        for (int t = tid; t < nr; t += NT) {
-            const unsigned my = stash[t];
-            if (my == 0xffffffffu) continue;
-            const unsigned pk = stash[tp];
-            int r = 0, wc = 0;
-            for (int f = 0; f < n4; f++) {
-                const uint4 q = s4[f];
-                r += (q.x < my) + (q.y < my) + (q.z < my) + (q.w < my);
-                wc += (q.x < pk) + (q.y < pk) + (q.z < pk) + (q.w < pk);
+        const unsigned pk = stash[tp];
+        for (int t0 = wid * 32; t0 < nr; t0 += NT) {      /* (whole warps: the rank of the pivot is a warp's work) */
+            const int t = t0 + lane;
+            const unsigned my = t < nr ? stash[t] : 0xffffffffu;
+            int r = 0;
+            if (my != 0xffffffffu)
+                for (int f = 0; f < n4; f++) {
+                    const uint4 q = s4[f];
+                    r += (q.x < my) + (q.y < my) + (q.z < my) + (q.w < my);
+                }
+            /* the first entry and the pivot exchange places: only the first entry needs the pivot's rank */
+            int wc = 0;
+            if (__ballot_sync(FULLMASK, my != 0xffffffffu && r == 0 && t != tp)) {
+                for (int f = lane; f < 4 * n4; f += 32) wc += stash[f] < pk;
+                wc = warp_sum(wc);
             }
-            const int p = t == tp ? 0 : (r == 0 ? wc : r);
-            d.clist[p] = (unsigned short)t;
-            d.cvalp[p] = DV((size_t)t * KD + cp);
+            if (my != 0xffffffffu) {
+                const int p = t == tp ? 0 : (r == 0 ? wc : r);
+                d.clist[p] = (unsigned short)t;
+                d.cvalp[p] = DV((size_t)t * KD + cp);
+            }
         }
     }
     mbar_wait(&S.mbar, phase);
     {
         const uint4 *s4 = (const uint4 *)rowk32;
         const int n4 = (nc + 3) >> 2;
-        for (int it = tid; it < KD + nc; it += NT) {
-            if (it < KD) continue;      /* (the threads that ranked the column are busy) */
-            const int c = it - KD;
-            const unsigned my = rowk32[c];
-            if (!bit_test(rbp, c)) {
+        const unsigned pk = rowk32[cp];
+        for (int it0 = wid * 32; it0 < KD + nc; it0 += NT) {
+            if (it0 < KD) continue;      /* (the warps that ranked the column are busy) */
+            const int c = it0 - KD + lane;
+            const bool on = c < nc && bit_test(rbp, c);
+            const unsigned my = c < nc ? rowk32[c] : 0xffffffffu;
 #ifdef BLU_EMU
-                BLU_CHECK(S, (my >> 16) == 0xffffu);
+            if (c < nc) BLU_CHECK(S, ((my >> 16) == 0xffffu) == !on);
 #endif
-                continue;
+            int r = 0;
+            if (on)
+                for (int f = 0; f < n4; f++) {
+                    const uint4 q = s4[f];
+                    r += (q.x < my) + (q.y < my) + (q.z < my) + (q.w < my);
+                }
+            int wr = 0;
+            if (__ballot_sync(FULLMASK, on && r == 0 && c != cp)) {
+                for (int f = lane; f < 4 * n4; f += 32) wr += rowk32[f] < pk;
+                wr = warp_sum(wr);
             }
-#ifdef BLU_EMU
-            BLU_CHECK(S, (my >> 16) != 0xffffu);
-#endif
-            const unsigned pk = rowk32[cp];
-            int r = 0, wr = 0;
-            for (int f = 0; f < n4; f++) {
-                const uint4 q = s4[f];
-                r += (q.x < my) + (q.y < my) + (q.z < my) + (q.w < my);
-                wr += (q.x < pk) + (q.y < pk) + (q.z < pk) + (q.w < pk);
+            if (on) {
+                const int p = c == cp ? 0 : (r == 0 ? wr : r);
+                d.rlist[p] = (unsigned short)c;
+                d.posr[c] = (unsigned short)p;
+                if (c != cp) { d.scm[c] = 0; d.kminp[c] = 0xffffffffu; }
+                if (SMALL) d.sdrop[p] = 0;
             }
-            const int p = c == cp ? 0 : (r == 0 ? wr : r);
-            d.rlist[p] = (unsigned short)c;
-            d.posr[c] = (unsigned short)p;
-            if (c != cp) { d.scm[c] = 0; d.kminp[c] = 0xffffffffu; }
-            if (SMALL) d.sdrop[p] = 0;
         }
     }
     bsync<NT>();
     const double pivot = d.cvalp[0];
     const int ubase = S.uput, lbase = S.lput;
-    const i64 cbase = S.cstamp, rbase = S.rstamp;
+    const i64 cbase = S.cstamp, rbase = S.rstamp, sbase = S.dstamp_base;
     const unsigned ekey = S.epoch << 8;
     if (tid == 0) { const i64 now = clock64(); S.t_phase[14] += now - tq; tq = now; }
 
@@ -598,7 +627,11 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
         d.cnz[c] = (unsigned short)cnt;
         const double cmx = __longlong_as_double((long long)d.scm[c]);
         M.colpiv[j] = cmx;
-        d.skeyc[c] = mkckey(cnt, cbase + kk, cmx, abstol);
+        {
+            const u64 k64 = mkckey(cnt, cbase + kk, cmx, abstol);
+            d.skeyc[c] = k64;
+            d.skey32[c] = k64 >= KEY_PARK ? 0xffffffffu : ((unsigned)cnt << 23) | (unsigned)(cbase + kk - sbase);
+        }
         {   /* pivot.rs:261-262: the first entry outside the pivot column moves to the place of the pivot-row entry */
             const unsigned pk = d.kminp[c], kpr = rowk32[c] & 0xffffu;
             if ((pk >> 8) < kpr) dkey[(size_t)(pk & 0xffu) * KD + c].c = (unsigned short)kpr;
@@ -625,7 +658,7 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
     acc = warp_sumd(acc);      /* (sums of small integers: exact in any order) */
     if (lane == 0 && acc != 0.0) atomicAdd(&S.elim_bytes, acc);
     for (int w = NT - 1 - tid; w < KW; w += NT) { cbm[cp * KW + w] = 0; rbm[tp * KW + w] = 0; }
-    if (tid == NT - 1) { d.skeyc[cp] = KEY_INF; d.cnz[cp] = 0; d.rnz[tp] = 0; }
+    if (tid == NT - 1) { d.skeyc[cp] = KEY_INF; d.skey32[cp] = 0xffffffffu; d.cnz[cp] = 0; d.rnz[tp] = 0; }
     bsync<NT>();
 
     /* the finisher warp closes the step while warp 0 already looks for the next candidates */
@@ -665,13 +698,13 @@ template <int NT, int RES> __device__ __noinline__ int dense_run(Shm &S) {
         /* A. the first `maxsearch` live columns in ascending (count, stamp) order: one warp, no block barriers */
         if (wid == 0) {
             int ncand = 0;
-            u64 prev = 0; int have_prev = 0;
+            unsigned prev = 0; int have_prev = 0;
             while (ncand < maxsearch) {
-                u64 k0 = KEY_INF, k1 = KEY_INF, k2 = KEY_INF;
+                unsigned k0 = 0xffffffffu, k1 = 0xffffffffu, k2 = 0xffffffffu;
                 int j0 = -1, j1 = -1, j2 = -1;
                 for (int c = lane; c < nc; c += 32) {
-                    const u64 kq = d.skeyc[c];
-                    if (kq >= KEY_PARK || (have_prev && kq <= prev)) continue;
+                    const unsigned kq = d.skey32[c];
+                    if (kq == 0xffffffffu || (have_prev && kq <= prev)) continue;
                     if (kq < k2) {
                         if (kq < k1) {
                             k2 = k1; j2 = j1;
@@ -682,11 +715,11 @@ template <int NT, int RES> __device__ __noinline__ int dense_run(Shm &S) {
                 }
                 int got = 0;
                 for (int r = 0; r < 3 && ncand < maxsearch; r++) {
-                    const u64 best = warp_min64(k0);
-                    if (best == KEY_INF) break;
+                    const unsigned best = warp_min_u32(k0);
+                    if (best == 0xffffffffu) break;
                     if (k0 == best) {
                         S.cand_col[ncand] = j0;
-                        k0 = k1; j0 = j1; k1 = k2; j1 = j2; k2 = KEY_INF; j2 = -1;
+                        k0 = k1; j0 = j1; k1 = k2; j1 = j2; k2 = 0xffffffffu; j2 = -1;
                     }
                     prev = best; have_prev = 1;
                     ncand++; got++;
@@ -704,7 +737,7 @@ template <int NT, int RES> __device__ __noinline__ int dense_run(Shm &S) {
             if (tid == 0) {
                 const int c0 = S.cand_col[0], pc = d.dcol[c0];
                 S.dpc = c0; S.pivot_col = pc; S.pivot_row = -1;
-                M.ckey[pc] = KEY_INF; d.skeyc[c0] = KEY_INF; S.ndead++; S.rankdef++;
+                M.ckey[pc] = KEY_INF; d.skeyc[c0] = KEY_INF; d.skey32[c0] = 0xffffffffu; S.ndead++; S.rankdef++;
                 S.t_phase[13] += clock64() - t0;
             }
             rankdef++;
@@ -843,15 +876,16 @@ template <int NT> __device__ __noinline__ void dense_restage(Shm &S) {
     const int r_drow = ra ? o.drow[t] : 0, r_rnz = ra ? (int)o.rnz[t] : 0;
     const int c_dcol = ca ? o.dcol[t] : 0, c_cnz = ca ? (int)o.cnz[t] : 0;
     const u64 c_key = ca ? o.skeyc[t] : KEY_INF, c_cm = ca ? o.scm[t] : 0;
+    const unsigned c_k32 = ca ? o.skey32[t] : 0xffffffffu;
     int nr2, nc2;
     const int rpos = block_excl_scan<NT>(ra, &nr2, S.iscr);
     const int cpos = block_excl_scan<NT>(ca, &nc2, S.iscr);
     if (nr2 > KDs || nc2 > KDs) { if (tid == 0) BLU_CHECK(S, 0); bsync<NT>(); return; }
     /* b. per-slot state of the new layout; tmps / tmpr map the new slots to the old ones */
-    for (int q = tid; q < KDs; q += NT) { n.skeyc[q] = KEY_INF; n.scm[q] = 0; n.cnz[q] = 0; n.rnz[q] = 0; }
+    for (int q = tid; q < KDs; q += NT) { n.skeyc[q] = KEY_INF; n.skey32[q] = 0xffffffffu; n.scm[q] = 0; n.cnz[q] = 0; n.rnz[q] = 0; }
     bsync<NT>();
     if (ra) { n.drow[rpos] = r_drow; n.rnz[rpos] = (unsigned short)r_rnz; n.tmps[rpos] = (unsigned short)t; }
-    if (ca) { n.dcol[cpos] = c_dcol; n.cnz[cpos] = (unsigned short)c_cnz; n.skeyc[cpos] = c_key; n.scm[cpos] = c_cm; n.tmpr[cpos] = (unsigned short)t; }
+    if (ca) { n.dcol[cpos] = c_dcol; n.cnz[cpos] = (unsigned short)c_cnz; n.skeyc[cpos] = c_key; n.skey32[cpos] = c_k32; n.scm[cpos] = c_cm; n.tmpr[cpos] = (unsigned short)t; }
     bsync<NT>();
     /* c. bitmaps: the old ones sit behind the old per-slot arrays, clear of the new per-slot arrays but not of the
      * new bitmaps, so the new words wait in registers (at most 8 per thread: NT >= kd_big) until all are computed */

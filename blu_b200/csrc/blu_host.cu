@@ -262,7 +262,8 @@ static int create_common(blu_b200 **out, int64_t nmat, int64_t m, int64_t bnz_ca
     if (st == BLU_OK) st = alloc_stores(o);
     if (st == BLU_OK) { d.slot_store = o->d_slot; st = clear_overrides(o); }
     if (st == BLU_OK) {
-        int kd = o->kd_smem_max, kb = single ? 0 : BLU_DENSE_K_MAX;
+        /* two-stage tail for batches: measured on configs[1] (profiles/r2u_sweep_two_stage.txt) 224 and 256 are within 1 % of each other and 8 % ahead of one stage */
+        int kd = o->kd_smem_max, kb = single ? 0 : 256;
         if (const char *e = getenv("BLU_B200_DENSE_K")) kd = atoi(e);      /* tuning knob, same as BLU_P_DENSE_K */
         if (const char *e = getenv("BLU_B200_DENSE_K_BIG")) kb = atoi(e);  /* tuning knob, same as BLU_P_DENSE_K_BIG */
         o->want_kbig = kb;
