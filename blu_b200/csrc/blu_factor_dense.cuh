@@ -48,6 +48,7 @@ struct DenseSm {
                             * stamp among the columns present at dense_enter; 0xffffffff when gone or hidden (KEY_PARK) */
     u64 *scm;              /* colmax of column slot c as the bits of a non-negative double */
     double *cvalp;         /* values of the pivot column in its storage order */
+    double *arow;          /* pivot row divided by the pivot, by column slot (pivot.rs:285: the multiplier of each column) */
     int *drow, *dcol;      /* slot -> row / column index */
     unsigned *keyc, *keyr; /* sort keys of the pivot column / row */
     u64 *sdrop;            /* pivot_small: cancellation mask per column of the pivot row (overlays keyc|keyr) */
@@ -63,6 +64,7 @@ __device__ __forceinline__ void dense_view(DenseSm &d, unsigned char *dyn, int K
     d.skeyc = p8; p8 += KD;
     d.scm = p8; p8 += KD;
     d.cvalp = (double *)p8; p8 += KD;
+    d.arow = (double *)p8; p8 += KD;
     int *p4 = (int *)p8;
     d.drow = p4; p4 += KD;
     d.dcol = p4; p4 += KD;
@@ -389,6 +391,8 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
             if (it0 < KD) continue;      /* (the warps that ranked the column are busy) */
             const int c = it0 - KD + lane;
             const bool on = c < nc && bit_test(rbp, c);
+            /* the multiplier of the column, once per step (the loads are in flight during the ranking) */
+            const double xrow = on ? DV((size_t)tp * KD + c) : 0.0, xpiv = DV((size_t)tp * KD + cp);
             const unsigned my = c < nc ? rowk32[c] : 0xffffffffu;
 #ifdef BLU_EMU
             if (c < nc) BLU_CHECK(S, ((my >> 16) == 0xffffu) == !on);
@@ -408,7 +412,7 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
                 const int p = c == cp ? 0 : (r == 0 ? wr : r);
                 d.rlist[p] = (unsigned short)c;
                 d.posr[c] = (unsigned short)p;
-                if (c != cp) { d.scm[c] = 0; d.kminp[c] = 0xffffffffu; }
+                if (c != cp) { d.scm[c] = 0; d.kminp[c] = 0xffffffffu; d.arow[c] = __ddiv_rn(xrow, xpiv); }
                 if (SMALL) d.sdrop[p] = 0;
             }
         }
@@ -484,7 +488,7 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
                 const int c = cw * 32 + lane;
                 if ((d.rmask[cw] >> lane) & 1u) {
                     inRm |= 1u << cw;
-                    a[cw] = __ddiv_rn(DV((size_t)tp * KD + c), pivot);
+                    a[cw] = d.arow[c];
                     rkv[cw] = ekey + (unsigned)d.posr[c];
                 }
                 if (c == cp) pw = cw;
@@ -505,8 +509,7 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
             mbar_wait(&mybar[b], (ph >> b) & 1u);
             ph ^= 1u << b;
             #pragma unroll
-            for (int cw = 0; cw < 8; cw++) {
-                if (cw >= KW) continue;
+            for (int cw = 0; cw < 8; cw++) {      /* (no bit of inRm beyond the last word) */
                 const int c = cw * 32 + lane;
                 if ((inRm >> cw) & 1u) {
                     const double x = __dsub_rn(buf[c], __dmul_rn(a[cw], cv));
@@ -546,7 +549,7 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
             const bool inR = (rm >> lane) & 1u;
             const bool isP = c == cp;
             double a = 0.0; unsigned rkv = 0; int kk = 0;
-            if (inR) { kk = d.posr[c]; a = __ddiv_rn(DV((size_t)tp * KD + c), pivot); rkv = ekey + (unsigned)kk; }
+            if (inR) { kk = d.posr[c]; a = d.arow[c]; rkv = ekey + (unsigned)kk; }
             double cmx = 0.0;
             u64 mydrop = 0;
             const int pend = (rs + 1) * chunk < cnz1 ? (rs + 1) * chunk : cnz1;

@@ -150,7 +150,7 @@ BLU_HD size_t blu_factor_smem_bytes(int cap, int nw, int m) {
 }
 /* per-step arrays of the dense tail (always in shared memory) */
 BLU_HD size_t blu_dense_smem_bytes(int kd) {
-    return (((size_t)kd * (3 * 8 + 4 * 4 + 7 * 2 + DENSE_STASH * 4 + 4 + 4) + (size_t)(kd / 32) * 3 * 4) + 15) & ~(size_t)15;
+    return (((size_t)kd * (4 * 8 + 4 * 4 + 7 * 2 + DENSE_STASH * 4 + 4 + 4) + (size_t)(kd / 32) * 3 * 4) + 15) & ~(size_t)15;
 }
 /* with the presence bitmaps and the values in shared memory as well */
 BLU_HD size_t blu_dense_smem_bytes_resident(int kd) {
