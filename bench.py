@@ -347,11 +347,11 @@ def main():
                 t = json.load(open(tf))
                 # dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch of that kernel (ncu --set
                 # full), per basis, scaled to this launch's batch -- quoted only if taken with these very sources
-                if t.get("kernel_source_hash") == kernel_source_hash():
+                if t.get("kernel_source_hash") == kernel_source_hash() and t.get("dominant", "head") == (dom if split else "whole"):
                     roofline["traffic"] = t["dram_bytes_per_basis"] * nmat
                     roofline["traffic_source"] = t["source"]
                 else:
-                    roofline["traffic_source"] = "none: profiles/traffic.json was captured with other kernel sources (%s, now %s)" % (t.get("kernel_source_hash"), kernel_source_hash())
+                    roofline["traffic_source"] = "none: profiles/traffic.json was captured with other kernel sources or for another kernel (%s %s, now %s %s)" % (t.get("kernel_source_hash"), t.get("dominant", "head"), kernel_source_hash(), dom)
             except Exception:
                 pass
         cpu = None
