@@ -38,6 +38,9 @@
 #ifndef BLU_FACTOR_DENSE_CUH
 #define BLU_FACTOR_DENSE_CUH
 /* included by blu_factor_bump.cuh after its helpers (finish_step, warp_squeeze) */
+#ifndef RING_LAG
+#define RING_LAG 2           /* rows between a buffer's store and its refill (stage-1 row ring) */
+#endif
 
 /* Pointers into the dynamic shared memory, computed locally from its base in every function so that the
  * compiler knows their address space (LDS/STS instead of generic loads, and no aliasing with the global
@@ -187,7 +190,7 @@ template <int NT, int RES> __device__ __noinline__ void dense_enter(Shm &S) {
             int nb = have > base ? (int)((have - base) / level) : 0;
             if (nb > RING_BARS / NW) nb = RING_BARS / NW;
             if (nb > 8) nb = 8;
-            S.ring_nbuf = nb >= 2 ? nb : 0;
+            S.ring_nbuf = nb > RING_LAG ? nb : 0;
         }
         S.dense = 1; S.nrs = nr; S.ncs = nc;
         S.epoch = 1;          /* the position keys handed out here are epoch 0 */
@@ -525,10 +528,10 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
             if (lane == 0) {
                 bulk_copy_s2g(dv + (size_t)t * KD, buf, rowbytes);
                 bulk_commit();
-                if (i >= 1 && i - 1 + NB < nmine) {      /* the buffer of the previous row is free once its store has read it */
-                    bulk_wait_read<1>();
-                    const int bp = (i - 1) % NB;
-                    bulk_copy_g2s(mybuf + (size_t)bp * KD, dv + (size_t)d.clist[1 + wid + (i - 1 + NB) * NW] * KD, rowbytes, &mybar[bp]);
+                if (i >= RING_LAG && i - RING_LAG + NB < nmine) {      /* a buffer is free once its store has read it: the store of RING_LAG rows ago has had time to */
+                    bulk_wait_read<RING_LAG>();
+                    const int bp = (i - RING_LAG) % NB;
+                    bulk_copy_g2s(mybuf + (size_t)bp * KD, dv + (size_t)d.clist[1 + wid + (i - RING_LAG + NB) * NW] * KD, rowbytes, &mybar[bp]);
                 }
             }
         }
