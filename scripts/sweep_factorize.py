@@ -29,6 +29,8 @@ for nt, kd, tail, kbig in [(a, b_, c, e) for a in nts for b_ in kds for c in (ta
         b.tail_threads = tail
         if kbig >= 0:
             b.dense_k_big = kbig
+        if os.environ.get("SWEEP_TREE_MIN"):
+            b.tree_min = int(os.environ["SWEEP_TREE_MIN"])
         if os.environ.get("SWEEP_W_MEM"):
             b.w_mem = int(os.environ["SWEEP_W_MEM"])
         elif not os.environ.get("SWEEP_DEFAULT_MEM"):
