@@ -354,6 +354,31 @@ def test_emu_two_stage_tail(emu, kd, kbig, tail, m):
         assert np.array_equal(x[k], xo)
 
 
+def test_emu_two_stage_tail_one_launch(emu):
+    """The two-stage tail inside ONE launch (BLU_MODE_WHOLE: a batch below split_min): the CTA that ran the sparse
+    head enters stage 1, restages and finishes; same factors as the oracle."""
+    from parity import STATS
+    nmat, m = 2, 220
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 40, 5.0, 9350, 9850)
+    b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()), lib=emu)
+    b.dense_k = 64; b.dense_k_big = 128; b.split_min = 1000; b.threads_per_basis = 128
+    l0 = b.launch_count()
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all()
+    assert b.launch_count() - l0 == 2       # one k_factorize + the condest/residual kernel
+    for k in range(nmat):
+        cp, ri, v = gen.basis(9350 + k, m, 40, 5.0)
+        o = oracle_for(m, len(v), 400)
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        _, fo = o.get_factors()
+        _, fg = b.get_factors(k)
+        for key in fo:
+            assert np.array_equal(fo[key], fg[key]), (k, key)
+        for name in STATS:
+            assert o.info(name) == b.info(k, name), (k, name)
+        assert b.info(k, "n_kind6") >= 2, "both stages ran"
+
+
 def test_emu_dense_tail_structures(emu):
     """Exact cancellation, rank deficiency and columns that fall below abstol inside the dense tail
     (the paths that leave it early: dense_exit + pivot.rs:96-106 on the line file)."""

@@ -570,6 +570,31 @@ def test_split_batch_parity(kd, tail, nt, kbig):
         assert np.array_equal(x[k], xo)
 
 
+def test_two_stage_tail_one_launch():
+    """The two-stage dense tail inside one launch (a batch below split_min runs BLU_MODE_WHOLE with 256-thread CTAs):
+    stage 1 at order 256 in HBM/L2, dense_restage, stage 2 at order 160 in shared memory."""
+    from parity import STATS
+    nmat, m = 6, 700
+    bb, be, bi, bx, rhs = gen.batch(nmat, m, 200, 5.0, 9250, 9750)
+    b = BLUBatch(nmat, m, int((be - bb).reshape(nmat, m).sum(1).max()))
+    b.dense_k = 160; b.dense_k_big = 256; b.split_min = 100; b.threads_per_basis = 256
+    l0 = b.launch_count()
+    st, status = b.factorize(bb, be, bi, bx)
+    assert st == 0 and (status == 0).all()
+    assert b.launch_count() - l0 == 2
+    for k in range(nmat):
+        cp, ri, v = gen.basis(9250 + k, m, 200, 5.0)
+        o = oracle_for(m, len(v))
+        assert o.factorize(cp[:-1], cp[1:], ri, v) == 0
+        _, fo = o.get_factors()
+        _, fg = b.get_factors(k)
+        for key in fo:
+            assert np.array_equal(fo[key], fg[key]), (k, key)
+        for name in STATS:
+            assert o.info(name) == b.info(k, name), (k, name)
+        assert b.info(k, "n_kind6") >= 2, "both stages ran"
+
+
 def test_dense_tail_structures():
     """tests/parity.py structures (exact cancellation, rank deficiency, columns below abstol) with a small
     dense-tail order so that the tail is entered, left early (dense_exit) and re-entered."""
