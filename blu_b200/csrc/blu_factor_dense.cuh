@@ -512,16 +512,20 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
             mbar_wait(&mybar[b], (ph >> b) & 1u);
             ph ^= 1u << b;
             #pragma unroll
-            for (int cw = 0; cw < 8; cw++) {      /* (no bit of inRm beyond the last word) */
+            for (int cw = 0; cw < 8; cw++) {      /* (no bit of inRm beyond the last word; straight-line code: selects and predicated stores, no divergent branches) */
+                if (cw * 32 >= KD) continue;
                 const int c = cw * 32 + lane;
-                if ((inRm >> cw) & 1u) {
-                    const double x = __dsub_rn(buf[c], __dmul_rn(a[cw], cv));
-                    buf[c] = x;
-                    BluKey2 kv; kv.c = (unsigned short)(ekey + (unsigned)p); kv.r = (unsigned short)rkv[cw];
-                    dkey[(size_t)t * KD + c] = kv;
-                    const double ax = fabs(x);
-                    if (ax > cmx[cw]) cmx[cw] = ax;
-                } else if (cw == pw) dkey[(size_t)t * KD + c] = gone;      /* the pivot column leaves the active submatrix */
+                const bool in = (inRm >> cw) & 1u;
+                const double x0 = buf[c];
+                const double x1 = __dsub_rn(x0, __dmul_rn(a[cw], cv));
+                const double x = in ? x1 : x0;
+                if (in) buf[c] = x;
+                BluKey2 kv;
+                kv.c = in ? (unsigned short)(ekey + (unsigned)p) : (unsigned short)0xffffu;
+                kv.r = in ? (unsigned short)rkv[cw] : (unsigned short)0xffffu;
+                if (in || cw == pw) dkey[(size_t)t * KD + c] = kv;      /* (cw == pw: the pivot column leaves the active submatrix) */
+                const double ax = in ? fabs(x) : 0.0;
+                cmx[cw] = ax > cmx[cw] ? ax : cmx[cw];
             }
             fence_async_smem();
             __syncwarp();
@@ -571,22 +575,17 @@ template <int NT, int RES, bool SMALL> __device__ __forceinline__ void dense_ste
                     if (tt[u] < 0) continue;       /* uniform: p does not depend on the lane */
                     const int p = p0 + u;
                     const size_t off = (size_t)tt[u] * KD + c;
-                    int keep = 0;
-                    if (inR) {
-                        const double x = __dsub_rn(xv[u], __dmul_rn(a, cv[u]));
-                        const double ax = fabs(x);
-                        keep = SMALL ? ax > droptol : 1;
-                        if (keep) {
-                            dv[off] = x;
-                            BluKey2 kv; kv.c = (unsigned short)(ekey + (unsigned)p); kv.r = (unsigned short)rkv;
-                            dkey[off] = kv;
-                            if (ax > cmx) cmx = ax;
-                        } else {
-                            dv[off] = 0.0;
-                            dkey[off] = gone;
-                            mydrop |= 1ull << (p - 1);
-                        }
-                    } else if (isP) dkey[off] = gone;      /* the pivot column leaves the active submatrix */
+                    /* straight-line code (selects and predicated stores): the lanes of a word differ in inR */
+                    const double x = __dsub_rn(xv[u], __dmul_rn(a, cv[u]));
+                    const double ax = fabs(x);
+                    const int keep = inR && (SMALL ? ax > droptol : 1);
+                    if (inR) dv[off] = keep ? x : 0.0;
+                    BluKey2 kv;
+                    kv.c = keep ? (unsigned short)(ekey + (unsigned)p) : (unsigned short)0xffffu;
+                    kv.r = keep ? (unsigned short)rkv : (unsigned short)0xffffu;
+                    if (inR || isP) dkey[off] = kv;      /* (dropped entries and the pivot column leave the active submatrix) */
+                    cmx = (keep && ax > cmx) ? ax : cmx;
+                    if (SMALL && inR && !keep) mydrop |= 1ull << (p - 1);
                     if (SMALL) {
                         const unsigned km = __ballot_sync(FULLMASK, keep);
                         if (lane == 0) { unsigned *wp = rbm + tt[u] * KW + cw; *wp = (*wp & ~rf) | km; }
