@@ -136,6 +136,21 @@ inline int __all_sync(unsigned m, int pred) {
     return __ballot_sync(m, pred) == full;
 }
 inline unsigned __activemask() { return 0xffffffffu; }
+/* lanes holding the same value (full warps only) */
+template <typename T> inline unsigned __match_any_sync(unsigned, T v) {
+    static_assert(sizeof(T) <= 8, "match of <= 8 bytes");
+    emu::Warp &w = emu::mywarp();
+    unsigned p = w.par & 1;
+    uint64_t raw = 0; memcpy(&raw, &v, sizeof(T));
+    w.slot[p][emu::lane()] = raw;
+    int l = emu::lane();
+    emu::warp_barrier();
+    if (l == 0) w.par++;
+    unsigned m = 0;
+    for (int q = 0; q < 32; q++) if (w.slot[p][q] == raw) m |= 1u << q;
+    emu::warp_barrier();
+    return m;
+}
 
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
