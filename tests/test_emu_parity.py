@@ -573,3 +573,15 @@ def test_emu_factorize_c0ntinue(emu):
     assert st == 0 and rounds >= 1
     assert_factor_parity(g, o, check_stats=False)
     assert g.factorize_c0ntinue(cp[:-1], cp[1:], ri, v, True) == -2      # nothing pending any more
+
+
+def test_emu_batch_hunt_sample():
+    """A few random batches through the split factorization under random dense-tail stage orders, CTA sizes and
+    tunables (scripts/batch_hunt.py --emu): every sampled basis equals the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "batch_hunt.py"), "47000", "6", "--emu"],
+                         capture_output=True, text=True, timeout=900).stdout
+    assert out.strip().splitlines()[-1].startswith("6 batches, 0 failures"), out[-1500:]
+

@@ -714,3 +714,15 @@ def test_device_pointer_entry_points_and_graph():
         assert b.graph_launch() == 0
     _, xg, sg = b.download()
     assert (sg == 0).all() and np.array_equal(xg, x_ref)
+
+
+def test_batch_hunt_sample():
+    """Random batches through the split factorization under random dense-tail stage orders, CTA sizes and tunables
+    (scripts/batch_hunt.py): every sampled basis equals the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "batch_hunt.py"), "48000", "20"],
+                         capture_output=True, text=True, timeout=900).stdout
+    assert out.strip().splitlines()[-1].startswith("20 batches, 0 failures"), out[-1500:]
+
